@@ -1,0 +1,200 @@
+/*
+ * nerfstyle_b200.h -- C ABI of libnerfstyle_b200.so (hand-written sm_100a CUDA).
+ *
+ * Drop-in boundary for the NeRF render/train hot path of hkust-vgd/nerfstyle.  Each entry point
+ * replaces one pybind11 function of the reference's two extensions (and the tiny-cuda-nn calls), with
+ * plain pointers + sizes instead of at::Tensor:
+ *
+ *   reference interface                                   replaced by
+ *   ----------------------------------------------------  -------------------------------------------
+ *   raymarching/src/raymarching.h:6   near_far_from_aabb   nrf_near_far_from_aabb
+ *   raymarching/src/raymarching.h:7   sph_from_ray         nrf_sph_from_ray
+ *   raymarching/src/raymarching.h:8   morton3D             nrf_morton3D
+ *   raymarching/src/raymarching.h:9   morton3D_invert      nrf_morton3D_invert
+ *   raymarching/src/raymarching.h:10  packbits             nrf_packbits
+ *   raymarching/src/raymarching.h:12  march_rays_train     nrf_march_rays_train (+ _count/_write split)
+ *   raymarching/src/raymarching.h:14  composite_rays_train_forward / :15 _backward
+ *                                                          nrf_composite_rays_train_forward / _backward
+ *   raymarching/src/raymarching.h:16  march_rays           nrf_march_rays
+ *   raymarching/src/raymarching.h:17  composite_rays       nrf_composite_rays (+ nrf_compact_alive)
+ *   gridencoder/src/gridencoder.h:12  grid_encode_forward  nrf_grid_encode_forward
+ *   gridencoder/src/gridencoder.h:13  grid_encode_backward nrf_grid_encode_backward
+ *   gridencoder/src/gridencoder.h:14  grid_initialize      nrf_grid_initialize
+ *   tinycudann Network fwd/bwd (networks/style_nerf.py:44-98)   nrf_mlp_forward / nrf_mlp_backward
+ *   loss.py:32-36,199-214 cosine_dists + mask + amin       nrf_nnfm_forward / nrf_nnfm_backward
+ *
+ * Conventions: all pointers are DEVICE pointers owned by the caller; the callee never
+ * allocates, never synchronises and never throws.  Every function launches on `stream` (a
+ * cudaStream_t passed as void*) of the CURRENT device and returns 0 on success or a negative NRF_E_*
+ * code; nrf_error_string() describes it.  Layouts and dtypes are the reference's unless stated.
+ */
+#ifndef NERFSTYLE_B200_H
+#define NERFSTYLE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRF_OK             0
+#define NRF_E_INVALID     -1   /* bad argument (null pointer, unsupported D / C / width ...) */
+#define NRF_E_UNSUPPORTED -2   /* combination the kernels do not implement */
+#define NRF_E_CUDA        -3   /* a CUDA runtime call or launch failed; see nrf_last_cuda_error() */
+
+#define NRF_DTYPE_F32 0
+#define NRF_DTYPE_F16 1
+
+/* activations of the tcnn-style MLP */
+#define NRF_ACT_NONE     0
+#define NRF_ACT_RELU     1
+#define NRF_ACT_SIGMOID  2
+#define NRF_ACT_EXP      3
+
+const char* nrf_error_string(int code);
+int  nrf_last_cuda_error(void);          /* cudaError_t of the last NRF_E_CUDA on this thread */
+int  nrf_version(void);                  /* ABI version, bumped on any signature change */
+int  nrf_device_info(int* sm_count, int* cc_major, int* cc_minor, int* l2_bytes);
+
+/* ------------------------------------------------------------------ ray-marching operator set */
+
+/* raymarching.cu:191-244.  rays_o/rays_d [N,3] f32, aabb [6] f32 -> nears/fars [N] f32. */
+int nrf_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N,
+                           float min_near, float* nears, float* fars, void* stream);
+
+/* raymarching.cu:262-297.  coords [N,2] f32. */
+int nrf_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords,
+                     void* stream);
+
+/* raymarching.cu:313-359.  coords [N,3] i32 <-> indices [N] i32. */
+int nrf_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, void* stream);
+int nrf_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, void* stream);
+
+/* raymarching.cu:367-388.  grid [8N] f32 -> bitfield [N] u8; bit i of byte n = grid[8n+i] > thresh. */
+int nrf_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield, void* stream);
+
+/* Size in bytes of the scratch buffer nrf_march_rays_train* need for N rays. */
+uint64_t nrf_march_scratch_bytes(uint32_t N);
+
+/* raymarching.cu:411-589, first pass.  Counts the samples of every ray, then scans: on return (stream
+ * order) rays[n] = (n, offset, count) with offset = counter[0]_at_entry + exclusive scan of the counts
+ * in RAY ORDER (one valid schedule of the reference's racing atomicAdd, deterministic), and
+ * counter[0] += total samples, counter[1] += N (like the reference's two atomics, :506-507).
+ * noises may be NULL (= all zero, raymarching.py:247).  scratch: nrf_march_scratch_bytes(N). */
+int nrf_march_rays_train_count(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                               float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                               const float* nears, const float* fars, const float* noises,
+                               int32_t* rays, int32_t* counter, void* scratch, void* stream);
+
+/* raymarching.cu:411-589, second pass.  Re-marches every ray and writes its samples at rays[n].offset:
+ * xyzs [rows,3], dirs [rows,3], deltas [rows,4] f32.  A ray is skipped when count == 0 or
+ * offset + count >= M (the reference's drop rule, :516-517); M is the reference's logical capacity
+ * (N*max_steps or the aligned mean_count), `rows` (<= M) is what the caller really allocated.  Rows in
+ * [zero_from, rows) are zero-filled by the kernel (the reference zero-fills the whole buffer on the
+ * host side, raymarching.py:238-240); pass zero_from = rows to skip. */
+int nrf_march_rays_train_write(const float* rays_o, const float* rays_d, const float* z_hats,
+                               const uint8_t* grid, float bound, float dt_gamma, uint32_t max_steps, int is_ndc,
+                               uint32_t N, uint32_t C, uint32_t H, uint32_t M, uint32_t rows, uint32_t zero_from,
+                               const float* nears, const float* fars, const float* noises, const int32_t* rays,
+                               float* xyzs, float* dirs, float* deltas, void* stream);
+
+/* One-call form with the reference's exact native signature (pre-allocated, zero-filled M rows). */
+int nrf_march_rays_train(const float* rays_o, const float* rays_d, const float* z_hats, const uint8_t* grid,
+                         float bound, float dt_gamma, uint32_t max_steps, int is_ndc, uint32_t N, uint32_t C,
+                         uint32_t H, uint32_t M, const float* nears, const float* fars, float* xyzs, float* dirs,
+                         float* deltas, int32_t* rays, int32_t* counter, const float* noises, void* scratch,
+                         void* stream);
+
+/* raymarching.cu:807-879.  sigmas [M], rgbs [M,C], deltas [M,4], rays [N,3] ->
+ * weights_sum [N], depth [N], image [N,C] (all f32). */
+int nrf_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas,
+                                     const int32_t* rays, uint32_t M, uint32_t N, uint32_t C, float T_thresh,
+                                     int is_ndc, float* weights_sum, float* depth, float* image, void* stream);
+
+/* raymarching.cu:905-986.  grad_sigmas [M] / grad_rgbs [M,C] must be zero-filled by the caller
+ * (raymarching.py:339-340); the reference's rgbs_buf scratch is not needed. */
+int nrf_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image, const float* sigmas,
+                                      const float* rgbs, const float* deltas, const int32_t* rays, int is_ndc,
+                                      const float* weights_sum, const float* image, uint32_t M, uint32_t N,
+                                      uint32_t C, float T_thresh, float* grad_sigmas, float* grad_rgbs,
+                                      void* stream);
+
+/* raymarching.cu:1005-1120.  xyzs/dirs [Mpad,3], deltas [Mpad,4]; rows [n_alive*n_step, Mpad) and the
+ * unused slots of exited rays are zero-filled by the kernel when zero_fill != 0 (the reference relies on a
+ * host-side torch.zeros, raymarching.py:409-412). */
+int nrf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                   const float* rays_o, const float* rays_d, const float* z_hats, float bound, float dt_gamma,
+                   uint32_t max_steps, int is_ndc, uint32_t C, uint32_t H, const uint8_t* grid, const float* nears,
+                   const float* fars, float* xyzs, float* dirs, float* deltas, const float* noises,
+                   uint32_t Mpad, int zero_fill, void* stream);
+
+/* raymarching.cu:1134-1231.  In place on rays_alive, rays_t, weights_sum, depth, image. */
+int nrf_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive, float* rays_t,
+                       const float* sigmas, const float* rgbs, const float* deltas, uint32_t C, int is_ndc,
+                       float* weights_sum, float* depth, float* image, void* stream);
+
+/* Extension (replaces `rays_alive[rays_alive >= 0]`, renderer.py:284): stable compaction of the
+ * non-negative entries of in[0..n) into out; *n_out (device int32) receives the new count.
+ * scratch: nrf_march_scratch_bytes(n). */
+int nrf_compact_alive(const int32_t* in, uint32_t n, int32_t* out, int32_t* n_out, void* scratch, void* stream);
+
+/* ------------------------------------------------------------------ hash-grid encoder */
+
+/* gridencoder.cu:439-462 (kernel_grid :83-235).  inputs [B,D] f32 in [0,1]; embeddings [rows,C] f32 or
+ * f16 (dtype); offsets [L+1] i32.  outputs: point_major != 0 -> [B, L*C] (what grid.py:58 produces after
+ * its permute), else the reference's native [L,B,C].  dy_dx [B, L*D*C] only when calc_grad_inputs.
+ * Supported: D in {2,3}, C in {1,2,4,8}. */
+int nrf_grid_encode_forward(const float* inputs, const void* embeddings, const int32_t* offsets, void* outputs,
+                            uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                            int calc_grad_inputs, void* dy_dx, uint32_t gridtype, int align_corners, uint32_t style,
+                            int dtype, int point_major, void* stream);
+
+/* gridencoder.cu:464-494 (kernel_grid_backward :238-328, kernel_input_backward :331-357).
+ * grad: [B, L*C] when point_major else [L,B,C]; grad_embeddings [rows,C] must be zero-filled by the caller
+ * (grid.py:82).  grad_inputs [B,D] (same dtype) only when calc_grad_inputs. */
+int nrf_grid_encode_backward(const void* grad, const float* inputs, const void* embeddings, const int32_t* offsets,
+                             void* grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
+                             uint32_t H, int calc_grad_inputs, const void* dy_dx, void* grad_inputs,
+                             uint32_t gridtype, int align_corners, uint32_t style, int dtype, int point_major,
+                             void* stream);
+
+/* gridencoder.cu:551-571 (D=3, C=2, f32 like the reference's only use). */
+int nrf_grid_initialize(const float* ref_embeddings, float* embeddings, const int32_t* ref_offsets,
+                        const int32_t* offsets, uint32_t L, float S, uint32_t H, uint32_t Ns, void* stream);
+
+/* ------------------------------------------------------------------ tcnn-style fully fused MLP */
+
+/* Bias-free MLP  y = act_out(W_n relu(... relu(W_1 x))) with `width`-wide hidden layers (width = 64).
+ * params: f16, tcnn FullyFusedMLP layout: W_1 [width, in_pad], (n_hidden-1) x [width, width],
+ * W_out [out_pad, width], row-major, concatenated; in_pad / out_pad = n_in / n_out rounded up to 16.
+ * x [B, n_in] (x_dtype f32 or f16, row stride n_in), y [B, n_out] (y_dtype).  Hidden activations are
+ * rounded to f16 between layers, products accumulate in f32 on the tensor cores. */
+int nrf_mlp_forward(const void* x, int x_dtype, const void* params_f16, uint32_t B, uint32_t n_in,
+                    uint32_t n_out, uint32_t n_hidden, uint32_t width, int hidden_act, int out_act,
+                    void* y, int y_dtype, void* stream);
+
+/* Backward of the above; recomputes the hidden activations from x (nothing but x and y is saved).
+ * dy [B, n_out] (dy_dtype); dx [B, n_in] (dx_dtype) or NULL; dparams f32 [same layout as params] is
+ * ACCUMULATED into (caller zero-fills).  loss_scale multiplies dy before the f16 tensor-core products and
+ * is divided out of dx / dparams (tcnn's loss_scale, 128 for f16). */
+int nrf_mlp_backward(const void* x, int x_dtype, const void* params_f16, const void* dy, int dy_dtype,
+                     uint32_t B, uint32_t n_in, uint32_t n_out, uint32_t n_hidden, uint32_t width,
+                     int hidden_act, int out_act, float loss_scale, void* dx, int dx_dtype, float* dparams,
+                     void* stream);
+
+/* ------------------------------------------------------------------ nearest-neighbour feature matching */
+
+/* loss.py:32-36,199-214.  a [N1,K] f16 (rows already L2-normalised), b [N2,K] f16 (normalised);
+ * a_label [N1] i32 (class of each image feature, <0 = unconstrained), b_label [N2] i32 (cluster of each
+ * style feature), match [n_class] i32 (class -> required cluster; NULL = no mask).
+ * min_dist [N1] f32 = min_j (1 - a_i.b_j) over allowed j (+inf if none), argmin [N1] i32 (-1 if none).
+ * The N1 x N2 matrix is never materialised. */
+int nrf_nnfm_forward(const void* a_f16, const void* b_f16, uint32_t N1, uint32_t N2, uint32_t K,
+                     const int32_t* a_label, const int32_t* b_label, const int32_t* match, uint32_t n_class,
+                     float* min_dist, int32_t* argmin, void* scratch, void* stream);
+uint64_t nrf_nnfm_scratch_bytes(uint32_t N1, uint32_t N2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERFSTYLE_B200_H */

@@ -1,0 +1,18 @@
+"""nerfstyle_b200 -- B200-native (sm_100a) NeRF render/train hot path behind the reference's operator surface.
+
+Sub-modules (each mirrors one reference interface):
+  raymarching   raymarching/raymarching.py   (near_far_from_aabb, march_rays_train, composite_rays_train, ...)
+  gridencoder   gridencoder/grid.py          (GridEncoder, grid_encode)
+  tcnn          tinycudann.Network           (fused 64-wide MLP)
+  nnfm          loss.py cosine_dists+amin    (nearest-neighbour feature matching)
+  dropin        sys.modules aliases so the reference's renderer.py / networks/*.py import these unchanged
+
+All compute goes through libnerfstyle_b200.so (C ABI: include/nerfstyle_b200.h).  No CPU fallback.
+"""
+__version__ = '0.1.0'
+
+from . import _lib  # noqa: F401
+
+
+def lib_path():
+    return _lib.LIB_PATH

@@ -1,0 +1,127 @@
+"""ctypes binding of libnerfstyle_b200.so (the C ABI declared in include/nerfstyle_b200.h).
+
+There is no CPU fallback: if the library is missing or a call fails, the ops raise RuntimeError.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libnerfstyle_b200.so')
+
+_vp = ctypes.c_void_p
+_u32 = ctypes.c_uint32
+_i32 = ctypes.c_int
+_f32 = ctypes.c_float
+_u64 = ctypes.c_uint64
+
+# name -> (restype, argtypes); mirrors include/nerfstyle_b200.h one to one
+SIGNATURES = {
+    'nrf_error_string': (ctypes.c_char_p, [_i32]),
+    'nrf_last_cuda_error': (_i32, []),
+    'nrf_version': (_i32, []),
+    'nrf_device_info': (_i32, [_vp, _vp, _vp, _vp]),
+    'nrf_near_far_from_aabb': (_i32, [_vp, _vp, _vp, _u32, _f32, _vp, _vp, _vp]),
+    'nrf_sph_from_ray': (_i32, [_vp, _vp, _f32, _u32, _vp, _vp]),
+    'nrf_morton3D': (_i32, [_vp, _u32, _vp, _vp]),
+    'nrf_morton3D_invert': (_i32, [_vp, _u32, _vp, _vp]),
+    'nrf_packbits': (_i32, [_vp, _u32, _f32, _vp, _vp]),
+    'nrf_march_scratch_bytes': (_u64, [_u32]),
+    'nrf_march_rays_train_count': (_i32, [_vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp,
+                                          _vp, _vp]),
+    'nrf_march_rays_train_write': (_i32, [_vp, _vp, _vp, _vp, _f32, _f32, _u32, _i32, _u32, _u32, _u32, _u32, _u32,
+                                          _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'nrf_march_rays_train': (_i32, [_vp, _vp, _vp, _vp, _f32, _f32, _u32, _i32, _u32, _u32, _u32, _u32, _vp, _vp, _vp,
+                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'nrf_composite_rays_train_forward': (_i32, [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _f32, _i32, _vp, _vp, _vp, _vp]),
+    'nrf_composite_rays_train_backward': (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _u32, _u32, _u32, _f32,
+                                                 _vp, _vp, _vp]),
+    'nrf_march_rays': (_i32, [_u32, _u32, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _u32, _i32, _u32, _u32, _vp, _vp, _vp,
+                              _vp, _vp, _vp, _vp, _u32, _i32, _vp]),
+    'nrf_composite_rays': (_i32, [_u32, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _u32, _i32, _vp, _vp, _vp, _vp]),
+    'nrf_compact_alive': (_i32, [_vp, _u32, _vp, _vp, _vp, _vp]),
+    'nrf_grid_encode_forward': (_i32, [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _u32, _i32, _vp, _u32, _i32,
+                                       _u32, _i32, _i32, _vp]),
+    'nrf_grid_encode_backward': (_i32, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _u32, _i32, _vp, _vp,
+                                        _u32, _i32, _u32, _i32, _i32, _vp]),
+    'nrf_grid_initialize': (_i32, [_vp, _vp, _vp, _vp, _u32, _f32, _u32, _u32, _vp]),
+    'nrf_mlp_forward': (_i32, [_vp, _i32, _vp, _u32, _u32, _u32, _u32, _u32, _i32, _i32, _vp, _i32, _vp]),
+    'nrf_mlp_backward': (_i32, [_vp, _i32, _vp, _vp, _i32, _u32, _u32, _u32, _u32, _u32, _i32, _i32, _f32, _vp, _i32,
+                                _vp, _vp]),
+    'nrf_nnfm_forward': (_i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
+    'nrf_nnfm_scratch_bytes': (_u64, [_u32, _u32]),
+}
+# tuning / extension entry points that are not part of the reference-replacing ABI
+EXTRA_SIGNATURES = {
+    'nrf_grid_set_tuning': (None, [_i32, _i32, _i32]),
+}
+
+DTYPE_F32, DTYPE_F16 = 0, 1
+ACT = {'none': 0, 'relu': 1, 'sigmoid': 2, 'exponential': 3}
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library (once).  Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            'nerfstyle_b200: %s is missing -- build it with `python -m nerfstyle_b200.build` '
+            '(there is no CPU fallback)' % LIB_PATH)
+    l = ctypes.CDLL(LIB_PATH)
+    for table in (SIGNATURES, EXTRA_SIGNATURES):
+        for name, (res, args) in table.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+    _lib = l
+    return _lib
+
+
+def check(code, what):
+    if code != 0:
+        l = lib()
+        msg = l.nrf_error_string(code).decode()
+        if code == -3:
+            msg += ' (cudaError %d)' % l.nrf_last_cuda_error()
+        raise RuntimeError('nerfstyle_b200.%s failed: %s' % (what, msg))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_of(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('nerfstyle_b200: expected a CUDA tensor, got device %s' % t.device)
+
+
+def dtype_code(dt):
+    if dt == torch.float32:
+        return DTYPE_F32
+    if dt == torch.float16:
+        return DTYPE_F16
+    raise RuntimeError('nerfstyle_b200: unsupported dtype %s (float32 or float16)' % dt)
+
+
+_scratch = {}
+
+
+def scratch(device, nbytes):
+    """Small per-device scratch buffer reused across calls on the same stream order."""
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
+        _scratch[key] = buf
+    return buf

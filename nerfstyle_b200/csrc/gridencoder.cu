@@ -1,0 +1,548 @@
+// Multiresolution hash-grid encoder for sm_100a (C ABI in include/nerfstyle_b200.h).
+//
+// Behavioural contract: /root/reference/gridencoder/src/gridencoder.cu (cited per function).  Written from
+// scratch: the forward is a vectorised 8-corner gather that writes point-major [B, L*C] directly (the
+// reference writes [L,B,C] and pays a permute copy, grid.py:58), the backward is a warp-aggregated scatter
+// (lanes that fall into the same cell are reduced with shuffles before ONE vector atomic per corner).
+// Index arithmetic (hash, strides, modulo) is bit-exact with the reference; the float interpolation uses
+// explicit __fmaf_rn at the reference's contraction points so f32 outputs are bit-exact too.
+#include "common.cuh"
+
+#define GRID_MAX_LEVELS 32
+#define GRID_BLOCK 256
+
+__host__ __device__ __forceinline__ uint32_t prime_of(int i) {
+    // gridencoder.cu:42
+    return i == 0 ? 1u : i == 1 ? 2654435761u : i == 2 ? 805459861u : i == 3 ? 3674653429u : i == 4 ? 2097192037u
+         : i == 5 ? 1434869437u : 2165219737u;
+}
+
+// per-level constants, computed once per block into shared memory
+struct LevelP {
+    uint32_t offset;        // row offset of the level
+    uint32_t size;          // hashmap_size (rows)
+    uint32_t resolution;
+    float scale;
+    uint32_t stride[3];     // dense strides actually accumulated (0 = dimension not accumulated)
+    uint32_t style_term;    // style*stride when the style stride fits (dense), else 0
+    uint32_t hash_style;    // style * primes[D]
+    uint32_t use_hash;
+    uint32_t mul, shift;    // exact x / size for any uint32 x:  t=umulhi(x,mul); q=(t+((x-t)>>1))>>(shift-1)
+    uint32_t pow2mask;      // size-1 when size is a power of two, else 0
+};
+
+// gridencoder.cu:55-80 stride logic, and :134-138 resolution/scale, for D dims
+__device__ __forceinline__ void level_setup(LevelP& p, const int32_t* __restrict__ offsets, uint32_t level, uint32_t D,
+                                            float S, uint32_t H, uint32_t gridtype, bool align_corners, uint32_t style) {
+    p.offset = (uint32_t)offsets[level];
+    p.size = (uint32_t)(offsets[level + 1] - offsets[level]);
+    p.resolution = (uint32_t)floorf(exp2f((float)level * S) * (float)H);
+    p.scale = (float)(p.resolution - (align_corners ? 0u : 1u));
+    uint32_t stride = 1;
+    p.stride[0] = p.stride[1] = p.stride[2] = 0;
+    for (uint32_t d = 0; d < D && stride <= p.size; d++) {
+        if (d < 3) p.stride[d] = stride;
+        stride *= (p.resolution + 1);
+    }
+    p.style_term = 0;
+    if (stride <= p.size) { p.style_term = style * stride; stride *= 512u; }
+    p.use_hash = (gridtype == 0 && stride > p.size) ? 1u : 0u;
+    p.hash_style = style * prime_of((int)D);
+    p.pow2mask = ((p.size & (p.size - 1)) == 0) ? p.size - 1 : 0u;
+    // Granlund-Montgomery round-up magic for exact unsigned division by p.size
+    uint32_t l = 0;
+    while ((1ull << l) < (uint64_t)p.size) l++;
+    p.shift = l;
+    p.mul = (uint32_t)((((1ull << 32) * ((1ull << l) - (uint64_t)p.size)) / (uint64_t)p.size) + 1ull);
+}
+
+__device__ __forceinline__ uint32_t mod_size(const LevelP& p, uint32_t x) {
+    if (p.pow2mask) return x & p.pow2mask;
+    if (p.size == 1) return 0;
+    const uint32_t t = __umulhi(x, p.mul);
+    const uint32_t q = (t + ((x - t) >> 1)) >> (p.shift - 1);
+    return x - q * p.size;
+}
+
+// position within a level (gridencoder.cu:144-149): pos = fma(x, scale, 0 | 0.5), cell = min(floor, res-1)
+__device__ __forceinline__ void locate1(float in, const LevelP& p, bool align_corners, uint32_t& cell, float& frac) {
+    const float pos = __fmaf_rn(in, p.scale, align_corners ? 0.0f : 0.5f);
+    cell = (uint32_t)fminf(floorf(pos), (float)(p.resolution - 1));
+    frac = __fsub_rn(pos, (float)cell);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward, fast path D=3 C=2 (the only instance the model uses)
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct Vec2;
+template <> struct Vec2<float> { typedef float2 type; };
+template <> struct Vec2<__half> { typedef __half2 type; };
+
+__device__ __forceinline__ void corner_rows_d3(const LevelP& p, uint32_t cx, uint32_t cy, uint32_t cz, uint32_t rows[8]) {
+    if (p.use_hash) {
+        const uint32_t hx0 = cx, hx1 = cx + 1;
+        const uint32_t hy0 = cy * 2654435761u, hy1 = (cy + 1) * 2654435761u;
+        const uint32_t hz0 = (cz * 805459861u) ^ p.hash_style, hz1 = ((cz + 1) * 805459861u) ^ p.hash_style;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            rows[k] = mod_size(p, ((k & 1) ? hx1 : hx0) ^ ((k & 2) ? hy1 : hy0) ^ ((k & 4) ? hz1 : hz0));
+    } else {
+        const uint32_t base = cx * p.stride[0] + cy * p.stride[1] + cz * p.stride[2] + p.style_term;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            rows[k] = mod_size(p, base + ((k & 1) ? p.stride[0] : 0u) + ((k & 2) ? p.stride[1] : 0u) + ((k & 4) ? p.stride[2] : 0u));
+    }
+}
+
+__device__ __forceinline__ void corner_weights_d3(float fx, float fy, float fz, float w[8]) {
+    // gridencoder.cu:157-170: w = 1; w *= (bit d ? f_d : 1-f_d) for d = 0,1,2 (in that order)
+    const float gx = __fsub_rn(1.0f, fx), gy = __fsub_rn(1.0f, fy), gz = __fsub_rn(1.0f, fz);
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        w[k] = __fmul_rn(__fmul_rn((k & 1) ? fx : gx, (k & 2) ? fy : gy), (k & 4) ? fz : gz);
+}
+
+__device__ __forceinline__ uint32_t h2u(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ uint32_t h2u(float2) { return 0u; }
+
+template <typename T, int LPT>
+__global__ void __launch_bounds__(GRID_BLOCK)
+k_grid_fwd_d3c2(const float* __restrict__ inputs, const T* __restrict__ table, const int32_t* __restrict__ offsets,
+                T* __restrict__ outputs, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align_corners,
+                uint32_t style, bool point_major) {
+    typedef typename Vec2<T>::type V2;
+    __shared__ LevelP lp[LPT];
+    const uint32_t l0 = blockIdx.y * LPT;
+    if (threadIdx.x < LPT && l0 + threadIdx.x < L) level_setup(lp[threadIdx.x], offsets, l0 + threadIdx.x, 3, S, H, gridtype, align_corners, style);
+    __syncthreads();
+    const uint32_t b = blockIdx.x * GRID_BLOCK + threadIdx.x;
+    if (b >= B) return;
+    const float x = __ldg(inputs + 3 * (size_t)b), y = __ldg(inputs + 3 * (size_t)b + 1), z = __ldg(inputs + 3 * (size_t)b + 2);
+    const bool oob = (x < 0 || x > 1) || (y < 0 || y > 1) || (z < 0 || z > 1);   // gridencoder.cu:107-114
+    V2 res[LPT];
+#pragma unroll
+    for (int j = 0; j < LPT; j++) {
+        if constexpr (sizeof(T) == 4) res[j] = make_float2(0.0f, 0.0f); else res[j] = __floats2half2_rn(0.0f, 0.0f);
+        if (l0 + j >= L || oob) continue;
+        const LevelP& p = lp[j];
+        uint32_t cx, cy, cz; float fx, fy, fz;
+        locate1(x, p, align_corners, cx, fx);
+        locate1(y, p, align_corners, cy, fy);
+        locate1(z, p, align_corners, cz, fz);
+        uint32_t rows[8]; float w[8];
+        corner_rows_d3(p, cx, cy, cz, rows);
+        corner_weights_d3(fx, fy, fz, w);
+        const V2* tl = reinterpret_cast<const V2*>(table) + p.offset;
+        V2 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = __ldg(tl + rows[k]);
+        if constexpr (sizeof(T) == 4) {
+            float r0 = 0.0f, r1 = 0.0f;   // gridencoder.cu:177 compiles to fma.rn
+#pragma unroll
+            for (int k = 0; k < 8; k++) { r0 = __fmaf_rn(w[k], v[k].x, r0); r1 = __fmaf_rn(w[k], v[k].y, r1); }
+            res[j] = make_float2(r0, r1);
+        } else {
+            // scalar_t = at::Half: the product is rounded to half, then the half sum is rounded to half
+            __half2 acc = __floats2half2_rn(0.0f, 0.0f);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float2 g = __half22float2(v[k]);
+                acc = __hadd2(acc, __floats2half2_rn(__fmul_rn(w[k], g.x), __fmul_rn(w[k], g.y)));
+            }
+            res[j] = acc;
+        }
+    }
+    if (point_major) {
+        V2* o = reinterpret_cast<V2*>(outputs) + (size_t)b * L + l0;
+        constexpr int PER16 = 16 / (int)sizeof(V2);
+        if (LPT % PER16 == 0 && (L % PER16) == 0 && l0 + LPT <= L && ((uintptr_t)outputs & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < LPT; j += PER16) {
+                uint4 u;
+                if constexpr (sizeof(T) == 4) {
+                    u = make_uint4(__float_as_uint(res[j].x), __float_as_uint(res[j].y), __float_as_uint(res[(j + 1) % LPT].x), __float_as_uint(res[(j + 1) % LPT].y));
+                } else {
+                    u = make_uint4(h2u(res[j]), h2u(res[(j + 1) % LPT]), h2u(res[(j + 2) % LPT]), h2u(res[(j + 3) % LPT]));
+                }
+                *reinterpret_cast<uint4*>(o + j) = u;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < LPT; j++) if (l0 + j < L) o[j] = res[j];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < LPT; j++) if (l0 + j < L) reinterpret_cast<V2*>(outputs)[(size_t)(l0 + j) * B + b] = res[j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward, generic (D in {2,3}, C in {1,2,4,8}, optional dy_dx): thread per (point, level), kernel_grid :83-235
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ uint32_t grid_row(const LevelP& p, const uint32_t pg[D]) {
+    uint32_t index;
+    if (p.use_hash) {
+        index = 0;
+#pragma unroll
+        for (int d = 0; d < D; d++) index ^= pg[d] * prime_of(d);
+        index ^= p.hash_style;
+    } else {
+        index = p.style_term;
+#pragma unroll
+        for (int d = 0; d < D; d++) index += pg[d] * p.stride[d];
+    }
+    return mod_size(p, index);
+}
+
+__device__ __forceinline__ float ld_as_float(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_as_float(const __half* p) { return __half2float(__ldg(p)); }
+__device__ __forceinline__ void st_from_float(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st_from_float(__half* p, float v) { *p = __float2half_rn(v); }
+// `acc += w*g` in the reference's scalar_t arithmetic
+__device__ __forceinline__ float acc_step(float acc, float w, float g, float) { return __fmaf_rn(w, g, acc); }
+__device__ __forceinline__ float acc_step(float acc, float w, float g, __half) {
+    const float prod = __half2float(__float2half_rn(__fmul_rn(w, g)));
+    return __half2float(__float2half_rn(__fadd_rn(acc, prod)));
+}
+
+template <typename T, int D, int C>
+__global__ void __launch_bounds__(GRID_BLOCK)
+k_grid_fwd_generic(const float* __restrict__ inputs, const T* __restrict__ table, const int32_t* __restrict__ offsets,
+                   T* __restrict__ outputs, uint32_t B, uint32_t L, float S, uint32_t H, bool calc_grad_inputs,
+                   T* __restrict__ dy_dx, uint32_t gridtype, bool align_corners, uint32_t style, bool point_major) {
+    __shared__ LevelP p;
+    const uint32_t level = blockIdx.y;
+    if (threadIdx.x == 0) level_setup(p, offsets, level, D, S, H, gridtype, align_corners, style);
+    __syncthreads();
+    const uint32_t b = blockIdx.x * GRID_BLOCK + threadIdx.x;
+    if (b >= B) return;
+    T* out = point_major ? outputs + ((size_t)b * L + level) * C : outputs + ((size_t)level * B + b) * C;
+    T* dd = dy_dx + (size_t)b * D * L * C + (size_t)level * D * C;
+    float in[D];
+    bool oob = false;
+#pragma unroll
+    for (int d = 0; d < D; d++) { in[d] = __ldg(inputs + (size_t)b * D + d); if (in[d] < 0 || in[d] > 1) oob = true; }
+    if (oob) {
+#pragma unroll
+        for (int c = 0; c < C; c++) st_from_float(out + c, 0.0f);
+        if (calc_grad_inputs) {
+#pragma unroll
+            for (int k = 0; k < D * C; k++) st_from_float(dd + k, 0.0f);
+        }
+        return;
+    }
+    uint32_t pg[D]; float pos[D];
+#pragma unroll
+    for (int d = 0; d < D; d++) locate1(in[d], p, align_corners, pg[d], pos[d]);
+    const T* tl = table + (size_t)p.offset * C;
+    float res[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) res[c] = 0.0f;
+#pragma unroll
+    for (int idx = 0; idx < (1 << D); idx++) {
+        float w = 1.0f; uint32_t pl[D];
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            if ((idx & (1 << d)) == 0) { w = __fmul_rn(w, __fsub_rn(1.0f, pos[d])); pl[d] = pg[d]; }
+            else { w = __fmul_rn(w, pos[d]); pl[d] = pg[d] + 1; }
+        }
+        const uint32_t row = grid_row<D>(p, pl);
+#pragma unroll
+        for (int c = 0; c < C; c++) res[c] = acc_step(res[c], w, ld_as_float(tl + (size_t)row * C + c), T());
+    }
+#pragma unroll
+    for (int c = 0; c < C; c++) st_from_float(out + c, res[c]);
+    if (calc_grad_inputs) {   // gridencoder.cu:191-234
+#pragma unroll
+        for (int gd = 0; gd < D; gd++) {
+            float rg[C];
+#pragma unroll
+            for (int c = 0; c < C; c++) rg[c] = 0.0f;
+#pragma unroll
+            for (int idx = 0; idx < (1 << (D - 1)); idx++) {
+                float w = p.scale; uint32_t pl[D];
+#pragma unroll
+                for (int nd = 0; nd < D - 1; nd++) {
+                    const int d = (nd >= gd) ? (nd + 1) : nd;
+                    if ((idx & (1 << nd)) == 0) { w = __fmul_rn(w, __fsub_rn(1.0f, pos[d])); pl[d] = pg[d]; }
+                    else { w = __fmul_rn(w, pos[d]); pl[d] = pg[d] + 1; }
+                }
+                pl[gd] = pg[gd];
+                const uint32_t rl = grid_row<D>(p, pl);
+                pl[gd] = pg[gd] + 1;
+                const uint32_t rr = grid_row<D>(p, pl);
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    float diff = __fsub_rn(ld_as_float(tl + (size_t)rr * C + c), ld_as_float(tl + (size_t)rl * C + c));
+                    if (sizeof(T) == 2) diff = __half2float(__float2half_rn(diff));
+                    rg[c] = acc_step(rg[c], w, diff, T());
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < C; c++) st_from_float(dd + gd * C + c, rg[c]);
+        }
+    }
+}
+
+static int g_fwd_lpt = 16;   // levels per thread of the fast path (tunable: nrf_grid_set_tuning)
+static int g_bwd_lpt = 16;
+static int g_bwd_agg = 24;   // aggregate when a warp has <= this many distinct cells (0 = never)
+NRF_EXPORT void nrf_grid_set_tuning(int fwd_lpt, int bwd_lpt, int bwd_agg) {
+    if (fwd_lpt > 0) g_fwd_lpt = fwd_lpt;
+    if (bwd_lpt > 0) g_bwd_lpt = bwd_lpt;
+    if (bwd_agg >= 0) g_bwd_agg = bwd_agg;
+}
+
+template <typename T>
+static int launch_fwd(const float* inputs, const void* embeddings, const int32_t* offsets, void* outputs, uint32_t B,
+                      uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, bool calc, void* dy_dx, uint32_t gridtype,
+                      bool ac, uint32_t style, bool pm, cudaStream_t s) {
+    const T* tab = (const T*)embeddings; T* out = (T*)outputs; T* dd = (T*)dy_dx;
+    const uint32_t nbx = ceil_div_u32(B, GRID_BLOCK);
+    if (D == 3 && C == 2 && !calc && (((uintptr_t)embeddings) & 7) == 0) {
+        const int lpt = g_fwd_lpt;
+#define FWD_FAST(LPT) k_grid_fwd_d3c2<T, LPT><<<dim3(nbx, ceil_div_u32(L, LPT)), GRID_BLOCK, 0, s>>>(inputs, tab, offsets, out, B, L, S, H, gridtype, ac, style, pm)
+        if (lpt >= 16) FWD_FAST(16); else if (lpt >= 8) FWD_FAST(8); else if (lpt >= 4) FWD_FAST(4); else if (lpt >= 2) FWD_FAST(2); else FWD_FAST(1);
+#undef FWD_FAST
+        return nrf_check_launch();
+    }
+    const dim3 grid(nbx, L);
+#define FWD_GEN(DD, CC) k_grid_fwd_generic<T, DD, CC><<<grid, GRID_BLOCK, 0, s>>>(inputs, tab, offsets, out, B, L, S, H, calc, dd, gridtype, ac, style, pm)
+    if (D == 3) { switch (C) { case 1: FWD_GEN(3, 1); break; case 2: FWD_GEN(3, 2); break; case 4: FWD_GEN(3, 4); break; case 8: FWD_GEN(3, 8); break; default: return NRF_E_UNSUPPORTED; } }
+    else if (D == 2) { switch (C) { case 1: FWD_GEN(2, 1); break; case 2: FWD_GEN(2, 2); break; case 4: FWD_GEN(2, 4); break; case 8: FWD_GEN(2, 8); break; default: return NRF_E_UNSUPPORTED; } }
+    else return NRF_E_UNSUPPORTED;
+#undef FWD_GEN
+    return nrf_check_launch();
+}
+
+NRF_EXPORT int nrf_grid_encode_forward(const float* inputs, const void* embeddings, const int32_t* offsets, void* outputs,
+                                       uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                                       int calc_grad_inputs, void* dy_dx, uint32_t gridtype, int align_corners, uint32_t style,
+                                       int dtype, int point_major, void* stream) {
+    if (B == 0) return NRF_OK;
+    if (!inputs || !embeddings || !offsets || !outputs) return NRF_E_INVALID;
+    if (calc_grad_inputs && !dy_dx) return NRF_E_INVALID;
+    if (L == 0 || L > GRID_MAX_LEVELS) return NRF_E_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == NRF_DTYPE_F32)
+        return launch_fwd<float>(inputs, embeddings, offsets, outputs, B, D, C, L, S, H, calc_grad_inputs != 0, dy_dx, gridtype, align_corners != 0, style, point_major != 0, s);
+    if (dtype == NRF_DTYPE_F16)
+        return launch_fwd<__half>(inputs, embeddings, offsets, outputs, B, D, C, L, S, H, calc_grad_inputs != 0, dy_dx, gridtype, align_corners != 0, style, point_major != 0, s);
+    return NRF_E_UNSUPPORTED;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward, fast path D=3 C=2: warp-aggregated scatter (kernel_grid_backward :238-328)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_add2(float* base, uint32_t row, float a, float b) {
+    atomicAdd(reinterpret_cast<float2*>(base) + row, make_float2(a, b));      // RED.ADD.F32x2 (sm_90+)
+}
+__device__ __forceinline__ void atomic_add2(__half* base, uint32_t row, float a, float b) {
+    atomicAdd(reinterpret_cast<__half2*>(base) + row, __floats2half2_rn(a, b));
+}
+
+template <typename T, int LPT>
+__global__ void __launch_bounds__(GRID_BLOCK)
+k_grid_bwd_d3c2(const T* __restrict__ grad, const float* __restrict__ inputs, const int32_t* __restrict__ offsets,
+                T* __restrict__ grad_table, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align_corners,
+                uint32_t style, bool point_major, int agg_max_groups) {
+    typedef typename Vec2<T>::type V2;
+    __shared__ LevelP lp[LPT];
+    const uint32_t l0 = blockIdx.y * LPT;
+    if (threadIdx.x < LPT && l0 + threadIdx.x < L) level_setup(lp[threadIdx.x], offsets, l0 + threadIdx.x, 3, S, H, gridtype, align_corners, style);
+    __syncthreads();
+    const uint32_t b = blockIdx.x * GRID_BLOCK + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    float x = -1.0f, y = -1.0f, z = -1.0f;
+    if (b < B) { x = __ldg(inputs + 3 * (size_t)b); y = __ldg(inputs + 3 * (size_t)b + 1); z = __ldg(inputs + 3 * (size_t)b + 2); }
+    const bool active = !((x < 0 || x > 1) || (y < 0 || y > 1) || (z < 0 || z > 1));   // oob points contribute nothing (:268-273)
+#pragma unroll 1
+    for (int j = 0; j < LPT; j++) {
+        if (l0 + j >= L) break;            // uniform
+        const LevelP& p = lp[j];
+        uint32_t cx = 0, cy = 0, cz = 0; float fx = 0, fy = 0, fz = 0;
+        uint32_t rows[8]; float w[8];
+        float g0 = 0.0f, g1 = 0.0f;
+        if (active) {
+            locate1(x, p, align_corners, cx, fx);
+            locate1(y, p, align_corners, cy, fy);
+            locate1(z, p, align_corners, cz, fz);
+            corner_rows_d3(p, cx, cy, cz, rows);
+            corner_weights_d3(fx, fy, fz, w);
+            const V2 gvj = point_major ? __ldg(reinterpret_cast<const V2*>(grad) + (size_t)b * L + l0 + j)
+                                       : __ldg(reinterpret_cast<const V2*>(grad) + (size_t)(l0 + j) * B + b);
+            if constexpr (sizeof(T) == 4) { g0 = gvj.x; g1 = gvj.y; }
+            else { const float2 gg = __half22float2(gvj); g0 = gg.x; g1 = gg.y; }
+        }
+        T* gl = grad_table + (size_t)p.offset * 2;
+        bool done = false;
+        if (agg_max_groups > 0) {
+            // lanes in the same cell share all 8 corner rows
+            const unsigned long long key = active ? (((unsigned long long)cz << 42) | ((unsigned long long)cy << 21) | (unsigned long long)cx)
+                                                  : (0xFFFFFFFF00000000ull | (unsigned)lane);
+            const uint32_t mask = __match_any_sync(NRF_FULL_MASK, key);
+            const int lo = __ffs(mask) - 1, hi = 31 - __clz(mask);
+            const uint32_t span = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+            const bool contiguous = (mask == span);
+            const int ngroups = __popc(__ballot_sync(NRF_FULL_MASK, lane == lo));
+            if (__all_sync(NRF_FULL_MASK, contiguous) && ngroups <= agg_max_groups) {
+                float v0[8], v1[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) { v0[k] = active ? __fmul_rn(w[k], g0) : 0.0f; v1[k] = active ? __fmul_rn(w[k], g1) : 0.0f; }
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const bool take = (lane + d <= hi);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const float o0 = __shfl_down_sync(NRF_FULL_MASK, v0[k], d);
+                        const float o1 = __shfl_down_sync(NRF_FULL_MASK, v1[k], d);
+                        if (take) { v0[k] += o0; v1[k] += o1; }
+                    }
+                }
+                if (active && lane == lo) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) atomic_add2(gl, rows[k], v0[k], v1[k]);
+                }
+                done = true;
+            }
+        }
+        if (!done && active) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) atomic_add2(gl, rows[k], __fmul_rn(w[k], g0), __fmul_rn(w[k], g1));
+        }
+    }
+}
+
+// generic backward: thread per (point, level, channel pair) like the reference
+template <typename T, int D, int C>
+__global__ void __launch_bounds__(GRID_BLOCK)
+k_grid_bwd_generic(const T* __restrict__ grad, const float* __restrict__ inputs, const int32_t* __restrict__ offsets,
+                   T* __restrict__ grad_table, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align_corners,
+                   uint32_t style, bool point_major) {
+    __shared__ LevelP p;
+    const uint32_t level = blockIdx.y;
+    if (threadIdx.x == 0) level_setup(p, offsets, level, D, S, H, gridtype, align_corners, style);
+    __syncthreads();
+    const uint32_t b = blockIdx.x * GRID_BLOCK + threadIdx.x;
+    if (b >= B) return;
+    float in[D];
+#pragma unroll
+    for (int d = 0; d < D; d++) { in[d] = __ldg(inputs + (size_t)b * D + d); if (in[d] < 0 || in[d] > 1) return; }
+    uint32_t pg[D]; float pos[D];
+#pragma unroll
+    for (int d = 0; d < D; d++) locate1(in[d], p, align_corners, pg[d], pos[d]);
+    const T* gp = point_major ? grad + ((size_t)b * L + level) * C : grad + ((size_t)level * B + b) * C;
+    float g[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) g[c] = ld_as_float(gp + c);
+    T* gl = grad_table + (size_t)p.offset * C;
+#pragma unroll
+    for (int idx = 0; idx < (1 << D); idx++) {
+        float w = 1.0f; uint32_t pl[D];
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            if ((idx & (1 << d)) == 0) { w = __fmul_rn(w, __fsub_rn(1.0f, pos[d])); pl[d] = pg[d]; }
+            else { w = __fmul_rn(w, pos[d]); pl[d] = pg[d] + 1; }
+        }
+        const uint32_t row = grid_row<D>(p, pl);
+        if constexpr (C == 1) {
+            if constexpr (sizeof(T) == 4) atomicAdd(reinterpret_cast<float*>(gl) + row, __fmul_rn(w, g[0]));
+            else atomicAdd(reinterpret_cast<__half*>(gl) + row, __float2half_rn(__fmul_rn(w, g[0])));
+        } else {
+#pragma unroll
+            for (int c = 0; c < C; c += 2) atomic_add2(gl + (size_t)row * C + c, 0, __fmul_rn(w, g[c]), __fmul_rn(w, g[c + 1]));
+        }
+    }
+}
+
+// kernel_input_backward :331-357
+template <typename T>
+__global__ void k_grid_input_bwd(const T* __restrict__ grad, const T* __restrict__ dy_dx, T* __restrict__ grad_inputs,
+                                 uint32_t B, uint32_t D, uint32_t C, uint32_t L, bool point_major) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * D) return;
+    const uint32_t b = t / D, d = t - b * D;
+    const T* dd = dy_dx + (size_t)b * L * D * C;
+    float result = 0.0f;
+    for (uint32_t l = 0; l < L; l++)
+        for (uint32_t c = 0; c < C; c++) {
+            const T* gp = point_major ? grad + ((size_t)b * L + l) * C + c : grad + ((size_t)l * B + b) * C + c;
+            if (sizeof(T) == 4) result = __fmaf_rn(ld_as_float(gp), ld_as_float(dd + l * D * C + d * C + c), result);
+            else result = acc_step(result, ld_as_float(gp), ld_as_float(dd + l * D * C + d * C + c), T());
+        }
+    st_from_float(grad_inputs + t, result);
+}
+
+template <typename T>
+static int launch_bwd(const void* grad, const float* inputs, const int32_t* offsets, void* grad_embeddings, uint32_t B,
+                      uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, bool calc, const void* dy_dx, void* grad_inputs,
+                      uint32_t gridtype, bool ac, uint32_t style, bool pm, cudaStream_t s) {
+    const T* g = (const T*)grad; T* ge = (T*)grad_embeddings;
+    const uint32_t nbx = ceil_div_u32(B, GRID_BLOCK);
+    if (D == 3 && C == 2 && (((uintptr_t)grad_embeddings) & 7) == 0) {
+        const int lpt = g_bwd_lpt;
+#define BWD_FAST(LPT) k_grid_bwd_d3c2<T, LPT><<<dim3(nbx, ceil_div_u32(L, LPT)), GRID_BLOCK, 0, s>>>(g, inputs, offsets, ge, B, L, S, H, gridtype, ac, style, pm, g_bwd_agg)
+        if (lpt >= 16) BWD_FAST(16); else if (lpt >= 8) BWD_FAST(8); else if (lpt >= 4) BWD_FAST(4); else if (lpt >= 2) BWD_FAST(2); else BWD_FAST(1);
+#undef BWD_FAST
+    } else {
+        const dim3 grid(nbx, L);
+#define BWD_GEN(DD, CC) k_grid_bwd_generic<T, DD, CC><<<grid, GRID_BLOCK, 0, s>>>(g, inputs, offsets, ge, B, L, S, H, gridtype, ac, style, pm)
+        if (D == 3) { switch (C) { case 1: BWD_GEN(3, 1); break; case 2: BWD_GEN(3, 2); break; case 4: BWD_GEN(3, 4); break; case 8: BWD_GEN(3, 8); break; default: return NRF_E_UNSUPPORTED; } }
+        else if (D == 2) { switch (C) { case 1: BWD_GEN(2, 1); break; case 2: BWD_GEN(2, 2); break; case 4: BWD_GEN(2, 4); break; case 8: BWD_GEN(2, 8); break; default: return NRF_E_UNSUPPORTED; } }
+        else return NRF_E_UNSUPPORTED;
+#undef BWD_GEN
+    }
+    if (calc) k_grid_input_bwd<T><<<ceil_div_u32((uint64_t)B * D, 256), 256, 0, s>>>(g, (const T*)dy_dx, (T*)grad_inputs, B, D, C, L, pm);
+    return nrf_check_launch();
+}
+
+NRF_EXPORT int nrf_grid_encode_backward(const void* grad, const float* inputs, const void* embeddings, const int32_t* offsets,
+                                        void* grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
+                                        uint32_t H, int calc_grad_inputs, const void* dy_dx, void* grad_inputs,
+                                        uint32_t gridtype, int align_corners, uint32_t style, int dtype, int point_major,
+                                        void* stream) {
+    (void)embeddings;
+    if (B == 0) return NRF_OK;
+    if (!grad || !inputs || !offsets || !grad_embeddings) return NRF_E_INVALID;
+    if (calc_grad_inputs && (!dy_dx || !grad_inputs)) return NRF_E_INVALID;
+    if (L == 0 || L > GRID_MAX_LEVELS) return NRF_E_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == NRF_DTYPE_F32)
+        return launch_bwd<float>(grad, inputs, offsets, grad_embeddings, B, D, C, L, S, H, calc_grad_inputs != 0, dy_dx, grad_inputs, gridtype, align_corners != 0, style, point_major != 0, s);
+    if (dtype == NRF_DTYPE_F16)
+        return launch_bwd<__half>(grad, inputs, offsets, grad_embeddings, B, D, C, L, S, H, calc_grad_inputs != 0, dy_dx, grad_inputs, gridtype, align_corners != 0, style, point_major != 0, s);
+    return NRF_E_UNSUPPORTED;
+}
+
+// ------------------------------------------------------------------------------------------------
+// grid_initialize (kernel_grid_initialize :497-531 and its host loop :534-548), D=3 C=2 f32
+// ------------------------------------------------------------------------------------------------
+__global__ void k_grid_initialize(const float* __restrict__ ref_grid, float* __restrict__ grid, const int32_t* __restrict__ ref_offsets,
+                                  const int32_t* __restrict__ offsets, uint32_t level, float S, uint32_t H, uint32_t Ns) {
+    __shared__ LevelP pr;
+    const uint32_t tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    if (tid == 0) level_setup(pr, ref_offsets, level, 3, S, H, 0, true, 0);
+    __syncthreads();
+    uint32_t pg[3] = { blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y * blockDim.y + threadIdx.y, blockIdx.z * blockDim.z + threadIdx.z };
+    const uint32_t resolution = pr.resolution;
+    if (pg[0] > resolution || pg[1] > resolution || pg[2] > resolution) return;
+    const float2 v = reinterpret_cast<const float2*>(ref_grid)[pr.offset + grid_row<3>(pr, pg)];
+    for (uint32_t s = 0; s < Ns; s++) {
+        LevelP p;
+        level_setup(p, offsets, level, 3, S, H, 0, true, s);
+        reinterpret_cast<float2*>(grid)[p.offset + grid_row<3>(p, pg)] = v;
+    }
+}
+
+NRF_EXPORT int nrf_grid_initialize(const float* ref_embeddings, float* embeddings, const int32_t* ref_offsets,
+                                   const int32_t* offsets, uint32_t L, float S, uint32_t H, uint32_t Ns, void* stream) {
+    if (!ref_embeddings || !embeddings || !ref_offsets || !offsets) return NRF_E_INVALID;
+    if (L == 0 || L > GRID_MAX_LEVELS) return NRF_E_UNSUPPORTED;
+    for (uint32_t level = 0; level < L; level++) {
+        const uint32_t resolution = (uint32_t)floorf(exp2f((float)level * S) * (float)H);   // host mirror of :539
+        const uint32_t nb = ceil_div_u32(resolution + 1, 8);
+        k_grid_initialize<<<dim3(nb, nb, nb), dim3(8, 8, 8), 0, (cudaStream_t)stream>>>(ref_embeddings, embeddings, ref_offsets, offsets, level, S, H, Ns);
+    }
+    return nrf_check_launch();
+}

@@ -1,0 +1,842 @@
+// Ray-marching operator set for sm_100a (C ABI in include/nerfstyle_b200.h).
+//
+// Behavioural contract: /root/reference/raymarching/src/raymarching.cu (cited per function).  The code is
+// written from scratch: every floating-point operation that decides an integer (cell index, sample
+// count) is spelled with explicit round-to-nearest intrinsics (__fmaf_rn/__fmul_rn/__fadd_rn) at exactly the
+// contraction points nvcc chose for the reference kernels, so sample counts and
+// occupancy indices are bit-exact and independent of compiler flags.
+#include "common.cuh"
+#include <float.h>
+
+thread_local int g_nrf_last_cuda_error = 0;
+
+NRF_EXPORT const char* nrf_error_string(int code) {
+    switch (code) {
+        case NRF_OK: return "ok";
+        case NRF_E_INVALID: return "invalid argument";
+        case NRF_E_UNSUPPORTED: return "unsupported configuration";
+        case NRF_E_CUDA: return "CUDA error";
+        default: return "unknown error";
+    }
+}
+NRF_EXPORT int nrf_last_cuda_error(void) { return g_nrf_last_cuda_error; }
+NRF_EXPORT int nrf_version(void) { return 1; }
+NRF_EXPORT int nrf_device_info(int* sm_count, int* cc_major, int* cc_minor, int* l2_bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    cudaDeviceProp p;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&p, dev);
+    if (e != cudaSuccess) { g_nrf_last_cuda_error = (int)e; return NRF_E_CUDA; }
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (l2_bytes) *l2_bytes = p.l2CacheSize;
+    return NRF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small utilities: near/far, spherical coords, Morton codes, bit packing
+// ------------------------------------------------------------------------------------------------
+
+// raymarching.cu:191-244
+__global__ void k_near_far_from_aabb(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                     const float* __restrict__ aabb, uint32_t N, float min_near,
+                                     float* __restrict__ nears, float* __restrict__ fars) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float ox = rays_o[3 * n], oy = rays_o[3 * n + 1], oz = rays_o[3 * n + 2];
+    const float dx = rays_d[3 * n], dy = rays_d[3 * n + 1], dz = rays_d[3 * n + 2];
+    const float rdx = __fdiv_rn(1.0f, dx), rdy = __fdiv_rn(1.0f, dy), rdz = __fdiv_rn(1.0f, dz);
+    float near = __fmul_rn(__fsub_rn(aabb[0], ox), rdx), far = __fmul_rn(__fsub_rn(aabb[3], ox), rdx);
+    if (near > far) { float t = near; near = far; far = t; }
+    float near_y = __fmul_rn(__fsub_rn(aabb[1], oy), rdy), far_y = __fmul_rn(__fsub_rn(aabb[4], oy), rdy);
+    if (near_y > far_y) { float t = near_y; near_y = far_y; far_y = t; }
+    if (near > far_y || near_y > far) { nears[n] = FLT_MAX; fars[n] = FLT_MAX; return; }
+    if (near_y > near) near = near_y;
+    if (far_y < far) far = far_y;
+    float near_z = __fmul_rn(__fsub_rn(aabb[2], oz), rdz), far_z = __fmul_rn(__fsub_rn(aabb[5], oz), rdz);
+    if (near_z > far_z) { float t = near_z; near_z = far_z; far_z = t; }
+    if (near > far_z || near_z > far) { nears[n] = FLT_MAX; fars[n] = FLT_MAX; return; }
+    if (near_z > near) near = near_z;
+    if (far_z < far) far = far_z;
+    if (near < min_near) near = min_near;
+    nears[n] = near;
+    fars[n] = far;
+}
+
+NRF_EXPORT int nrf_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N,
+                                      float min_near, float* nears, float* fars, void* stream) {
+    if (N == 0) return NRF_OK;
+    if (!rays_o || !rays_d || !aabb || !nears || !fars) return NRF_E_INVALID;
+    k_near_far_from_aabb<<<ceil_div_u32(N, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, aabb, N, min_near, nears, fars);
+    return nrf_check_launch();
+}
+
+// raymarching.cu:262-297
+__global__ void k_sph_from_ray(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float radius,
+                               uint32_t N, float* __restrict__ coords) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float RPI = 0.3183098861837907f;
+    const float ox = rays_o[3 * n], oy = rays_o[3 * n + 1], oz = rays_o[3 * n + 2];
+    const float dx = rays_d[3 * n], dy = rays_d[3 * n + 1], dz = rays_d[3 * n + 2];
+    const float A = dx * dx + dy * dy + dz * dz;
+    const float B = ox * dx + oy * dy + oz * dz;
+    const float C = ox * ox + oy * oy + oz * oz - radius * radius;
+    const float t = (-B + sqrtf(B * B - A * C)) / A;
+    const float x = ox + t * dx, y = oy + t * dy, z = oz + t * dz;
+    const float theta = atan2f(sqrtf(x * x + z * z), y);
+    const float phi = atan2f(z, x);
+    coords[2 * n] = 2 * theta * RPI - 1;
+    coords[2 * n + 1] = phi * RPI;
+}
+
+NRF_EXPORT int nrf_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords,
+                                void* stream) {
+    if (N == 0) return NRF_OK;
+    if (!rays_o || !rays_d || !coords) return NRF_E_INVALID;
+    k_sph_from_ray<<<ceil_div_u32(N, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, radius, N, coords);
+    return nrf_check_launch();
+}
+
+// raymarching.cu:56-81
+__device__ __forceinline__ uint32_t expand_bits(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+__device__ __forceinline__ uint32_t morton3D_dev(uint32_t x, uint32_t y, uint32_t z) {
+    return expand_bits(x) | (expand_bits(y) << 1) | (expand_bits(z) << 2);
+}
+__device__ __forceinline__ uint32_t morton3D_invert_dev(uint32_t x) {
+    x = x & 0x49249249u;
+    x = (x | (x >> 2)) & 0xc30c30c3u;
+    x = (x | (x >> 4)) & 0x0f00f00fu;
+    x = (x | (x >> 8)) & 0xff0000ffu;
+    x = (x | (x >> 16)) & 0x0000ffffu;
+    return x;
+}
+
+// raymarching.cu:313-325
+__global__ void k_morton3D(const int32_t* __restrict__ coords, uint32_t N, int32_t* __restrict__ indices) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    indices[n] = (int32_t)morton3D_dev((uint32_t)coords[3 * n], (uint32_t)coords[3 * n + 1], (uint32_t)coords[3 * n + 2]);
+}
+// raymarching.cu:336-353
+__global__ void k_morton3D_invert(const int32_t* __restrict__ indices, uint32_t N, int32_t* __restrict__ coords) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int32_t ind = indices[n];
+    coords[3 * n + 0] = (int32_t)morton3D_invert_dev((uint32_t)(ind >> 0));
+    coords[3 * n + 1] = (int32_t)morton3D_invert_dev((uint32_t)(ind >> 1));
+    coords[3 * n + 2] = (int32_t)morton3D_invert_dev((uint32_t)(ind >> 2));
+}
+NRF_EXPORT int nrf_morton3D(const int32_t* coords, uint32_t N, int32_t* indices, void* stream) {
+    if (N == 0) return NRF_OK;
+    if (!coords || !indices) return NRF_E_INVALID;
+    k_morton3D<<<ceil_div_u32(N, 256), 256, 0, (cudaStream_t)stream>>>(coords, N, indices);
+    return nrf_check_launch();
+}
+NRF_EXPORT int nrf_morton3D_invert(const int32_t* indices, uint32_t N, int32_t* coords, void* stream) {
+    if (N == 0) return NRF_OK;
+    if (!coords || !indices) return NRF_E_INVALID;
+    k_morton3D_invert<<<ceil_div_u32(N, 256), 256, 0, (cudaStream_t)stream>>>(indices, N, coords);
+    return nrf_check_launch();
+}
+
+// raymarching.cu:367-388.  One thread packs 4 bytes (32 cells = 8 x 16-byte loads) so that global
+// stores are 4 bytes wide; the tail (N % 4 bytes) falls back to one byte per thread.
+__global__ void k_packbits4(const float4* __restrict__ grid4, uint32_t N4, float thresh, uint32_t* __restrict__ out) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N4) return;
+    uint32_t word = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const float4 v = __ldg(grid4 + (size_t)n * 8 + j);
+        uint32_t nib = (v.x > thresh ? 1u : 0u) | (v.y > thresh ? 2u : 0u) | (v.z > thresh ? 4u : 0u) | (v.w > thresh ? 8u : 0u);
+        word |= nib << (4 * j);
+    }
+    out[n] = word;
+}
+__global__ void k_packbits1(const float* __restrict__ grid, uint32_t n0, uint32_t N, float thresh, uint8_t* __restrict__ out) {
+    const uint32_t n = n0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    uint8_t bits = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) bits |= (grid[(size_t)n * 8 + i] > thresh) ? (uint8_t)(1u << i) : 0;
+    out[n] = bits;
+}
+NRF_EXPORT int nrf_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield, void* stream) {
+    if (N == 0) return NRF_OK;
+    if (!grid || !bitfield) return NRF_E_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    uint32_t N4 = 0;
+    if ((((uintptr_t)grid) & 15) == 0 && (((uintptr_t)bitfield) & 3) == 0) N4 = N / 4;
+    if (N4) k_packbits4<<<ceil_div_u32(N4, 256), 256, 0, s>>>((const float4*)grid, N4, density_thresh, (uint32_t*)bitfield);
+    if (N4 * 4 < N) k_packbits1<<<ceil_div_u32(N - N4 * 4, 256), 256, 0, s>>>(grid, N4 * 4, N, density_thresh, bitfield);
+    return nrf_check_launch();
+}
+
+// ------------------------------------------------------------------------------------------------
+// The marching state machine shared by train and inference marching
+// (raymarching.cu:436-500 / :1037-1119; geometry normative in SURVEY.md 8a.2, contraction 8a.3)
+// ------------------------------------------------------------------------------------------------
+struct MarchCtx {
+    float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz, sx, sy, sz;
+    float rH, H3, Hf, Hm1, bound, nbound, dt_gamma, dt_min, dt_max;
+    int Cm1;
+};
+
+__device__ __forceinline__ void march_init(MarchCtx& c, const float* __restrict__ o, const float* __restrict__ d,
+                                           float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H) {
+    c.ox = o[0]; c.oy = o[1]; c.oz = o[2];
+    c.dx = d[0]; c.dy = d[1]; c.dz = d[2];
+    c.rdx = __fdiv_rn(1.0f, c.dx); c.rdy = __fdiv_rn(1.0f, c.dy); c.rdz = __fdiv_rn(1.0f, c.dz);
+    c.sx = 0.5f * copysignf(1.0f, c.dx); c.sy = 0.5f * copysignf(1.0f, c.dy); c.sz = 0.5f * copysignf(1.0f, c.dz);
+    c.Hf = (float)H;
+    c.Hm1 = (float)(H - 1);
+    c.rH = __fdiv_rn(1.0f, c.Hf);
+    c.H3 = (float)(H * H * H);
+    c.bound = bound; c.nbound = -bound;
+    c.dt_gamma = dt_gamma;
+    const float two_sqrt3 = 2.0f * 1.7320508075688772f;
+    c.dt_min = __fdiv_rn(two_sqrt3, (float)max_steps);
+    c.dt_max = __fdiv_rn(__fmul_rn(two_sqrt3, (float)(1 << (C - 1))), c.Hf);
+    c.Cm1 = (int)C - 1;
+}
+
+// frexpf exponent clamped to [0, Cm1] (raymarching.cu:42-54): for finite v >= 0 the frexp exponent is
+// (biased exponent - 126); zero / denormals clamp to 0 either way.
+__device__ __forceinline__ int mip_exponent(float v, int Cm1) {
+    const int e = (int)((__float_as_uint(v) >> 23) & 0xffu) - 126;
+    return min(Cm1, max(0, e));
+}
+
+__device__ __forceinline__ float march_t0(const MarchCtx& c, float t, float noise) {
+    return __fmaf_rn(noise, nrf_clamp(__fmul_rn(t, c.dt_gamma), c.dt_min, c.dt_max), t);
+}
+
+// One visit of the loop body at t.  Returns true when the cell is occupied (x,y,z,dt = the sample); else
+// advances t past the empty cell exactly like the reference's do/while and returns false.
+__device__ __forceinline__ bool march_visit(const MarchCtx& c, const uint8_t* __restrict__ grid, float& t,
+                                            float& x, float& y, float& z, float& dt) {
+    x = nrf_clamp(__fmaf_rn(c.dx, t, c.ox), c.nbound, c.bound);
+    y = nrf_clamp(__fmaf_rn(c.dy, t, c.oy), c.nbound, c.bound);
+    z = nrf_clamp(__fmaf_rn(c.dz, t, c.oz), c.nbound, c.bound);
+    dt = nrf_clamp(__fmul_rn(t, c.dt_gamma), c.dt_min, c.dt_max);
+    const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+    const int level = max(mip_exponent(mx, c.Cm1), mip_exponent(__fmul_rn(dt, c.Hf) * 0.5f, c.Cm1));
+    const float mip_bound = fminf(__uint_as_float((uint32_t)(127 + level) << 23), c.bound);
+    const float mip_rbound = __fdiv_rn(1.0f, mip_bound);
+    const int nx = (int)nrf_clamp(__fmul_rn(0.5f * __fmaf_rn(x, mip_rbound, 1.0f), c.Hf), 0.0f, c.Hm1);
+    const int ny = (int)nrf_clamp(__fmul_rn(0.5f * __fmaf_rn(y, mip_rbound, 1.0f), c.Hf), 0.0f, c.Hm1);
+    const int nz = (int)nrf_clamp(__fmul_rn(0.5f * __fmaf_rn(z, mip_rbound, 1.0f), c.Hf), 0.0f, c.Hm1);
+    const uint32_t index = (uint32_t)__fmaf_rn(c.H3, (float)level, (float)morton3D_dev((uint32_t)nx, (uint32_t)ny, (uint32_t)nz));
+    const bool occ = (__ldg(grid + (index >> 3)) >> (index & 7u)) & 1u;
+    if (occ) return true;
+    const float tx = __fmul_rn(c.rdx, __fsub_rn(__fmul_rn(mip_bound, __fmaf_rn(__fmul_rn(c.rH, __fadd_rn(c.sx, __fadd_rn((float)nx, 0.5f))), 2.0f, -1.0f)), x));
+    const float ty = __fmul_rn(c.rdy, __fsub_rn(__fmul_rn(mip_bound, __fmaf_rn(__fmul_rn(c.rH, __fadd_rn(c.sy, __fadd_rn((float)ny, 0.5f))), 2.0f, -1.0f)), y));
+    const float tz = __fmul_rn(c.rdz, __fsub_rn(__fmul_rn(mip_bound, __fmaf_rn(__fmul_rn(c.rH, __fadd_rn(c.sz, __fadd_rn((float)nz, 0.5f))), 2.0f, -1.0f)), z));
+    const float tt = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+    do {
+        t = __fadd_rn(t, nrf_clamp(__fmul_rn(t, c.dt_gamma), c.dt_min, c.dt_max));
+    } while (t < tt);
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// march_rays_train: count -> scan -> write   (reference: one kernel, two passes + 2 atomics per ray,
+// raymarching.cu:411-589; here offsets are the exclusive scan in ray order = one valid schedule of the
+// reference's racing atomicAdd, and deterministic).
+// ------------------------------------------------------------------------------------------------
+#define MARCH_BLOCK 64
+
+// rays[n] = (n, block-local exclusive offset, count); block_sums[blockIdx.x] = sum of counts
+__global__ void __launch_bounds__(MARCH_BLOCK)
+k_march_count(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const uint8_t* __restrict__ grid,
+              float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+              const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ noises,
+              int32_t* __restrict__ rays, uint32_t* __restrict__ block_sums) {
+    const uint32_t n = blockIdx.x * MARCH_BLOCK + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t num_steps = 0;
+    if (n < N) {
+        MarchCtx c;
+        march_init(c, rays_o + 3 * (size_t)n, rays_d + 3 * (size_t)n, bound, dt_gamma, max_steps, C, H);
+        const float far = fars[n];
+        float t = march_t0(c, nears[n], noises ? noises[n] : 0.0f);
+        float x, y, z, dt;
+        while (t < far && num_steps < max_steps) {
+            if (march_visit(c, grid, t, x, y, z, dt)) { num_steps++; t = __fadd_rn(t, dt); }
+        }
+    }
+    __shared__ uint32_t warp_tot[MARCH_BLOCK / 32];
+    const uint32_t incl = warp_scan_add_u32(num_steps, lane);
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t base = 0;
+#pragma unroll
+    for (int w = 0; w < MARCH_BLOCK / 32; w++) if (w < warp) base += warp_tot[w];
+    if (n < N) {
+        rays[3 * (size_t)n + 0] = (int32_t)n;
+        rays[3 * (size_t)n + 1] = (int32_t)(base + incl - num_steps);
+        rays[3 * (size_t)n + 2] = (int32_t)num_steps;
+    }
+    if (threadIdx.x == MARCH_BLOCK - 1) block_sums[blockIdx.x] = base + incl;
+}
+
+// single block: exclusive scan of block_sums (in place) starting from counter[0]; updates the counter.
+__global__ void __launch_bounds__(1024)
+k_scan_block_sums(uint32_t* __restrict__ block_sums, uint32_t nb, int32_t* __restrict__ counter, uint32_t N) {
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = counter ? (uint32_t)counter[0] : 0u;
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < nb; i0 += 1024) {
+        const uint32_t i = i0 + threadIdx.x;
+        const uint32_t v = i < nb ? block_sums[i] : 0u;
+        const uint32_t incl = warp_scan_add_u32(v, lane);
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = warp_tot[lane];
+            const uint32_t wi = warp_scan_add_u32(w, lane);
+            warp_tot[lane] = wi - w;   // exclusive over warps
+        }
+        __syncthreads();
+        const uint32_t excl = carry + warp_tot[warp] + incl - v;
+        if (i < nb) block_sums[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && counter) {
+        counter[0] = (int32_t)carry;
+        counter[1] = counter[1] + (int32_t)N;
+    }
+}
+
+__global__ void k_add_block_offsets(int32_t* __restrict__ rays, const uint32_t* __restrict__ block_offs, uint32_t N) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    rays[3 * (size_t)n + 1] += (int32_t)block_offs[n / MARCH_BLOCK];
+}
+
+NRF_EXPORT uint64_t nrf_march_scratch_bytes(uint32_t N) {
+    return ((uint64_t)ceil_div_u32(N, MARCH_BLOCK) + 1024) * sizeof(uint32_t);
+}
+
+NRF_EXPORT int nrf_march_rays_train_count(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                                          float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                          const float* nears, const float* fars, const float* noises,
+                                          int32_t* rays, int32_t* counter, void* scratch, void* stream) {
+    if (N == 0) return NRF_OK;
+    if (!rays_o || !rays_d || !grid || !nears || !fars || !rays || !scratch) return NRF_E_INVALID;
+    if (C < 1 || C > 24 || H < 1 || H > 1024) return NRF_E_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t nb = ceil_div_u32(N, MARCH_BLOCK);
+    uint32_t* block_sums = (uint32_t*)scratch;
+    k_march_count<<<nb, MARCH_BLOCK, 0, s>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, block_sums);
+    k_scan_block_sums<<<1, 1024, 0, s>>>(block_sums, nb, counter, N);
+    k_add_block_offsets<<<ceil_div_u32(N, 256), 256, 0, s>>>(rays, block_sums, N);
+    return nrf_check_launch();
+}
+
+// second pass: thread per ray re-marches and writes its samples (raymarching.cu:519-588)
+__global__ void __launch_bounds__(MARCH_BLOCK)
+k_march_write(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ z_hats,
+              const uint8_t* __restrict__ grid, float bound, float dt_gamma, uint32_t max_steps, bool is_ndc,
+              uint32_t N, uint32_t C, uint32_t H, uint32_t M, uint32_t rows,
+              const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ noises,
+              const int32_t* __restrict__ rays, float* __restrict__ xyzs, float* __restrict__ dirs,
+              float* __restrict__ deltas) {
+    const uint32_t n = blockIdx.x * MARCH_BLOCK + threadIdx.x;
+    if (n >= N) return;
+    const uint32_t point_index = (uint32_t)rays[3 * (size_t)n + 1];
+    const uint32_t num_steps = (uint32_t)rays[3 * (size_t)n + 2];
+    if (num_steps == 0) return;
+    if (point_index + num_steps >= M) {
+        // dropped ray (raymarching.cu:517): its slots stay zero in the reference's zero-filled buffers
+        for (uint32_t i = point_index; i < min(point_index + num_steps, rows); i++) {
+            xyzs[3 * (size_t)i] = 0; xyzs[3 * (size_t)i + 1] = 0; xyzs[3 * (size_t)i + 2] = 0;
+            dirs[3 * (size_t)i] = 0; dirs[3 * (size_t)i + 1] = 0; dirs[3 * (size_t)i + 2] = 0;
+            reinterpret_cast<float4*>(deltas)[i] = make_float4(0, 0, 0, 0);
+        }
+        return;
+    }
+    MarchCtx c;
+    march_init(c, rays_o + 3 * (size_t)n, rays_d + 3 * (size_t)n, bound, dt_gamma, max_steps, C, H);
+    const float far = fars[n];
+    float t = march_t0(c, nears[n], noises ? noises[n] : 0.0f);
+    float* px = xyzs + 3 * (size_t)point_index;
+    float* pd = dirs + 3 * (size_t)point_index;
+    float4* pl = reinterpret_cast<float4*>(deltas) + point_index;
+    uint32_t step = 0;
+    float last_t = t;
+    float last_z = nrf_clamp(__fmaf_rn(c.dz, t, c.oz), c.nbound, c.bound);
+    const float zh = is_ndc ? z_hats[n] : 1.0f;
+    float x, y, z, dt;
+    while (t < far && step < num_steps) {
+        if (march_visit(c, grid, t, x, y, z, dt)) {
+            px[0] = x; px[1] = y; px[2] = z;
+            pd[0] = c.dx; pd[1] = c.dy; pd[2] = c.dz;
+            t = __fadd_rn(t, dt);
+            float4 dl = make_float4(dt, __fsub_rn(t, last_t), 0.0f, 0.0f);
+            last_t = t;
+            if (is_ndc) {   // raymarching.cu:566-571 (train updates last_z = z)
+                const float new_z = nrf_clamp(__fmaf_rn(c.dz, t, c.oz), c.nbound, c.bound);
+                dl.z = (2 / (new_z - 1) - 2 / (z - 1)) / zh;
+                dl.w = (2 / (new_z - 1) - 2 / (last_z - 1)) / zh;
+                last_z = z;
+            }
+            *pl = dl;
+            px += 3; pd += 3; pl += 1; step++;
+        }
+    }
+}
+
+__global__ void k_zero_rows(float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
+                            uint32_t from, uint32_t to) {
+    const uint32_t i = from + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= to) return;
+    xyzs[3 * (size_t)i] = 0; xyzs[3 * (size_t)i + 1] = 0; xyzs[3 * (size_t)i + 2] = 0;
+    dirs[3 * (size_t)i] = 0; dirs[3 * (size_t)i + 1] = 0; dirs[3 * (size_t)i + 2] = 0;
+    reinterpret_cast<float4*>(deltas)[i] = make_float4(0, 0, 0, 0);
+}
+
+NRF_EXPORT int nrf_march_rays_train_write(const float* rays_o, const float* rays_d, const float* z_hats,
+                                          const uint8_t* grid, float bound, float dt_gamma, uint32_t max_steps,
+                                          int is_ndc, uint32_t N, uint32_t C, uint32_t H, uint32_t M, uint32_t rows,
+                                          uint32_t zero_from, const float* nears, const float* fars,
+                                          const float* noises, const int32_t* rays, float* xyzs, float* dirs,
+                                          float* deltas, void* stream) {
+    if (N == 0) return NRF_OK;
+    if (!rays_o || !rays_d || !grid || !nears || !fars || !rays || !xyzs || !dirs || !deltas) return NRF_E_INVALID;
+    if (is_ndc && !z_hats) return NRF_E_INVALID;
+    if ((((uintptr_t)deltas) & 15) != 0) return NRF_E_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (zero_from < rows) k_zero_rows<<<ceil_div_u32(rows - zero_from, 256), 256, 0, s>>>(xyzs, dirs, deltas, zero_from, rows);
+    k_march_write<<<ceil_div_u32(N, MARCH_BLOCK), MARCH_BLOCK, 0, s>>>(rays_o, rays_d, z_hats, grid, bound, dt_gamma, max_steps,
+                                                                  is_ndc != 0, N, C, H, M, rows, nears, fars, noises, rays,
+                                                                  xyzs, dirs, deltas);
+    return nrf_check_launch();
+}
+
+NRF_EXPORT int nrf_march_rays_train(const float* rays_o, const float* rays_d, const float* z_hats, const uint8_t* grid,
+                                    float bound, float dt_gamma, uint32_t max_steps, int is_ndc, uint32_t N, uint32_t C,
+                                    uint32_t H, uint32_t M, const float* nears, const float* fars, float* xyzs,
+                                    float* dirs, float* deltas, int32_t* rays, int32_t* counter, const float* noises,
+                                    void* scratch, void* stream) {
+    int rc = nrf_march_rays_train_count(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises,
+                                        rays, counter, scratch, stream);
+    if (rc != NRF_OK) return rc;
+    return nrf_march_rays_train_write(rays_o, rays_d, z_hats, grid, bound, dt_gamma, max_steps, is_ndc, N, C, H, M, M, M,
+                                      nears, fars, noises, rays, xyzs, dirs, deltas, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// composite_rays_train forward / backward as per-ray segmented scans: one warp per ray, 32 consecutive
+// samples per step (coalesced), transmittance by a multiplicative warp scan, early termination by ballot.
+// Contract: raymarching.cu:807-879 (fwd), :905-986 (bwd); normative restatement SURVEY.md 8a.4.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float alpha_from(float sigma, float delta) {
+    // 1 - __expf(-sigma*delta): the reference compiles to mul, mul by -log2(e), ex2.approx, sub
+    float e;
+    asm("ex2.approx.f32 %0, %1;" : "=f"(e) : "f"(__fmul_rn(__fmul_rn(sigma, delta), -1.4426950408889634f)));
+    return 1.0f - e;
+}
+
+#define COMP_WARPS 4
+
+template <int CMAX>
+__global__ void __launch_bounds__(COMP_WARPS * 32)
+k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas,
+                      const int32_t* __restrict__ rays, uint32_t M, uint32_t N, uint32_t C, float T_thresh, bool is_ndc,
+                      float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image) {
+    const uint32_t n = blockIdx.x * COMP_WARPS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const uint32_t index = (uint32_t)rays[3 * (size_t)n], offset = (uint32_t)rays[3 * (size_t)n + 1], num_steps = (uint32_t)rays[3 * (size_t)n + 2];
+    float acc[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; c++) acc[c] = 0.0f;
+    float ws = 0.0f, d = 0.0f;
+    if (num_steps != 0 && offset + num_steps < M) {
+        float T_run = 1.0f, t_run = 0.0f;
+        for (uint32_t base = 0; base < num_steps; base += 32) {
+            const uint32_t i = base + lane;
+            const bool valid = i < num_steps;
+            float sigma = 0.0f, d0 = 0.0f, d1 = 0.0f;
+            if (valid) {
+                const float4 dl = __ldg(reinterpret_cast<const float4*>(deltas) + offset + i);
+                sigma = __ldg(sigmas + offset + i);
+                d0 = is_ndc ? dl.z : dl.x;
+                d1 = is_ndc ? dl.w : dl.y;
+            }
+            const float alpha = valid ? alpha_from(sigma, d0) : 0.0f;
+            const float P = warp_scan_mul(1.0f - alpha, lane);            // inclusive product
+            float Pex = __shfl_up_sync(NRF_FULL_MASK, P, 1);
+            if (lane == 0) Pex = 1.0f;
+            const float T_before = T_run * Pex, T_after = T_run * P;
+            const uint32_t term = __ballot_sync(NRF_FULL_MASK, valid && (T_after < T_thresh));
+            const int last = term ? (__ffs(term) - 1) : 31;               // the terminating sample still counts (fwd)
+            const float w = (valid && lane <= last) ? alpha * T_before : 0.0f;
+            const float tsum = warp_scan_add(d1, lane);
+            d = __fmaf_rn(w, t_run + tsum, d);
+            ws += w;
+            if (w != 0.0f) {
+                const float* r = rgbs + (size_t)(offset + i) * C;
+#pragma unroll
+                for (int c = 0; c < CMAX; c++) if (c < (int)C) acc[c] = __fmaf_rn(w, __ldg(r + c), acc[c]);
+            }
+            if (term) break;
+            T_run = __shfl_sync(NRF_FULL_MASK, T_after, 31);
+            t_run += __shfl_sync(NRF_FULL_MASK, tsum, 31);
+        }
+        ws = warp_sum(ws);
+        d = warp_sum(d);
+#pragma unroll
+        for (int c = 0; c < CMAX; c++) acc[c] = warp_sum(acc[c]);
+    }
+    if (lane == 0) { weights_sum[index] = ws; depth[index] = d; }
+#pragma unroll
+    for (int c = 0; c < CMAX; c++) if (c < (int)C && lane == (c & 31)) image[(size_t)index * C + c] = acc[c];
+}
+
+// generic fallback (any C): one thread per ray, serial like the reference
+__global__ void k_composite_train_fwd_serial(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                             const float* __restrict__ deltas, const int32_t* __restrict__ rays, uint32_t M,
+                                             uint32_t N, uint32_t C, float T_thresh, bool is_ndc, float* __restrict__ weights_sum,
+                                             float* __restrict__ depth, float* __restrict__ image) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const uint32_t index = (uint32_t)rays[3 * (size_t)n], offset = (uint32_t)rays[3 * (size_t)n + 1], num_steps = (uint32_t)rays[3 * (size_t)n + 2];
+    float* img = image + (size_t)index * C;
+    for (uint32_t c = 0; c < C; c++) img[c] = 0.0f;
+    if (num_steps == 0 || offset + num_steps >= M) { weights_sum[index] = 0; depth[index] = 0; return; }
+    float T = 1.0f, ws = 0, t = 0, d = 0;
+    for (uint32_t i = 0; i < num_steps; i++) {
+        const float4 dl = reinterpret_cast<const float4*>(deltas)[offset + i];
+        const float alpha = alpha_from(sigmas[offset + i], is_ndc ? dl.z : dl.x);
+        const float w = alpha * T;
+        const float* r = rgbs + (size_t)(offset + i) * C;
+        for (uint32_t c = 0; c < C; c++) img[c] = __fmaf_rn(w, r[c], img[c]);
+        t += is_ndc ? dl.w : dl.y;
+        d = __fmaf_rn(w, t, d);
+        ws += w;
+        T *= 1.0f - alpha;
+        if (T < T_thresh) break;
+    }
+    weights_sum[index] = ws; depth[index] = d;
+}
+
+NRF_EXPORT int nrf_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas,
+                                                const int32_t* rays, uint32_t M, uint32_t N, uint32_t C, float T_thresh,
+                                                int is_ndc, float* weights_sum, float* depth, float* image, void* stream) {
+    if (N == 0) return NRF_OK;
+    if (!sigmas || !rgbs || !deltas || !rays || !weights_sum || !depth || !image) return NRF_E_INVALID;
+    if ((((uintptr_t)deltas) & 15) != 0) return NRF_E_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t nb = ceil_div_u32(N, COMP_WARPS);
+    const bool ndc = is_ndc != 0;
+#define LAUNCH_FWD(CM) k_composite_train_fwd<CM><<<nb, COMP_WARPS * 32, 0, s>>>(sigmas, rgbs, deltas, rays, M, N, C, T_thresh, ndc, weights_sum, depth, image)
+    if (C <= 4) LAUNCH_FWD(4);
+    else if (C <= 8) LAUNCH_FWD(8);
+    else if (C <= 16) LAUNCH_FWD(16);
+    else if (C <= 32) LAUNCH_FWD(32);
+    else k_composite_train_fwd_serial<<<ceil_div_u32(N, 128), 128, 0, s>>>(sigmas, rgbs, deltas, rays, M, N, C, T_thresh, ndc, weights_sum, depth, image);
+#undef LAUNCH_FWD
+    return nrf_check_launch();
+}
+
+template <int CMAX>
+__global__ void __launch_bounds__(COMP_WARPS * 32)
+k_composite_train_bwd(const float* __restrict__ grad_ws, const float* __restrict__ grad_image, const float* __restrict__ sigmas,
+                      const float* __restrict__ rgbs, const float* __restrict__ deltas, const int32_t* __restrict__ rays, bool is_ndc,
+                      const float* __restrict__ weights_sum, const float* __restrict__ image, uint32_t M, uint32_t N, uint32_t C,
+                      float T_thresh, float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs) {
+    const uint32_t n = blockIdx.x * COMP_WARPS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const uint32_t index = (uint32_t)rays[3 * (size_t)n], offset = (uint32_t)rays[3 * (size_t)n + 1], num_steps = (uint32_t)rays[3 * (size_t)n + 2];
+    if (num_steps == 0 || offset + num_steps >= M) return;
+    float g[CMAX];
+    float G_total = 0.0f;     // sum_c g_c * image_c
+#pragma unroll
+    for (int c = 0; c < CMAX; c++) {
+        g[c] = (c < (int)C) ? __ldg(grad_image + (size_t)index * C + c) : 0.0f;
+        if (c < (int)C) G_total = __fmaf_rn(g[c], __ldg(image + (size_t)index * C + c), G_total);
+    }
+    const float ws_term = __ldg(grad_ws + index) * (1.0f - __ldg(weights_sum + index));
+    float T_run = 1.0f, pre_run = 0.0f;
+    for (uint32_t base = 0; base < num_steps; base += 32) {
+        const uint32_t i = base + lane;
+        const bool valid = i < num_steps;
+        float sigma = 0.0f, d0 = 0.0f;
+        float rgb[CMAX];
+        float gdot = 0.0f;    // g . rgb_i
+        if (valid) {
+            const float4 dl = __ldg(reinterpret_cast<const float4*>(deltas) + offset + i);
+            sigma = __ldg(sigmas + offset + i);
+            d0 = is_ndc ? dl.z : dl.x;
+            const float* r = rgbs + (size_t)(offset + i) * C;
+#pragma unroll
+            for (int c = 0; c < CMAX; c++) {
+                rgb[c] = (c < (int)C) ? __ldg(r + c) : 0.0f;
+                gdot = __fmaf_rn(g[c], rgb[c], gdot);
+            }
+        }
+        const float alpha = valid ? alpha_from(sigma, d0) : 0.0f;
+        const float P = warp_scan_mul(1.0f - alpha, lane);
+        float Pex = __shfl_up_sync(NRF_FULL_MASK, P, 1);
+        if (lane == 0) Pex = 1.0f;
+        const float T_before = T_run * Pex, T_after = T_run * P;
+        const uint32_t term = __ballot_sync(NRF_FULL_MASK, valid && (T_after < T_thresh));
+        const int last = term ? (__ffs(term) - 1) : 32;
+        // the terminating sample contributes to rgbs_buf but gets no gradient (raymarching.cu:954-961)
+        const float w = (valid && lane <= last) ? alpha * T_before : 0.0f;
+        const float pre = pre_run + warp_scan_add(w * gdot, lane);        // sum_{j<=i} w_j (g . rgb_j)
+        if (valid && lane < last) {
+            float* gr = grad_rgbs + (size_t)(offset + i) * C;
+#pragma unroll
+            for (int c = 0; c < CMAX; c++) if (c < (int)C) gr[c] = g[c] * w;
+            grad_sigmas[offset + i] = d0 * (__fmaf_rn(T_after, gdot, -(G_total - pre)) + ws_term);
+        }
+        if (term) break;
+        T_run = __shfl_sync(NRF_FULL_MASK, T_after, 31);
+        pre_run = __shfl_sync(NRF_FULL_MASK, pre, 31);
+    }
+}
+
+__global__ void k_composite_train_bwd_serial(const float* __restrict__ grad_ws, const float* __restrict__ grad_image,
+                                             const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                             const float* __restrict__ deltas, const int32_t* __restrict__ rays, bool is_ndc,
+                                             const float* __restrict__ weights_sum, const float* __restrict__ image, uint32_t M,
+                                             uint32_t N, uint32_t C, float T_thresh, float* __restrict__ grad_sigmas,
+                                             float* __restrict__ grad_rgbs) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const uint32_t index = (uint32_t)rays[3 * (size_t)n], offset = (uint32_t)rays[3 * (size_t)n + 1], num_steps = (uint32_t)rays[3 * (size_t)n + 2];
+    if (num_steps == 0 || offset + num_steps >= M) return;
+    const float* gi = grad_image + (size_t)index * C;
+    const float* img = image + (size_t)index * C;
+    float G_total = 0.0f;
+    for (uint32_t c = 0; c < C; c++) G_total = __fmaf_rn(gi[c], img[c], G_total);
+    const float ws_term = grad_ws[index] * (1.0f - weights_sum[index]);
+    float T = 1.0f, pre = 0.0f;
+    for (uint32_t i = 0; i < num_steps; i++) {
+        const float4 dl = reinterpret_cast<const float4*>(deltas)[offset + i];
+        const float d0 = is_ndc ? dl.z : dl.x;
+        const float alpha = alpha_from(sigmas[offset + i], d0);
+        const float w = alpha * T;
+        const float* r = rgbs + (size_t)(offset + i) * C;
+        float gdot = 0.0f;
+        for (uint32_t c = 0; c < C; c++) gdot = __fmaf_rn(gi[c], r[c], gdot);
+        pre = __fmaf_rn(w, gdot, pre);
+        T *= 1.0f - alpha;
+        if (T < T_thresh) break;
+        float* gr = grad_rgbs + (size_t)(offset + i) * C;
+        for (uint32_t c = 0; c < C; c++) gr[c] = gi[c] * w;
+        grad_sigmas[offset + i] = d0 * (__fmaf_rn(T, gdot, -(G_total - pre)) + ws_term);
+    }
+}
+
+NRF_EXPORT int nrf_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image, const float* sigmas,
+                                                 const float* rgbs, const float* deltas, const int32_t* rays, int is_ndc,
+                                                 const float* weights_sum, const float* image, uint32_t M, uint32_t N,
+                                                 uint32_t C, float T_thresh, float* grad_sigmas, float* grad_rgbs,
+                                                 void* stream) {
+    if (N == 0) return NRF_OK;
+    if (!grad_weights_sum || !grad_image || !sigmas || !rgbs || !deltas || !rays || !weights_sum || !image || !grad_sigmas || !grad_rgbs)
+        return NRF_E_INVALID;
+    if ((((uintptr_t)deltas) & 15) != 0) return NRF_E_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t nb = ceil_div_u32(N, COMP_WARPS);
+    const bool ndc = is_ndc != 0;
+#define LAUNCH_BWD(CM) k_composite_train_bwd<CM><<<nb, COMP_WARPS * 32, 0, s>>>(grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays, ndc, weights_sum, image, M, N, C, T_thresh, grad_sigmas, grad_rgbs)
+    if (C <= 4) LAUNCH_BWD(4);
+    else if (C <= 8) LAUNCH_BWD(8);
+    else if (C <= 16) LAUNCH_BWD(16);
+    else if (C <= 32) LAUNCH_BWD(32);
+    else k_composite_train_bwd_serial<<<ceil_div_u32(N, 128), 128, 0, s>>>(grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays, ndc, weights_sum, image, M, N, C, T_thresh, grad_sigmas, grad_rgbs);
+#undef LAUNCH_BWD
+    return nrf_check_launch();
+}
+
+// ------------------------------------------------------------------------------------------------
+// inference: march_rays (raymarching.cu:1005-1120) / composite_rays (:1134-1231) / alive-ray compaction
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays_alive, const float* __restrict__ rays_t,
+             const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ z_hats, float bound,
+             float dt_gamma, uint32_t max_steps, bool is_ndc, uint32_t C, uint32_t H, const uint8_t* __restrict__ grid,
+             const float* __restrict__ fars, float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
+             const float* __restrict__ noises, uint32_t Mpad, bool zero_fill) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_alive) {
+        // padding rows [n_alive*n_step, Mpad): spread over the surplus threads of the grid
+        if (zero_fill) {
+            const uint32_t total_threads = gridDim.x * blockDim.x;
+            for (uint32_t i = n_alive * n_step + (n - n_alive); i < Mpad; i += total_threads - n_alive) {
+                xyzs[3 * (size_t)i] = 0; xyzs[3 * (size_t)i + 1] = 0; xyzs[3 * (size_t)i + 2] = 0;
+                dirs[3 * (size_t)i] = 0; dirs[3 * (size_t)i + 1] = 0; dirs[3 * (size_t)i + 2] = 0;
+                reinterpret_cast<float4*>(deltas)[i] = make_float4(0, 0, 0, 0);
+            }
+        }
+        return;
+    }
+    const int32_t index = rays_alive[n];
+    MarchCtx c;
+    march_init(c, rays_o + 3 * (size_t)index, rays_d + 3 * (size_t)index, bound, dt_gamma, max_steps, C, H);
+    float t = rays_t[(size_t)index * (is_ndc ? 2 : 1)];
+    const float far = fars[index];
+    float* px = xyzs + 3 * (size_t)n * n_step;
+    float* pd = dirs + 3 * (size_t)n * n_step;
+    float4* pl = reinterpret_cast<float4*>(deltas) + (size_t)n * n_step;
+    uint32_t step = 0;
+    t = march_t0(c, t, noises ? noises[n] : 0.0f);
+    float last_t = t;
+    float last_z = nrf_clamp(__fmaf_rn(c.dz, t, c.oz), c.nbound, c.bound);
+    const float zh = is_ndc ? z_hats[index] : 1.0f;
+    float x, y, z, dt;
+    while (t < far && step < n_step) {
+        if (march_visit(c, grid, t, x, y, z, dt)) {
+            px[0] = x; px[1] = y; px[2] = z;
+            pd[0] = c.dx; pd[1] = c.dy; pd[2] = c.dz;
+            t = __fadd_rn(t, dt);
+            float4 dl = make_float4(dt, __fsub_rn(t, last_t), 0.0f, 0.0f);
+            if (is_ndc) {   // raymarching.cu:1094-1099 (inference updates last_z = new_z)
+                const float new_z = nrf_clamp(__fmaf_rn(c.dz, t, c.oz), c.nbound, c.bound);
+                dl.z = (2 / (new_z - 1) - 2 / (z - 1)) / zh;
+                dl.w = (2 / (new_z - 1) - 2 / (last_z - 1)) / zh;
+                last_z = new_z;
+            }
+            last_t = t;
+            *pl = dl;
+            px += 3; pd += 3; pl += 1; step++;
+        }
+    }
+    if (zero_fill) {
+        for (; step < n_step; step++) {
+            px[0] = 0; px[1] = 0; px[2] = 0; pd[0] = 0; pd[1] = 0; pd[2] = 0;
+            *pl = make_float4(0, 0, 0, 0);
+            px += 3; pd += 3; pl += 1;
+        }
+    }
+}
+
+NRF_EXPORT int nrf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                              const float* rays_o, const float* rays_d, const float* z_hats, float bound, float dt_gamma,
+                              uint32_t max_steps, int is_ndc, uint32_t C, uint32_t H, const uint8_t* grid, const float* nears,
+                              const float* fars, float* xyzs, float* dirs, float* deltas, const float* noises,
+                              uint32_t Mpad, int zero_fill, void* stream) {
+    (void)nears;
+    if (!xyzs || !dirs || !deltas) return NRF_E_INVALID;
+    if ((((uintptr_t)deltas) & 15) != 0) return NRF_E_INVALID;
+    if (n_alive && (!rays_alive || !rays_t || !rays_o || !rays_d || !grid || !fars)) return NRF_E_INVALID;
+    if (is_ndc && !z_hats) return NRF_E_INVALID;
+    if ((uint64_t)n_alive * n_step > Mpad) return NRF_E_INVALID;
+    const uint32_t pad = Mpad - n_alive * n_step;
+    const uint32_t threads = n_alive + (zero_fill ? min(pad, 4096u) : 0u);
+    if (threads == 0) return NRF_OK;
+    k_march_rays<<<ceil_div_u32(threads, 128), 128, 0, (cudaStream_t)stream>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d,
+                                                                             z_hats, bound, dt_gamma, max_steps, is_ndc != 0, C, H,
+                                                                             grid, fars, xyzs, dirs, deltas, noises, Mpad,
+                                                                             zero_fill != 0);
+    return nrf_check_launch();
+}
+
+__global__ void __launch_bounds__(128)
+k_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* __restrict__ rays_alive, float* __restrict__ rays_t,
+                 const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas, uint32_t C,
+                 bool is_ndc, float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_alive) return;
+    const int32_t index = rays_alive[n];
+    const float* s = sigmas + (size_t)n * n_step;
+    const float* r = rgbs + (size_t)n * n_step * C;
+    const float4* dl4 = reinterpret_cast<const float4*>(deltas) + (size_t)n * n_step;
+    float* rt = rays_t + (size_t)index * (is_ndc ? 2 : 1);
+    float* img = image + (size_t)index * C;
+    float t_rm = 0.0f, t_phy;
+    if (is_ndc) { t_rm = rt[0]; t_phy = rt[1]; } else { t_phy = rt[0]; }
+    float weight_sum = weights_sum[index], d = depth[index];
+    uint32_t step = 0;
+    while (step < n_step) {
+        const float4 dl = __ldg(dl4 + step);
+        if (dl.x == 0.0f) break;
+        const float alpha = alpha_from(__ldg(s + step), is_ndc ? dl.z : dl.x);
+        const float T = 1.0f - weight_sum;
+        const float w = alpha * T;
+        weight_sum += w;
+        if (is_ndc) { t_rm += dl.y; t_phy += dl.w; } else { t_phy += dl.y; }
+        d = __fmaf_rn(w, t_phy, d);
+        const float* rr = r + (size_t)step * C;
+        for (uint32_t c = 0; c < C; c++) img[c] = __fmaf_rn(w, __ldg(rr + c), img[c]);
+        if (T < T_thresh) break;
+        step++;
+    }
+    if (step < n_step) rays_alive[n] = -1;
+    else { if (is_ndc) { rt[0] = t_rm; rt[1] = t_phy; } else rt[0] = t_phy; }
+    weights_sum[index] = weight_sum;
+    depth[index] = d;
+}
+
+NRF_EXPORT int nrf_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive, float* rays_t,
+                                  const float* sigmas, const float* rgbs, const float* deltas, uint32_t C, int is_ndc,
+                                  float* weights_sum, float* depth, float* image, void* stream) {
+    if (n_alive == 0) return NRF_OK;
+    if (!rays_alive || !rays_t || !sigmas || !rgbs || !deltas || !weights_sum || !depth || !image) return NRF_E_INVALID;
+    if ((((uintptr_t)deltas) & 15) != 0) return NRF_E_INVALID;
+    k_composite_rays<<<ceil_div_u32(n_alive, 128), 128, 0, (cudaStream_t)stream>>>(n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas,
+                                                                                  rgbs, deltas, C, is_ndc != 0, weights_sum, depth, image);
+    return nrf_check_launch();
+}
+
+// stable compaction of the non-negative entries (replaces rays_alive[rays_alive >= 0], renderer.py:284)
+#define COMPACT_BLOCK 256
+__global__ void __launch_bounds__(COMPACT_BLOCK)
+k_compact_count(const int32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ block_sums) {
+    const uint32_t i = blockIdx.x * COMPACT_BLOCK + threadIdx.x;
+    const bool keep = i < n && in[i] >= 0;
+    const int c = __syncthreads_count(keep);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = (uint32_t)c;
+}
+__global__ void k_compact_finish(const uint32_t* __restrict__ block_sums_scanned_end, int32_t* __restrict__ n_out) {
+    *n_out = (int32_t)*block_sums_scanned_end;
+}
+__global__ void __launch_bounds__(COMPACT_BLOCK)
+k_compact_write(const int32_t* __restrict__ in, uint32_t n, const uint32_t* __restrict__ block_offs, int32_t* __restrict__ out) {
+    __shared__ uint32_t warp_tot[COMPACT_BLOCK / 32];
+    const uint32_t i = blockIdx.x * COMPACT_BLOCK + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int32_t v = i < n ? in[i] : -1;
+    const bool keep = v >= 0;
+    const uint32_t m = __ballot_sync(NRF_FULL_MASK, keep);
+    if (lane == 0) warp_tot[warp] = __popc(m);
+    __syncthreads();
+    uint32_t base = block_offs[blockIdx.x];
+    for (int w = 0; w < warp; w++) base += warp_tot[w];
+    if (keep) out[base + __popc(m & ((1u << lane) - 1u))] = v;
+}
+
+NRF_EXPORT int nrf_compact_alive(const int32_t* in, uint32_t n, int32_t* out, int32_t* n_out, void* scratch, void* stream) {
+    if (!n_out) return NRF_E_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) return cudaMemsetAsync(n_out, 0, sizeof(int32_t), s) == cudaSuccess ? NRF_OK : NRF_E_CUDA;
+    if (!in || !out || !scratch) return NRF_E_INVALID;
+    const uint32_t nb = ceil_div_u32(n, COMPACT_BLOCK);
+    uint32_t* block_sums = (uint32_t*)scratch;      // nb entries + 1 (grand total written by the scan via counter)
+    // scratch sized by nrf_march_scratch_bytes(n): ceil(n/64)+1024 words >= nb + 2
+    int32_t* total = (int32_t*)(block_sums + nb);
+    cudaMemsetAsync(total, 0, 2 * sizeof(int32_t), s);
+    k_compact_count<<<nb, COMPACT_BLOCK, 0, s>>>(in, n, block_sums);
+    k_scan_block_sums<<<1, 1024, 0, s>>>(block_sums, nb, total, 0);
+    k_compact_write<<<nb, COMPACT_BLOCK, 0, s>>>(in, n, block_sums, out);
+    cudaMemcpyAsync(n_out, total, sizeof(int32_t), cudaMemcpyDeviceToDevice, s);
+    return nrf_check_launch();
+}

@@ -1,0 +1,158 @@
+"""Drop-in for the reference's `gridencoder` package (gridencoder/grid.py).
+
+`GridEncoder` keeps the reference's constructor, attributes, parameter / buffer names (`embeddings`,
+`offsets`), initialisation and forward signature; `grid_encode` is the autograd Function behind it.  The
+CUDA side writes the point-major [B, L*C] layout directly (no permute copy) and takes point-major grads.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+from torch.amp import custom_bwd, custom_fwd
+
+from . import _lib as L
+
+_gridtype_to_id = {'hash': 0, 'tiled': 1}
+
+
+class _grid_encode(Function):
+    """grid.py:19-97 -> gridencoder.cu:439-494"""
+
+    @staticmethod
+    @custom_fwd(device_type='cuda')
+    def forward(ctx, inputs, embeddings, offsets, per_level_scale, base_resolution, calc_grad_inputs=False,
+                gridtype=0, align_corners=False, style=0):
+        L.require_cuda(inputs, embeddings, offsets)
+        if offsets.dtype != torch.int32:
+            raise RuntimeError('offsets must be an int tensor')
+        if not inputs.is_floating_point() or not embeddings.is_floating_point():
+            raise RuntimeError('inputs / embeddings must be floating tensors')
+        inputs = inputs.contiguous()
+        if inputs.dtype != torch.float32:
+            inputs = inputs.float()
+        B, D = inputs.shape
+        Lv = offsets.shape[0] - 1
+        C = embeddings.shape[1]
+        S = float(np.float32(np.log2(per_level_scale)))
+        H = int(base_resolution)
+        # grid.py:42-43: half-precision tables under autocast when C is even
+        if torch.is_autocast_enabled('cuda') and C % 2 == 0:
+            embeddings = embeddings.to(torch.half)
+        embeddings = embeddings.contiguous()
+        offsets = offsets.contiguous()
+        dt = L.dtype_code(embeddings.dtype)
+        outputs = torch.empty(B, Lv * C, device=inputs.device, dtype=embeddings.dtype)
+        if calc_grad_inputs:
+            dy_dx = torch.empty(B, Lv * D * C, device=inputs.device, dtype=embeddings.dtype)
+        else:
+            dy_dx = None
+        with torch.cuda.device(inputs.device):
+            L.check(L.lib().nrf_grid_encode_forward(L.ptr(inputs), L.ptr(embeddings), L.ptr(offsets), L.ptr(outputs), B,
+                                                    D, C, Lv, S, H, int(bool(calc_grad_inputs)), L.ptr(dy_dx),
+                                                    int(gridtype), int(bool(align_corners)), int(style), dt, 1,
+                                                    L.stream_of(inputs)), 'grid_encode_forward')
+        ctx.save_for_backward(inputs, embeddings, offsets, dy_dx)
+        ctx.dims = [B, D, C, Lv, S, H, gridtype]
+        ctx.calc_grad_inputs = calc_grad_inputs
+        ctx.align_corners = align_corners
+        ctx.style = style
+        return outputs
+
+    @staticmethod
+    @custom_bwd(device_type='cuda')
+    def backward(ctx, grad):
+        inputs, embeddings, offsets, dy_dx = ctx.saved_tensors
+        B, D, C, Lv, S, H, gridtype = ctx.dims
+        calc_grad_inputs = ctx.calc_grad_inputs
+        grad = grad.contiguous()
+        if grad.dtype != embeddings.dtype:
+            grad = grad.to(embeddings.dtype)
+        grad_embeddings = torch.zeros_like(embeddings)
+        grad_inputs = torch.zeros_like(inputs, dtype=embeddings.dtype) if calc_grad_inputs else None
+        with torch.cuda.device(inputs.device):
+            L.check(L.lib().nrf_grid_encode_backward(L.ptr(grad), L.ptr(inputs), L.ptr(embeddings), L.ptr(offsets),
+                                                     L.ptr(grad_embeddings), B, D, C, Lv, S, H,
+                                                     int(bool(calc_grad_inputs)), L.ptr(dy_dx), L.ptr(grad_inputs),
+                                                     int(gridtype), int(bool(ctx.align_corners)), int(ctx.style),
+                                                     L.dtype_code(embeddings.dtype), 1, L.stream_of(inputs)),
+                    'grid_encode_backward')
+        if calc_grad_inputs:
+            grad_inputs = grad_inputs.to(inputs.dtype)
+            return grad_inputs, grad_embeddings, None, None, None, None, None, None, None
+        return None, grad_embeddings, None, None, None, None, None, None, None
+
+
+grid_encode = _grid_encode.apply
+
+
+class GridEncoder(nn.Module):
+    """grid.py:103-191 (same arguments, attributes and state-dict keys)."""
+
+    def __init__(self, input_dim=3, num_levels=16, level_dim=2, per_level_scale=2, base_resolution=16,
+                 log2_hashmap_size=19, desired_resolution=None, gridtype='hash', align_corners=False):
+        super().__init__()
+        if desired_resolution is not None:
+            per_level_scale = np.exp2(np.log2(desired_resolution / base_resolution) / (num_levels - 1))
+        self.input_dim = input_dim
+        self.num_levels = num_levels
+        self.level_dim = level_dim
+        self.per_level_scale = per_level_scale
+        self.log2_hashmap_size = log2_hashmap_size
+        self.base_resolution = base_resolution
+        self.output_dim = num_levels * level_dim
+        self.gridtype = gridtype
+        self.gridtype_id = _gridtype_to_id[gridtype]
+        self.align_corners = align_corners
+        self.n_output_dims = num_levels * level_dim
+
+        offsets = []
+        offset = 0
+        self.max_params = 2 ** log2_hashmap_size
+        for i in range(num_levels):
+            resolution = int(np.ceil(base_resolution * per_level_scale ** i))
+            params_in_level = min(self.max_params, (resolution if align_corners else resolution + 1) ** input_dim)
+            params_in_level = int(np.ceil(params_in_level / 8) * 8)
+            offsets.append(offset)
+            offset += params_in_level
+        offsets.append(offset)
+        offsets = torch.from_numpy(np.array(offsets, dtype=np.int32))
+        self.register_buffer('offsets', offsets)
+        self.n_params = offsets[-1] * level_dim
+        self.embeddings = nn.Parameter(torch.empty(offset, level_dim))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        std = 1e-4
+        self.embeddings.data.uniform_(-std, std)
+
+    def initialize(self, ref_embeddings, ref_offsets, num_styles=64):
+        """grid.py:154-164 -> gridencoder.cu:551-571"""
+        Lv = self.offsets.shape[0] - 1
+        S = float(np.float32(np.log2(self.per_level_scale)))
+        H = int(self.base_resolution)
+        tmp = torch.zeros_like(self.embeddings)
+        ref_embeddings = ref_embeddings.detach().float().contiguous()
+        L.require_cuda(ref_embeddings, tmp, ref_offsets, self.offsets)
+        with torch.cuda.device(tmp.device):
+            L.check(L.lib().nrf_grid_initialize(L.ptr(ref_embeddings), L.ptr(tmp), L.ptr(ref_offsets.contiguous()),
+                                                L.ptr(self.offsets), Lv, S, H, int(num_styles), L.stream_of(tmp)),
+                    'grid_initialize')
+        state_dict = self.state_dict()
+        state_dict['embeddings'] = tmp
+        self.load_state_dict(state_dict)
+
+    def __repr__(self):
+        return (f"GridEncoder: input_dim={self.input_dim} num_levels={self.num_levels} level_dim={self.level_dim} "
+                f"resolution={self.base_resolution} -> "
+                f"{int(round(self.base_resolution * self.per_level_scale ** (self.num_levels - 1)))} "
+                f"per_level_scale={self.per_level_scale:.4f} params={tuple(self.embeddings.shape)} "
+                f"gridtype={self.gridtype} align_corners={self.align_corners}")
+
+    def forward(self, inputs, bound=1, style=0):
+        inputs = (inputs + bound) / (2 * bound)  # map to [0, 1]
+        prefix_shape = list(inputs.shape[:-1])
+        inputs = inputs.view(-1, self.input_dim)
+        outputs = grid_encode(inputs, self.embeddings, self.offsets, self.per_level_scale, self.base_resolution,
+                              inputs.requires_grad, self.gridtype_id, self.align_corners, style)
+        outputs = outputs.view(prefix_shape + [self.output_dim])
+        return outputs

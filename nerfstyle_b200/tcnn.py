@@ -1,0 +1,144 @@
+"""tiny-cuda-nn style `Network` / `Encoding` modules on the hand-written fused MLP kernels.
+
+Mirrors the part of the `tinycudann` torch binding the reference uses
+(networks/style_nerf.py:34-98, networks/tcnn_nerf.py:38-50,87-122):
+
+    tcnn.Network(n_input_dims=, n_output_dims=, network_config={'otype': 'FullyFusedMLP', 'activation': 'ReLU',
+                 'output_activation': 'None'|'Sigmoid', 'n_neurons': 64, 'n_hidden_layers': h}, seed=)
+
+* one flat fp32 `params` Parameter in tcnn's FullyFusedMLP layout (row-major [out,in] per layer, input and
+  output widths padded to 16), cast to fp16 on every forward;
+* fp16 output `[batch, n_output_dims]`; attributes `n_input_dims`, `n_output_dims`, `params`, `dtype`,
+  `loss_scale`, `seed`.
+
+tiny-cuda-nn is an un-vendored, unpinned dependency of the reference (README.md:25-26), so its numerics
+are restated, not copied: fp16 operands, fp32 tensor-core accumulation, hidden activations rounded to
+fp16 between layers (tcnn itself accumulates in fp16); weight init is Xavier-uniform from a torch
+generator seeded with `seed` (tcnn's pcg32 stream is not reproducible here; parity tests inject weights).
+"""
+import math
+
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from . import _lib as L
+
+_ACT = {'none': 0, 'relu': 1, 'sigmoid': 2, 'exponential': 3}
+
+
+def _pad16(n):
+    return (n + 15) // 16 * 16
+
+
+class _mlp_function(Function):
+    @staticmethod
+    def forward(ctx, x, params, cfg):
+        n_in, n_out, n_hidden, width, hidden_act, out_act, loss_scale = cfg
+        L.require_cuda(x, params)
+        if x.dtype not in (torch.float16, torch.float32):
+            x = x.float()
+        x = x.contiguous()
+        params_h = params.detach().to(torch.float16).contiguous()
+        B = x.shape[0]
+        y = torch.empty(B, n_out, dtype=torch.float16, device=x.device)
+        with torch.cuda.device(x.device):
+            L.check(L.lib().nrf_mlp_forward(L.ptr(x), L.dtype_code(x.dtype), L.ptr(params_h), B, n_in, n_out, n_hidden,
+                                            width, hidden_act, out_act, L.ptr(y), L.DTYPE_F16, L.stream_of(x)),
+                    'mlp_forward')
+        ctx.save_for_backward(x, params_h)
+        ctx.cfg = cfg
+        ctx.need_dx = ctx.needs_input_grad[0]
+        ctx.need_dp = ctx.needs_input_grad[1]
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, params_h = ctx.saved_tensors
+        n_in, n_out, n_hidden, width, hidden_act, out_act, loss_scale = ctx.cfg
+        if dy.dtype not in (torch.float16, torch.float32):
+            dy = dy.float()
+        dy = dy.contiguous()
+        B = x.shape[0]
+        dx = torch.empty_like(x) if ctx.need_dx else None
+        dparams = torch.zeros(params_h.shape, dtype=torch.float32, device=x.device) if ctx.need_dp else None
+        if ctx.need_dx or ctx.need_dp:
+            with torch.cuda.device(x.device):
+                L.check(L.lib().nrf_mlp_backward(L.ptr(x), L.dtype_code(x.dtype), L.ptr(params_h), L.ptr(dy),
+                                                 L.dtype_code(dy.dtype), B, n_in, n_out, n_hidden, width, hidden_act,
+                                                 out_act, float(loss_scale), L.ptr(dx), L.dtype_code(x.dtype),
+                                                 L.ptr(dparams), L.stream_of(x)), 'mlp_backward')
+        return dx, dparams, None
+
+
+class Network(nn.Module):
+    """tcnn.Network look-alike (FullyFusedMLP / CutlassMLP otypes map to the same fused kernel)."""
+
+    def __init__(self, n_input_dims, n_output_dims, network_config, seed=1337):
+        super().__init__()
+        otype = network_config.get('otype', 'FullyFusedMLP')
+        if otype not in ('FullyFusedMLP', 'CutlassMLP'):
+            raise RuntimeError('nerfstyle_b200.tcnn.Network: unsupported otype %r' % otype)
+        self.n_input_dims = int(n_input_dims)
+        self.n_output_dims = int(n_output_dims)
+        self.network_config = dict(network_config)
+        self.seed = seed
+        self.n_neurons = int(network_config.get('n_neurons', 64))
+        self.n_hidden_layers = int(network_config.get('n_hidden_layers', 1))
+        act = str(network_config.get('activation', 'ReLU')).lower()
+        out_act = str(network_config.get('output_activation', 'None')).lower()
+        if act not in ('relu', 'none') or out_act not in _ACT:
+            raise RuntimeError('nerfstyle_b200.tcnn.Network: unsupported activation %r / %r' % (act, out_act))
+        if self.n_neurons != 64 or not (1 <= self.n_hidden_layers <= 2) or self.n_input_dims > 64 \
+                or self.n_output_dims > 16:
+            raise RuntimeError('nerfstyle_b200.tcnn.Network: supported shapes are n_neurons=64, 1-2 hidden layers, '
+                               'n_input_dims<=64, n_output_dims<=16')
+        self.hidden_act = _ACT[act]
+        self.out_act = _ACT[out_act]
+        self.dtype = torch.float16
+        self.loss_scale = 128.0
+        self.in_pad = _pad16(self.n_input_dims)
+        self.out_pad = _pad16(self.n_output_dims)
+        shapes = [(self.n_neurons, self.in_pad)]
+        shapes += [(self.n_neurons, self.n_neurons)] * (self.n_hidden_layers - 1)
+        shapes += [(self.out_pad, self.n_neurons)]
+        self.layer_shapes = shapes
+        gen = torch.Generator(device='cpu')
+        gen.manual_seed(int(seed))
+        chunks = []
+        for (o, i) in shapes:
+            bound = math.sqrt(6.0 / (i + o))
+            chunks.append((torch.rand(o, i, generator=gen) * 2 - 1).mul_(bound).reshape(-1))
+        self.params = nn.Parameter(torch.cat(chunks))
+
+    def layer_views(self, flat=None):
+        """The per-layer [out_pad, in_pad] views of a flat parameter vector (default: self.params)."""
+        flat = self.params if flat is None else flat
+        views, o = [], 0
+        for (r, c) in self.layer_shapes:
+            views.append(flat[o:o + r * c].view(r, c))
+            o += r * c
+        return views
+
+    def forward(self, x):
+        cfg = (self.n_input_dims, self.n_output_dims, self.n_hidden_layers, self.n_neurons, self.hidden_act,
+               self.out_act, self.loss_scale)
+        lead = x.shape[:-1]
+        y = _mlp_function.apply(x.reshape(-1, self.n_input_dims), self.params, cfg)
+        return y.view(*lead, self.n_output_dims)
+
+    def extra_repr(self):
+        return 'n_input_dims=%d, n_output_dims=%d, n_hidden_layers=%d, n_neurons=%d' % (
+            self.n_input_dims, self.n_output_dims, self.n_hidden_layers, self.n_neurons)
+
+
+class Encoding(nn.Module):
+    """tcnn.Encoding look-alike.  Only needed when the model is built with use_dir=True (SphericalHarmonics,
+    networks/style_nerf.py:33-42), which no shipped trainer / renderer does (trainers/base.py:149-151); see
+    SURVEY.md 8f NEXT-3."""
+
+    def __init__(self, n_input_dims, encoding_config, seed=1337, dtype=None):
+        super().__init__()
+        raise NotImplementedError(
+            'nerfstyle_b200.tcnn.Encoding(%r) is not implemented yet (off the default path; SURVEY.md 8f NEXT-3)'
+            % (encoding_config.get('otype'),))

@@ -1,0 +1,125 @@
+"""Host-side mirror of the reference interface (no GPU): module surface, parameter names, layouts."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+REF = '/root/reference'
+
+
+def test_gridencoder_layout():
+    from nerfstyle_b200.model import get_grid_encoder
+    enc = get_grid_encoder(max_bound=4.0)
+    assert enc.offsets.dtype == torch.int32 and enc.offsets[-1].item() == 6299960
+    assert tuple(enc.embeddings.shape) == (6299960, 2)
+    assert enc.n_output_dims == 32 and enc.output_dim == 32
+    assert abs(enc.per_level_scale - 2 ** (8 / 15)) < 1e-12
+    assert float(enc.embeddings.abs().max()) <= 1e-4
+    assert set(enc.state_dict().keys()) == {'embeddings', 'offsets'}
+
+
+def test_tcnn_network_params():
+    from nerfstyle_b200 import tcnn
+    cfg = lambda h, a: {'otype': 'FullyFusedMLP', 'activation': 'ReLU', 'output_activation': a, 'n_neurons': 64,  # noqa
+                        'n_hidden_layers': h}
+    sizes = [tcnn.Network(32, 1, cfg(1, 'None'), 80000).params.numel(), tcnn.Network(32, 8, cfg(1, 'None')).params.numel(),
+             tcnn.Network(32, 16, cfg(1, 'None')).params.numel(), tcnn.Network(16, 3, cfg(2, 'Sigmoid')).params.numel()]
+    assert sizes == [3072, 3072, 3072, 6144]
+    n = tcnn.Network(32, 1, cfg(1, 'None'), 80000)
+    assert n.params.dtype == torch.float32 and n.dtype == torch.float16 and n.loss_scale == 128.0
+    assert n.n_input_dims == 32 and n.n_output_dims == 1
+    a = tcnn.Network(32, 1, cfg(1, 'None'), 1).params
+    b = tcnn.Network(32, 1, cfg(1, 'None'), 1).params
+    assert torch.equal(a, b)
+    with pytest.raises(RuntimeError):
+        tcnn.Network(32, 1, dict(cfg(1, 'None'), n_neurons=128))
+
+
+def test_model_parameter_names():
+    from nerfstyle_b200.model import StyleTCNerf
+    m = StyleTCNerf([-2., -2., -2.], [2., 2., 2.], class_dim=8)
+    names = {n for n, _ in m.named_parameters()}
+    assert names == {'x_density_embedder.embeddings', 'x_color_embedder.embeddings', 'density_net.params',
+                     'color1_net.params', 'color2_net.params', 'class_net.params'}
+    # trainers/base.py:186-198 selects by these substrings
+    for kw in ('x_density_embedder', 'x_color_embedder', 'net'):
+        assert any(kw in n for n in names)
+
+
+def test_ops_raise_without_cuda():
+    """No CPU fallback: CPU tensors are moved with .cuda() like the reference, which fails loudly without a GPU."""
+    if torch.cuda.is_available():
+        pytest.skip('has a GPU')
+    from nerfstyle_b200 import raymarching
+    with pytest.raises((RuntimeError, AssertionError)):
+        raymarching.near_far_from_aabb(torch.zeros(4, 3), torch.ones(4, 3), torch.tensor([-1., -1, -1, 1, 1, 1]))
+
+
+def test_dropin_surface():
+    import nerfstyle_b200.dropin as dropin
+    rm, ge, tc = dropin.install(force=True)
+    import raymarching
+    from gridencoder import GridEncoder  # noqa: F401
+    import tinycudann as tcnn
+    for name in ['near_far_from_aabb', 'sph_from_ray', 'morton3D', 'morton3D_invert', 'packbits', 'march_rays_train',
+                 'composite_rays_train', 'march_rays', 'composite_rays']:
+        assert callable(getattr(raymarching, name))
+    assert hasattr(tcnn, 'Network') and hasattr(tcnn, 'Encoding')
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference checkout not mounted (GPU box)')
+def test_reference_modules_import_unchanged_on_dropin():
+    """networks/tcnn_nerf.py and networks/style_nerf.py of the reference import and construct against the drop-in
+    (their non-hot-path imports -- config/utils/common need dacite, simple_parsing ... -- are stubbed)."""
+    import types
+    import nerfstyle_b200.dropin as dropin
+    dropin.install(force=True)
+    saved = {k: sys.modules.get(k) for k in ('common', 'config', 'utils', 'networks', 'networks.tcnn_nerf', 'networks.style_nerf')}
+    try:
+        common = types.ModuleType('common')
+
+        class TensorModule(torch.nn.Module):
+            pass
+
+        class BBox:
+            def __init__(self, lo, hi):
+                self.min_pt, self.max_pt = torch.tensor(lo), torch.tensor(hi)
+
+            @property
+            def size(self):
+                return self.max_pt - self.min_pt
+
+            def normalize(self, pts):
+                return (pts - self.min_pt) / self.size
+        common.TensorModule, common.BBox = TensorModule, BBox
+        config = types.ModuleType('config')
+        config.NetworkConfig = object
+        utils = types.ModuleType('utils')
+        sys.modules.update(common=common, config=config, utils=utils)
+        pkg = types.ModuleType('networks')
+        pkg.__path__ = [os.path.join(REF, 'networks')]
+        sys.modules['networks'] = pkg
+        import importlib
+        tn = importlib.import_module('networks.tcnn_nerf')
+        sn = importlib.import_module('networks.style_nerf')
+        assert tn.GridEncoder.__module__ == 'nerfstyle_b200.gridencoder'
+
+        class PosEnc:
+            n_lvls, n_feats_per_lvl, hashmap_size, min_res, max_res_coeff = 16, 2, 19, 16, 1024
+
+        class Cfg:
+            pos_enc = PosEnc
+            network_seed = 80000
+            density_hidden_dims, density_hidden_layers, rgb_hidden_dims, rgb_hidden_layers = 64, 1, 64, 2
+            density_out_dims, dir_enc_sh_deg = 16, 4
+        model = sn.StyleTCNerf(Cfg, BBox([-2., -2., -2.], [2., 2., 2.]), 8, torch.float16, use_dir=False)
+        assert model.x_density_embedder.offsets[-1].item() == 6299960
+        assert model.color2_net.params.numel() == 6144
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
