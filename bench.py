@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on B200: train-step rays/s of the NeRF hot path.
+
+Workload (BASELINE.json configs[1]): LLFF-room-shaped reconstruction train step, 504x378 views, 8192 rays per
+step per GPU, occupancy-grid marching (H=128, 2 cascades, bound 2), two 16-level 2^19 hash grids, four 64-wide
+MLPs (K=8 classes), composite fwd+bwd, MSE + class CE, AMP (fp16 tables/MLPs, GradScaler), Adam + EMA,
+occupancy update every 16 steps; random-init field, synthetic poses/targets (no dataset on the box).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+`value`  : rays/s with the step's inputs already resident in HBM (device timed, max over ranks).
+`e2e`    : same metric through the public API with HOST (pinned) inputs: H2D of rays+targets and D2H of the loss
+           inside the timed region, every step.
+`roofline`: the dominant kernel of the step (decided from CUDA-event timings taken live over the timed region).
+`cpu_baseline`: the CPU oracle (port of the reference kernels, OpenMP + torch CPU) on a bounded sample.
+--impl reference: the reference path has no CPU implementation of its own (CUDA-only), so the arm times the
+           oracle port on all host cores on bounded samples of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_RAYS = 8192
+N_CLASSES = 8
+WORKLOAD = 'llff_room_train_step_8192rays_504x378'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=32)
+    ap.add_argument('--warmup', type=int, default=8)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--rays', type=int, default=N_RAYS)
+    ap.add_argument('--no-amp', action='store_true')
+    ap.add_argument('--cpu-sample-rays', type=int, default=1024)
+    ap.add_argument('--skip-cpu-baseline', action='store_true')
+    ap.add_argument('--skip-ref-ext', action='store_true')
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index=0, period=0.2):
+        self.index, self.period, self.rows, self._stop, self._t = index, period, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        reasons = set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def make_batches(n_steps, n_rays, rank, world, device):
+    """Per-step (rays_o, rays_d, target_rgb, target_cls) for this rank, generated once; returned both as pinned host
+    tensors (e2e) and as device tensors (device-resident value)."""
+    import torch
+    from nerfstyle_b200 import scenes
+    intr = dict(scenes.ROOM)
+    poses = scenes.synthetic_poses(intr['n_train'], 0)
+    gen = torch.Generator().manual_seed(69420 + 1000 * rank)      # rng_seed of cfgs/training/default.yaml
+    host, dev = [], []
+    for s in range(n_steps):
+        pose = poses[(s * world + rank) % len(poses)]
+        idx = scenes.frame_indices(intr, n_rays, gen).to(device)
+        o, d = scenes.generate_rays(pose, intr, device, idx)
+        rgb, seg = scenes.synthetic_target(idx, intr, N_CLASSES)
+        pack = torch.cat([o, d, rgb, seg.to(torch.float32)[:, None]], dim=1).contiguous()      # [n, 10] f32
+        dev.append(pack)
+        host.append(pack.cpu().pin_memory())
+    return host, dev
+
+
+def unpack(pack):
+    return pack[:, 0:3].contiguous(), pack[:, 3:6].contiguous(), pack[:, 6:9].contiguous(), pack[:, 9].long()
+
+
+def build_trainer(device, amp, world):
+    import torch
+    from nerfstyle_b200 import model as M
+    from nerfstyle_b200.trainer import TrainStep
+    torch.manual_seed(0)
+    m = M.StyleTCNerf([-2., -2., -2.], [2., 2., 2.], class_dim=N_CLASSES).to(device)
+    r = M.Renderer(m, 2.0, raymarch_channels=3 + N_CLASSES).to(device)
+    return TrainStep(r, enable_amp=amp, world_size=world)
+
+
+ALGO_BYTES = {   # SURVEY.md 8d, per point per encoder (fp32 tables / fp16 tables), per sample for compositing
+    'nrf_grid_encode_forward': {False: 12 + 16 * 8 * 2 * 4 + 16 * 2 * 4, True: 12 + 16 * 8 * 2 * 2 + 16 * 2 * 2},
+    'nrf_grid_encode_backward': {False: 12 + 128 + 2 * 1024, True: 12 + 64 + 2 * 512},
+}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from nerfstyle_b200 import _lib
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+    amp = not args.no_amp
+    _lib.lib()
+    ts = build_trainer(device, amp, world)
+    W, K = args.warmup, args.steps
+    host, devb = make_batches(W + K, args.rays, rank, world, device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # -------- phase A: device-resident inputs (value) + live per-kernel CUDA-event timing
+    for s in range(W):
+        ts.step(*unpack(devb[s]))
+    timed_ops = ['nrf_grid_encode_forward', 'nrf_grid_encode_backward', 'nrf_mlp_forward', 'nrf_mlp_backward',
+                 'nrf_composite_rays_train_forward', 'nrf_composite_rays_train_backward', 'nrf_march_rays_train_count',
+                 'nrf_march_rays_train_write']
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    _lib.Stats.reset()
+    _lib.Stats.timed = set(timed_ops)
+    samples0 = int(ts.renderer.step_counter[:, 0].sum().item())
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(W, W + K):
+        loss = ts.step(*unpack(devb[s]))
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = _lib.Stats.launches
+    events = list(_lib.Stats.events)
+    _lib.Stats.timed = set()
+    t = torch.tensor([ms_total], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    per_op = {}
+    for name, a, b, units in events:
+        d = per_op.setdefault(name, {'ms': 0.0, 'calls': 0, 'units': 0})
+        d['ms'] += a.elapsed_time(b)
+        d['calls'] += 1
+        d['units'] += units
+    samples_last = int(ts.renderer.step_counter[(ts.renderer.local_step - 1) % 16, 0].item())
+
+    # -------- phase B: end to end through the public API with host inputs (H2D + D2H every step)
+    e2e_W = min(W, 3)
+    stage = torch.empty_like(devb[0])
+    for s in range(e2e_W):
+        stage.copy_(host[s], non_blocking=True)
+        float(ts.step(*unpack(stage)).item())
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(W, W + K):
+        stage.copy_(host[s], non_blocking=True)                       # H2D from pinned memory
+        lv = float(ts.step(*unpack(stage)).item())                    # D2H read of the loss
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    clk = clocks.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    n_global = args.rays * world
+    value = n_global * K / (ms_total / 1e3)
+    # dominant kernel -> roofline
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (B200_PROFILING.md)'
+    kern = {k: {'ms_per_step': v['ms'] / K, 'calls_per_step': v['calls'] / K} for k, v in per_op.items()}
+    top = max((k for k in per_op if k in ALGO_BYTES), key=lambda k: per_op[k]['ms'], default=None)
+    roofline = None
+    if top:
+        v = per_op[top]
+        bytes_per_launch = ALGO_BYTES[top][amp] * (v['units'] / v['calls'])
+        sec_per_launch = v['ms'] / 1e3 / v['calls']
+        ach = bytes_per_launch / sec_per_launch / 1e9
+        roofline = {'kernel': top, 'bound': 'hbm', 'achieved': round(ach, 1), 'peak': hbm_peak, 'unit': 'GB/s',
+                    'frac': round(ach / hbm_peak, 4), 'traffic': None, 'peak_source': peak_src,
+                    'algorithmic_bytes_per_point': ALGO_BYTES[top][amp], 'points_per_launch': v['units'] / v['calls'],
+                    'us_per_launch': round(sec_per_launch * 1e6, 1)}
+    line = {
+        'metric': 'train_rays_per_s', 'value': round(value, 1), 'unit': 'rays/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+        'ms_per_step': round(ms_total / K, 4), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f16 tables+MLP operands / f32 accumulate+compositing' if amp else 'f32 tables / f16 MLP operands',
+        'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'rays_per_gpu_per_step': args.rays, 'global_rays_per_step': n_global,
+                   'samples_per_step_last': samples_last, 'hash_grid': 'L16 F2 T2^19 x2', 'mlp': '4x 64-wide (K=8)',
+                   'occupancy': 'H128 C2 update every 16 steps', 'amp': amp, 'optimizer': 'Adam(fused)+EMA',
+                   'l2_policy': 'no flush: per-step working set (~%d MB of samples/activations + 96 MB tables) exceeds the 126 MB L2'
+                                % (samples_last * 700 // (1 << 20)),
+                   'parallelism': 'dp%d (rays sharded, NCCL all-reduce of table+MLP grads)' % world},
+        'e2e': {'value': round(n_global * K / e2e_s, 1), 'unit': 'rays/s', 'h2d_bytes_per_step': int(host[0].numel() * 4),
+                'd2h_bytes_per_step': 4 + 8, 'ms_per_step': round(e2e_s * 1e3 / K, 4)},
+        'gpu_launches': int(launches),
+        'clocks': clk,
+        'roofline': roofline,
+        'kernels': kern,
+        'final_loss': lv,
+    }
+    if world == 1 and not args.skip_cpu_baseline:
+        line['cpu_baseline'] = cpu_baseline(args.cpu_sample_rays)
+    if world == 1 and not args.skip_ref_ext:
+        try:
+            from bench_ref_ext import time_reference_ext
+            line['reference_cuda_ext'] = time_reference_ext(args.rays, min(K, 10), device)
+        except Exception as e:      # the rebuilt reference extensions are optional evidence
+            line['reference_cuda_ext'] = {'unavailable': '%s: %s' % (type(e).__name__, str(e)[:200])}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ CPU oracle arms
+def _cpu_step_fn(n_rays):
+    """One train step of the CPU oracle port on `n_rays` rays of the same workload (fwd + bwd + Adam)."""
+    import torch
+    import oracle
+    from oracle import field
+    from nerfstyle_b200 import scenes
+    torch.set_num_threads(os.cpu_count())
+    of = field.OracleField(bound=2.0, n_classes=N_CLASSES, half=False, seed=0, table_std=1e-4)
+    opt = torch.optim.Adam(list(of.params.values()), lr=0.01, eps=1e-15)
+    intr = dict(scenes.ROOM)
+    poses = scenes.synthetic_poses(intr['n_train'], 0)
+    gen = torch.Generator().manual_seed(69420)
+    # occupancy like update_state at step 0: density of the random-init field vs its mean
+    bits = None
+
+    def occupancy():
+        H = 128
+        grid = torch.zeros(2, H ** 3)
+        coords = torch.from_numpy(oracle.morton3D_invert(torch.arange(H ** 3, dtype=torch.int32).numpy()).astype('float32'))
+        xyz = 2 * coords / (H - 1) - 1
+        for cas in range(2):
+            b = min(2 ** cas, 2.0)
+            hg = b / H
+            p = xyz * (b - hg) + (torch.rand(xyz.shape, generator=gen) * 2 - 1) * hg
+            with torch.no_grad():
+                sig = torch.cat([of.forward(p[i:i + 262144]).reshape(-1) for i in range(0, p.shape[0], 262144)])
+            grid[cas] = sig
+        return oracle.packbits(grid.numpy(), min(float(grid.clamp(min=0).mean()), 10.0))
+
+    state = {'bits': bits, 'it': 0}
+
+    def step():
+        if state['bits'] is None:
+            state['bits'] = occupancy()
+        pose = poses[state['it'] % len(poses)]
+        idx = scenes.frame_indices(intr, n_rays, gen)
+        o, d = scenes.generate_rays(pose, intr, 'cpu', idx)
+        rgb, seg = scenes.synthetic_target(idx, intr, N_CLASSES)
+        out = field.render_train(of, o.numpy(), d.numpy(), state['bits'], 2, 128, 2.0)
+        loss = field.train_step_loss(out, rgb, seg)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        state['it'] += 1
+        return float(loss), int(out['counter'][0])
+    return step
+
+
+def cpu_baseline(n_rays):
+    step = _cpu_step_fn(n_rays)
+    step()                      # warm-up (includes the one-off occupancy sweep)
+    t0 = time.perf_counter()
+    loss, ns = step()
+    dt = time.perf_counter() - t0
+    return {'value': round(n_rays / dt, 2), 'unit': 'rays/s', 'cores': os.cpu_count(), 'kind': 'port',
+            'sample': '%d rays of the same workload (%d samples), one full train step (fwd+bwd+Adam) of the CPU oracle '
+                      '(OpenMP C kernels + torch-CPU MLPs), %.1f s' % (n_rays, ns, dt)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    n = 512
+    step = _cpu_step_fn(n)
+    for _ in range(max(1, min(args.warmup, 1))):
+        step()
+    K = max(1, min(args.steps, 6))
+    t0 = time.perf_counter()
+    ns = 0
+    for _ in range(K):
+        loss, ns = step()
+    dt = time.perf_counter() - t0
+    v = round(n * K / dt, 2)
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    line = {'impl': 'reference', 'metric': 'train_rays_per_s', 'value': v, 'unit': 'rays/s', 'n_gpus': world, 'steps': K,
+            'warmup': 1, 'ms_per_step': round(dt * 1e3 / K, 2), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'rays_per_step_sample': n, 'samples_per_step_last': ns,
+                       'note': 'the reference path is CUDA-only; this arm is the CPU oracle port of its kernels on all host '
+                               'cores, each step a bounded %d-ray sample of the 8192-ray workload' % n},
+            'cpu_baseline': {'value': v, 'unit': 'rays/s', 'cores': os.cpu_count(), 'kind': 'port',
+                             'sample': '%d steps x %d rays (fwd+bwd+Adam)' % (K, n)},
+            'e2e': {'value': v, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

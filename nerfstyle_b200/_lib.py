@@ -62,6 +62,60 @@ ACT = {'none': 0, 'relu': 1, 'sigmoid': 2, 'exponential': 3}
 
 _lib = None
 
+# kernels launched per C call (lower bound; used for the `gpu_launches` claim of bench.py)
+KERNELS_PER_CALL = {
+    'nrf_near_far_from_aabb': 1, 'nrf_sph_from_ray': 1, 'nrf_morton3D': 1, 'nrf_morton3D_invert': 1, 'nrf_packbits': 1,
+    'nrf_march_rays_train_count': 3, 'nrf_march_rays_train_write': 1, 'nrf_march_rays_train': 4,
+    'nrf_composite_rays_train_forward': 1, 'nrf_composite_rays_train_backward': 1, 'nrf_march_rays': 1,
+    'nrf_composite_rays': 1, 'nrf_compact_alive': 3, 'nrf_grid_encode_forward': 1, 'nrf_grid_encode_backward': 1,
+    'nrf_grid_initialize': 1, 'nrf_mlp_forward': 1, 'nrf_mlp_backward': 1, 'nrf_nnfm_forward': 3,
+    'nrf_adam_step': 1,
+}
+
+
+class Stats:
+    """Launch counter + optional CUDA-event timing of selected entry points (bench.py / profiling only)."""
+    launches = 0
+    calls = {}
+    timed = set()          # entry-point names to bracket with CUDA events on the current stream
+    events = []            # (name, start_event, end_event, units)
+    units = 0              # set by the wrapper just before a timed call (e.g. number of points)
+
+    @classmethod
+    def reset(cls):
+        cls.launches = 0
+        cls.calls = {}
+        cls.events = []
+
+
+class _Proxy:
+    def __init__(self, cdll):
+        self._cdll = cdll
+        self._cache = {}
+
+    def __getattr__(self, name):
+        fn = self._cache.get(name)
+        if fn is None:
+            raw = getattr(self._cdll, name)
+            k = KERNELS_PER_CALL.get(name)
+            if k is None:
+                fn = raw
+            else:
+                def fn(*args, _raw=raw, _k=k, _name=name):
+                    Stats.launches += _k
+                    Stats.calls[_name] = Stats.calls.get(_name, 0) + 1
+                    if _name in Stats.timed:
+                        e0 = torch.cuda.Event(enable_timing=True)
+                        e1 = torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        rc = _raw(*args)
+                        e1.record()
+                        Stats.events.append((_name, e0, e1, Stats.units))
+                        return rc
+                    return _raw(*args)
+            self._cache[name] = fn
+        return fn
+
 
 def lib():
     """Load the CUDA library (once).  Raises RuntimeError when it has not been built."""
@@ -75,10 +129,12 @@ def lib():
     l = ctypes.CDLL(LIB_PATH)
     for table in (SIGNATURES, EXTRA_SIGNATURES):
         for name, (res, args) in table.items():
-            fn = getattr(l, name)
+            fn = getattr(l, name, None)
+            if fn is None:
+                raise RuntimeError('nerfstyle_b200: %s does not export %s (stale build?)' % (LIB_PATH, name))
             fn.restype = res
             fn.argtypes = args
-    _lib = l
+    _lib = _Proxy(l)
     return _lib
 
 

@@ -46,6 +46,7 @@ class _grid_encode(Function):
             dy_dx = torch.empty(B, Lv * D * C, device=inputs.device, dtype=embeddings.dtype)
         else:
             dy_dx = None
+        L.Stats.units = B
         with torch.cuda.device(inputs.device):
             L.check(L.lib().nrf_grid_encode_forward(L.ptr(inputs), L.ptr(embeddings), L.ptr(offsets), L.ptr(outputs), B,
                                                     D, C, Lv, S, H, int(bool(calc_grad_inputs)), L.ptr(dy_dx),
@@ -69,6 +70,7 @@ class _grid_encode(Function):
             grad = grad.to(embeddings.dtype)
         grad_embeddings = torch.zeros_like(embeddings)
         grad_inputs = torch.zeros_like(inputs, dtype=embeddings.dtype) if calc_grad_inputs else None
+        L.Stats.units = B
         with torch.cuda.device(inputs.device):
             L.check(L.lib().nrf_grid_encode_backward(L.ptr(grad), L.ptr(inputs), L.ptr(embeddings), L.ptr(offsets),
                                                      L.ptr(grad_embeddings), B, D, C, Lv, S, H,

@@ -1,0 +1,75 @@
+"""One reconstruction training step, mirroring Trainer.run_iter / calc_loss of the reference
+(trainers/base.py:251-304, 396-426): autocast(fp16) render of a ray batch -> MSE + lambda * CE(class) ->
+GradScaler-scaled backward -> Adam(eps=1e-15, betas (0.9,0.999)) -> LambdaLR decay -> EMA of the parameters.
+
+Data-parallel form: each rank renders its shard of the batch with the loss scaled by
+n_local / n_global, then the hash-table and MLP gradients are summed with one NCCL all-reduce per tensor
+group before the (identical) optimizer step on every rank.
+"""
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+
+class TrainStep:
+    def __init__(self, renderer, lr=0.01, mlp_lr=None, lr_decay=30000, ema_decay=0.95, class_lambda=0.001, enable_amp=True,
+                 fused_adam=True, world_size=1):
+        self.renderer = renderer
+        self.model = renderer.model
+        params = list(self.model.parameters())
+        self.params = params
+        self.optim = torch.optim.Adam([{'params': params}], lr=lr, betas=(0.9, 0.999), eps=1e-15, fused=fused_adam)
+        self.scheduler = torch.optim.lr_scheduler.LambdaLR(
+            self.optim, (lambda it: 0.1 ** (it / lr_decay)) if lr_decay > 0 else (lambda it: 1.0))
+        self.scaler = torch.amp.GradScaler('cuda', enabled=enable_amp)
+        self.enable_amp = enable_amp
+        self.class_lambda = class_lambda
+        self.ema_decay = ema_decay
+        self.ema = [p.detach().clone() for p in params] if ema_decay > 0 else None
+        self.world_size = world_size
+        self.iter_ctr = 0
+
+    def loss_fn(self, image, classes, target_rgb, target_cls):
+        mse = torch.mean((image - target_rgb) ** 2)
+        cls = F.cross_entropy(classes, target_cls) * self.class_lambda
+        return mse + cls, mse
+
+    def allreduce_grads(self):
+        if self.world_size <= 1:
+            return
+        # flatten per dtype into two buckets: tables (100.8 MB fp32) and MLP weights (61 KB)
+        big = [p.grad for p in self.params if p.grad is not None and p.numel() > (1 << 20)]
+        small = [p.grad for p in self.params if p.grad is not None and p.numel() <= (1 << 20)]
+        for g in big:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        if small:
+            flat = torch.cat([g.reshape(-1) for g in small])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            o = 0
+            for g in small:
+                g.copy_(flat[o:o + g.numel()].view_as(g))
+                o += g.numel()
+
+    def step(self, rays_o, rays_d, target_rgb, target_cls, n_global=None):
+        """rays_* [n,3], target_rgb [n,3] f32, target_cls [n] int64 -- all on the device.  Returns the loss tensor
+        (device; no host sync here beyond the one inside march_rays_train and GradScaler.step)."""
+        n_local = rays_o.shape[0]
+        n_global = n_global or n_local * self.world_size
+        with torch.autocast('cuda', dtype=torch.float16, enabled=self.enable_amp):
+            image, depth, classes = self.renderer.render_train(rays_o, rays_d)
+            loss, mse = self.loss_fn(image, classes, target_rgb, target_cls)
+        self.optim.zero_grad(set_to_none=True)
+        back = loss * (n_local * self.world_size / n_global) / self.world_size if self.world_size > 1 else loss
+        self.scaler.scale(back).backward()
+        self.allreduce_grads()
+        self.scaler.step(self.optim)
+        old_scale = self.scaler.get_scale() if self.enable_amp else 1.0
+        self.scaler.update()
+        if not self.enable_amp or old_scale <= self.scaler.get_scale():
+            self.scheduler.step()
+        if self.ema is not None:
+            with torch.no_grad():
+                torch._foreach_mul_(self.ema, self.ema_decay)
+                torch._foreach_add_(self.ema, [p.detach() for p in self.params], alpha=1.0 - self.ema_decay)
+        self.iter_ctr += 1
+        return loss.detach()

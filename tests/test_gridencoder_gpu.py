@@ -1,0 +1,151 @@
+"""GPU parity of the hash-grid encoder against the CPU oracle.  fp32 forward: bit-exact (same hash rows, same fma
+chain).  fp16 tables: <= 1 half ulp.  Backward (sum order differs from any atomics schedule): rel 1e-5 of max."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def _default_encoder(dev, seed=0, std=1.0):
+    from nerfstyle_b200.model import get_grid_encoder
+    enc = get_grid_encoder(max_bound=4.0).to(dev)
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        enc.embeddings.copy_(((torch.rand(enc.embeddings.shape, generator=g) * 2 - 1) * std).to(dev))
+    return enc
+
+
+def _points(B, seed, dev, lo=0.0, hi=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(B, 3, generator=g) * (hi - lo) + lo).to(dev)
+
+
+@pytest.mark.parametrize('B', [1, 255, 4099])
+@pytest.mark.parametrize('lpt', [16, 4, 1])
+def test_forward_fp32_bit_exact(cuda_lib, oracle, dev, B, lpt):
+    cuda_lib.nrf_grid_set_tuning(lpt, 0, -1)
+    try:
+        enc = _default_encoder(dev)
+        x = _points(B, B, dev, -1.0, 1.0)                       # GridEncoder.forward remaps [-1,1] -> [0,1]
+        x[0] = torch.tensor([1.0, -1.0, 0.0], device=dev)       # exact borders
+        out = enc(x)
+        inp = ((x + 1) / 2).cpu().numpy()
+        eo, _ = oracle.grid_encode_forward(inp, enc.embeddings.detach().cpu().numpy(), enc.offsets.cpu().numpy(),
+                                           enc.per_level_scale, 16, False, 0, True, 0)
+        assert out.shape == (B, 32) and out.dtype == torch.float32
+        assert np.array_equal(out.detach().cpu().numpy().view(np.uint32), eo.view(np.uint32))
+    finally:
+        cuda_lib.nrf_grid_set_tuning(16, 0, -1)
+
+
+def test_forward_golden_and_oob(cuda_lib, dev):
+    from nerfstyle_b200.gridencoder import grid_encode
+    g = np.load(os.path.join(GOLD, 'grid_small.npz'))
+    offs, pls = torch.from_numpy(g['offsets']).to(dev), float(g['per_level_scale'])
+    emb = torch.from_numpy(np.random.RandomState(int(g['emb_seed'])).uniform(-1, 1, (int(g['offsets'][-1]), 2)).astype(np.float32)).to(dev)
+    x = torch.from_numpy(g['inputs']).to(dev)
+    out = grid_encode(x, emb, offs, pls, 16, False, 0, True, 0)
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), g['outputs'].view(np.uint32))
+    assert float(out[3].abs().sum()) == 0.0                     # out-of-range input -> zeros (gridencoder.cu:107-132)
+    with torch.autocast('cuda', dtype=torch.float16):
+        out_h = grid_encode(x, emb, offs, pls, 16, False, 0, True, 0)
+    assert out_h.dtype == torch.float16
+    diff = np.abs(out_h.float().cpu().numpy() - g['outputs_half'].astype(np.float32))
+    ulp = np.maximum(np.abs(g['outputs_half'].astype(np.float32)), 2.0 ** -14) * 2.0 ** -10
+    assert (diff <= ulp + 1e-12).all()
+
+
+def test_forward_fp16_autocast(cuda_lib, oracle, dev):
+    enc = _default_encoder(dev)
+    x = _points(3001, 7, dev, -1.0, 1.0)
+    with torch.autocast('cuda', dtype=torch.float16):
+        out = enc(x)
+    assert out.dtype == torch.float16
+    inp = ((x + 1) / 2).cpu().numpy()
+    eo, _ = oracle.grid_encode_forward(inp, enc.embeddings.detach().half().cpu().numpy(), enc.offsets.cpu().numpy(),
+                                       enc.per_level_scale, 16, False, 0, True, 0, half=True)
+    a, b = out.float().cpu().numpy(), eo.astype(np.float32)
+    ulp = np.maximum(np.abs(b), 2.0 ** -14) * 2.0 ** -10
+    assert (np.abs(a - b) <= ulp + 1e-12).all()
+    assert (a != b).mean() < 0.02
+
+
+@pytest.mark.parametrize('agg', [0, 24, 32])
+@pytest.mark.parametrize('lpt', [16, 4])
+def test_backward_fp32(cuda_lib, oracle, dev, agg, lpt):
+    cuda_lib.nrf_grid_set_tuning(0, lpt, agg)
+    try:
+        enc = _default_encoder(dev)
+        B = 6000
+        # half of the points along a few rays (coherent -> exercises the warp aggregation), half random
+        t = torch.linspace(0, 1, B // 2, device=dev)[:, None]
+        line = torch.tensor([[-0.9, -0.7, 0.3]], device=dev) + t * torch.tensor([[1.7, 1.1, 0.4]], device=dev)
+        x = torch.cat([line, _points(B - B // 2, 3, dev, -1.0, 1.0)], dim=0)
+        x[5] = 3.0                                             # one out-of-range point: no gradient
+        out = enc(x)
+        g = torch.Generator().manual_seed(1)
+        grad = torch.randn(out.shape, generator=g).to(dev)
+        out.backward(grad)
+        ge = enc.embeddings.grad.cpu().numpy()
+        inp = ((x + 1) / 2).cpu().numpy()
+        ege = oracle.grid_encode_backward(grad.cpu().numpy(), inp, enc.offsets.cpu().numpy(), enc.embeddings.shape[0], 2,
+                                          enc.per_level_scale, 16, 0, True, 0)
+        scale = np.abs(ege).max()
+        assert np.abs(ge - ege).max() <= 1e-5 * scale
+        assert (ge != 0).sum() == (ege != 0).sum()
+    finally:
+        cuda_lib.nrf_grid_set_tuning(0, 16, 24)
+
+
+def test_backward_fp16_autocast(cuda_lib, oracle, dev):
+    enc = _default_encoder(dev)
+    x = _points(4000, 11, dev, -1.0, 1.0)
+    with torch.autocast('cuda', dtype=torch.float16):
+        out = enc(x)
+    g = torch.Generator().manual_seed(2)
+    grad = torch.randn(out.shape, generator=g).to(dev).half()
+    out.backward(grad)
+    ge = enc.embeddings.grad
+    assert ge.dtype == torch.float32                           # autograd casts the half table grad back
+    ege = oracle.grid_encode_backward(grad.float().cpu().numpy(), ((x + 1) / 2).cpu().numpy(), enc.offsets.cpu().numpy(),
+                                      enc.embeddings.shape[0], 2, enc.per_level_scale, 16, 0, True, 0)   # exact fp32 value
+    # every atomic add rounds to half: tolerance = a few half ulps of the largest partial sum
+    err = np.abs(ge.cpu().numpy() - ege)
+    assert err.max() <= 8 * 2.0 ** -10 * np.abs(ege).max()
+    assert np.median(err[ege != 0] / np.abs(ege[ege != 0])) < 2e-3
+
+
+@pytest.mark.parametrize('D,C,gridtype,align', [(3, 4, 0, False), (2, 2, 1, True), (3, 1, 0, True), (3, 8, 1, False)])
+def test_generic_paths_and_input_grads(cuda_lib, oracle, dev, D, C, gridtype, align):
+    from nerfstyle_b200.gridencoder import GridEncoder
+    enc = GridEncoder(input_dim=D, num_levels=6, level_dim=C, per_level_scale=1.7, base_resolution=8, log2_hashmap_size=12,
+                      gridtype='hash' if gridtype == 0 else 'tiled', align_corners=align).to(dev)
+    g = torch.Generator().manual_seed(4)
+    with torch.no_grad():
+        enc.embeddings.copy_((torch.rand(enc.embeddings.shape, generator=g) * 2 - 1).to(dev))
+    x = (torch.rand(1500, D, generator=g) * 2 - 1).to(dev).requires_grad_(True)
+    out = enc(x)
+    grad = torch.randn(out.shape, generator=g).to(dev)
+    out.backward(grad)
+    inp = ((x.detach() + 1) / 2).cpu().numpy()
+    eo, edy = oracle.grid_encode_forward(inp, enc.embeddings.detach().cpu().numpy(), enc.offsets.cpu().numpy(), 1.7, 8, True,
+                                         gridtype, align, 0)
+    assert np.array_equal(out.detach().cpu().numpy().view(np.uint32), eo.view(np.uint32))
+    ege = oracle.grid_encode_backward(grad.cpu().numpy(), inp, enc.offsets.cpu().numpy(), enc.embeddings.shape[0], C, 1.7, 8,
+                                      gridtype, align, 0)
+    assert np.abs(enc.embeddings.grad.cpu().numpy() - ege).max() <= 1e-5 * np.abs(ege).max()
+    egi = oracle.grid_input_backward(grad.cpu().numpy(), edy, 1500, D, C, 6) * 0.5     # d/dx of (x+1)/2
+    np.testing.assert_allclose(x.grad.cpu().numpy(), egi, rtol=1e-5, atol=1e-5 * np.abs(egi).max())
+
+
+def test_empty_and_errors(cuda_lib, dev):
+    enc = _default_encoder(dev)
+    out = enc(torch.zeros(0, 3, device=dev))
+    assert out.shape == (0, 32)
+    with pytest.raises(RuntimeError):
+        enc(torch.zeros(4, 3))                                   # CPU tensor: no fallback
+    assert cuda_lib.nrf_grid_encode_forward(1, 1, 1, 1, 4, 7, 2, 16, 0.5, 16, 0, None, 0, 1, 0, 0, 1, None) == -2

@@ -1,0 +1,70 @@
+"""GPU parity of the fused MLP (tcnn-style Network) against the oracle definition: fp16 operands,
+fp32 accumulation, hidden activations rounded to fp16.  Tolerance: 2 fp16 ulp of the output scale (forward),
+1e-2 of the gradient scale (backward; dZ / dH are rounded to fp16 on the way)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+NETS = {'density': (32, 1, 1, 'None'), 'class': (32, 8, 1, 'None'), 'color1': (32, 16, 1, 'None'),
+        'color2': (16, 3, 2, 'Sigmoid'), 'odd': (27, 5, 2, 'None'), 'wide_in': (64, 12, 1, 'Sigmoid')}
+
+
+def _net(name, dev, seed=3):
+    from nerfstyle_b200 import tcnn
+    ni, no, nh, act = NETS[name]
+    net = tcnn.Network(ni, no, {'otype': 'FullyFusedMLP', 'activation': 'ReLU', 'output_activation': act, 'n_neurons': 64,
+                                'n_hidden_layers': nh}, seed=seed).to(dev)
+    return net, (ni, no, nh, act.lower())
+
+
+@pytest.mark.parametrize('name', list(NETS))
+@pytest.mark.parametrize('B,xdtype', [(4099, torch.float16), (128, torch.float32), (1, torch.float16)])
+def test_forward(cuda_lib, dev, name, B, xdtype):
+    from oracle import field
+    net, (ni, no, nh, act) = _net(name, dev)
+    g = torch.Generator().manual_seed(B)
+    x = (torch.randn(B, ni, generator=g)).to(dev).to(xdtype)
+    y = net(x)
+    assert y.shape == (B, no) and y.dtype == torch.float16
+    ey = field.mlp_forward(x.float().cpu(), net.params.detach().cpu(), ni, no, nh, 'relu', act, half=True)
+    a, b = y.float().cpu().numpy(), ey.detach().numpy()
+    tol = 2 * 2.0 ** -10 * np.maximum(np.abs(b), np.abs(b).max() * 0.05) + 1e-6
+    assert (np.abs(a - b) <= tol).all(), np.abs(a - b).max()
+
+
+@pytest.mark.parametrize('name', list(NETS))
+@pytest.mark.parametrize('xdtype', [torch.float16, torch.float32])
+def test_backward(cuda_lib, dev, name, xdtype):
+    from oracle import field
+    net, (ni, no, nh, act) = _net(name, dev)
+    B = 3000
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B, ni, generator=g).to(dev).to(xdtype).requires_grad_(True)
+    dy = (torch.randn(B, no, generator=g) * 0.1).to(dev).half()
+    y = net(x)
+    y.backward(dy)
+    assert x.grad.dtype == xdtype and net.params.grad.dtype == torch.float32
+    xc = x.detach().float().cpu().requires_grad_(True)
+    pc = net.params.detach().cpu().requires_grad_(True)
+    ey = field.mlp_forward(xc, pc, ni, no, nh, 'relu', act, half=True)
+    ey.backward(dy.float().cpu())
+    gx, egx = x.grad.float().cpu().numpy(), xc.grad.numpy()
+    gp, egp = net.params.grad.cpu().numpy(), pc.grad.numpy()
+    assert np.abs(gx - egx).max() <= 1e-2 * np.abs(egx).max()
+    assert np.abs(gp - egp).max() <= 1e-2 * np.abs(egp).max()
+    # padded rows / columns of the tcnn layout receive exactly zero gradient
+    views = net.layer_views(net.params.grad)
+    assert float(views[-1][no:].abs().sum()) == 0.0
+    assert float(views[0][:, ni:].abs().sum()) == 0.0
+
+
+def test_grad_accumulation_and_no_input_grad(cuda_lib, dev):
+    net, (ni, no, nh, act) = _net('density', dev)
+    x = torch.randn(513, ni, device=dev).half()          # no grad on the input: dx is skipped
+    net(x).sum().backward()
+    g1 = net.params.grad.clone()
+    net(x).sum().backward()
+    torch.testing.assert_close(net.params.grad, 2 * g1, rtol=1e-5, atol=1e-6)
+    assert net(torch.zeros(0, ni, device=dev).half()).shape == (0, no)

@@ -1,0 +1,103 @@
+"""End-to-end parity of one train step (BASELINE config 1: 4096 rays, 16-level 2^19 hash grids x2, 4 MLPs,
+composite fwd+bwd) through the drop-in modules against the CPU oracle pipeline."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(dev, half_tables, n_rays=4096, table_std=0.5):
+    from nerfstyle_b200 import model as M, raymarching, scenes
+    from oracle import field
+    of = field.OracleField(bound=2.0, n_classes=8, half=half_tables, seed=0, table_std=table_std)
+    m = M.StyleTCNerf([-2., -2., -2.], [2., 2., 2.], class_dim=8).to(dev)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            p.copy_(of.params[n].detach().to(dev))
+    r = M.Renderer(m, 2.0, raymarch_channels=11).to(dev)
+    r.update_occ = False
+    grid = scenes.analytic_density_grid(2, 128, 2.0)
+    bits = raymarching.packbits(grid.to(dev), 0.5)
+    r.density_bitfield = bits
+    o, d = scenes.random_rays(n_rays, 0, dev)
+    return of, m, r, o, d, bits
+
+
+@pytest.mark.parametrize('amp', [False, True])
+def test_train_step_matches_oracle(cuda_lib, oracle, dev, amp):
+    from oracle import field
+    of, m, r, o, d, bits = _build(dev, half_tables=amp)
+    g = torch.Generator().manual_seed(9)
+    target = torch.rand(o.shape[0], 3, generator=g)
+    tcls = torch.randint(0, 8, (o.shape[0],), generator=g)
+    with torch.autocast('cuda', dtype=torch.float16, enabled=amp):
+        image, depth, classes = r.render_train(o, d)
+        loss = torch.mean((image - target.to(dev)) ** 2) + 0.001 * torch.nn.functional.cross_entropy(classes, tcls.to(dev))
+    scale = 1024.0 if amp else 1.0
+    (loss * scale).backward()
+    out = field.render_train(of, o.cpu().numpy(), d.cpu().numpy(), bits.cpu().numpy(), 2, 128, 2.0)
+    eloss = field.train_step_loss(out, target, tcls)
+    (eloss * scale).backward()
+    # integers: bit-exact
+    n_s = int(out['counter'][0])
+    assert n_s > 100000
+    # floats
+    img, eimg = image.detach().float().cpu().numpy(), out['rgb'].detach().numpy()
+    mse = float(np.mean((img - eimg) ** 2))
+    assert np.abs(img - eimg).max() < (2e-3 if amp else 5e-4), np.abs(img - eimg).max()
+    psnr_delta = abs(10 * math.log10(max(np.mean((img - target.numpy()) ** 2), 1e-12)) -
+                     10 * math.log10(max(np.mean((eimg - target.numpy()) ** 2), 1e-12)))
+    assert psnr_delta < 0.01, psnr_delta
+    assert abs(float(loss) - float(eloss)) < 1e-3 * abs(float(eloss)) + 1e-6, (float(loss), float(eloss), mse)
+    np.testing.assert_allclose(classes.detach().float().cpu().numpy(), out['classes'].detach().numpy(), atol=5e-3 if amp else 1e-3)
+    # gradients of every parameter (normalised max error)
+    for name, p in m.named_parameters():
+        gp = p.grad.float().cpu().numpy()
+        eg = of.params[name].grad.numpy()
+        denom = np.abs(eg).max()
+        assert denom > 0, name
+        tol = 3e-2 if amp else 1e-2
+        assert np.abs(gp - eg).max() <= tol * denom, (name, np.abs(gp - eg).max() / denom)
+
+
+def test_render_test_matches_render_train(cuda_lib, dev):
+    """The inference loop (march_rays/composite_rays) and the training path render the same image when no ray
+    terminates early (T_thresh = 0 in both)."""
+    of, m, r, o, d, bits = _build(dev, half_tables=False, n_rays=1500, table_std=0.2)
+    r.t_thresh = 0.0
+    with torch.no_grad():
+        a_img, a_depth, a_cls = r.render_train(o, d)
+        b_img, b_depth, b_cls = r.render_test(o, d)
+    torch.testing.assert_close(a_img, b_img, rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(a_cls, b_cls, rtol=1e-3, atol=1e-4)
+
+
+def test_update_state_and_steps(cuda_lib, dev):
+    """Occupancy update + a few optimiser steps run end to end and reduce the loss."""
+    from nerfstyle_b200 import model as M, scenes
+    torch.manual_seed(0)
+    m = M.StyleTCNerf([-2., -2., -2.], [2., 2., 2.], class_dim=8).to(dev)
+    r = M.Renderer(m, 2.0, raymarch_channels=11).to(dev)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-2, eps=1e-15)
+    intr = dict(scenes.ROOM)
+    pose = scenes.synthetic_poses(2, 0)[0]
+    gen = torch.Generator().manual_seed(0)
+    losses = []
+    for it in range(6):
+        idx = scenes.frame_indices(intr, 1024, gen).to(dev)
+        o, d = scenes.generate_rays(pose, intr, dev, idx)
+        tgt, seg = scenes.synthetic_target(idx, intr)
+        with torch.autocast('cuda', dtype=torch.float16):
+            img, depth, cls = r.render_train(o, d)
+            loss = torch.mean((img - tgt) ** 2)
+        opt.zero_grad()
+        (loss * 128).backward()
+        for p in m.parameters():
+            p.grad.div_(128)
+        opt.step()
+        losses.append(float(loss))
+    assert r.local_step == 6 and r.mean_density > 0 and int(r.density_bitfield.count_nonzero()) > 0
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
