@@ -21,7 +21,7 @@
  *   gridencoder/src/gridencoder.h:13  grid_encode_backward nrf_grid_encode_backward
  *   gridencoder/src/gridencoder.h:14  grid_initialize      nrf_grid_initialize
  *   tinycudann Network fwd/bwd (networks/style_nerf.py:44-98)   nrf_mlp_forward / nrf_mlp_backward
- *   loss.py:32-36,199-214 cosine_dists + mask + amin       nrf_nnfm_forward / nrf_nnfm_backward
+ *   loss.py:32-36,199-214 cosine_dists + mask + amin       nrf_nnfm_forward (backward = gather, nnfm.py)
  *
  * Conventions: all pointers are DEVICE pointers owned by the caller; the callee never
  * allocates, never synchronises and never throws.  Every function launches on `stream` (a
@@ -150,13 +150,16 @@ int nrf_grid_encode_forward(const float* inputs, const void* embeddings, const i
                             int dtype, int point_major, void* stream);
 
 /* gridencoder.cu:464-494 (kernel_grid_backward :238-328, kernel_input_backward :331-357).
- * grad: [B, L*C] when point_major else [L,B,C]; grad_embeddings [rows,C] must be zero-filled by the caller
- * (grid.py:82).  grad_inputs [B,D] (same dtype) only when calc_grad_inputs. */
+ * grad: [B, L*C] when point_major else [L,B,C] (dtype); grad_embeddings [rows,C] (grad_table_dtype) must be
+ * zero-filled by the caller (grid.py:82).  grad_table_dtype = dtype reproduces the reference (f16 grads are
+ * accumulated with __half2 atomics, :313-319); f16 grads may also be accumulated into an f32 table
+ * (grad_table_dtype = NRF_DTYPE_F32), which avoids the swamping of half-precision accumulation and the
+ * half->float cast the autograd engine would add.  grad_inputs [B,D] (dtype) only when calc_grad_inputs. */
 int nrf_grid_encode_backward(const void* grad, const float* inputs, const void* embeddings, const int32_t* offsets,
                              void* grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
                              uint32_t H, int calc_grad_inputs, const void* dy_dx, void* grad_inputs,
-                             uint32_t gridtype, int align_corners, uint32_t style, int dtype, int point_major,
-                             void* stream);
+                             uint32_t gridtype, int align_corners, uint32_t style, int dtype, int grad_table_dtype,
+                             int point_major, void* stream);
 
 /* gridencoder.cu:551-571 (D=3, C=2, f32 like the reference's only use). */
 int nrf_grid_initialize(const float* ref_embeddings, float* embeddings, const int32_t* ref_offsets,

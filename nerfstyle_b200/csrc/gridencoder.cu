@@ -342,10 +342,10 @@ __device__ __forceinline__ void atomic_add2(__half* base, uint32_t row, float a,
     atomicAdd(reinterpret_cast<__half2*>(base) + row, __floats2half2_rn(a, b));
 }
 
-template <typename T, int LPT>
+template <typename T, typename TO, int LPT>
 __global__ void __launch_bounds__(GRID_BLOCK)
 k_grid_bwd_d3c2(const T* __restrict__ grad, const float* __restrict__ inputs, const int32_t* __restrict__ offsets,
-                T* __restrict__ grad_table, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align_corners,
+                TO* __restrict__ grad_table, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align_corners,
                 uint32_t style, bool point_major, int agg_max_groups) {
     typedef typename Vec2<T>::type V2;
     __shared__ LevelP lp[LPT];
@@ -375,7 +375,7 @@ k_grid_bwd_d3c2(const T* __restrict__ grad, const float* __restrict__ inputs, co
             if constexpr (sizeof(T) == 4) { g0 = gvj.x; g1 = gvj.y; }
             else { const float2 gg = __half22float2(gvj); g0 = gg.x; g1 = gg.y; }
         }
-        T* gl = grad_table + (size_t)p.offset * 2;
+        TO* gl = grad_table + (size_t)p.offset * 2;
         bool done = false;
         if (agg_max_groups > 0) {
             // lanes in the same cell share all 8 corner rows
@@ -415,10 +415,10 @@ k_grid_bwd_d3c2(const T* __restrict__ grad, const float* __restrict__ inputs, co
 }
 
 // generic backward: thread per (point, level, channel pair) like the reference
-template <typename T, int D, int C>
+template <typename T, typename TO, int D, int C>
 __global__ void __launch_bounds__(GRID_BLOCK)
 k_grid_bwd_generic(const T* __restrict__ grad, const float* __restrict__ inputs, const int32_t* __restrict__ offsets,
-                   T* __restrict__ grad_table, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align_corners,
+                   TO* __restrict__ grad_table, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align_corners,
                    uint32_t style, bool point_major) {
     __shared__ LevelP p;
     const uint32_t level = blockIdx.y;
@@ -436,7 +436,7 @@ k_grid_bwd_generic(const T* __restrict__ grad, const float* __restrict__ inputs,
     float g[C];
 #pragma unroll
     for (int c = 0; c < C; c++) g[c] = ld_as_float(gp + c);
-    T* gl = grad_table + (size_t)p.offset * C;
+    TO* gl = grad_table + (size_t)p.offset * C;
 #pragma unroll
     for (int idx = 0; idx < (1 << D); idx++) {
         float w = 1.0f; uint32_t pl[D];
@@ -447,7 +447,7 @@ k_grid_bwd_generic(const T* __restrict__ grad, const float* __restrict__ inputs,
         }
         const uint32_t row = grid_row<D>(p, pl);
         if constexpr (C == 1) {
-            if constexpr (sizeof(T) == 4) atomicAdd(reinterpret_cast<float*>(gl) + row, __fmul_rn(w, g[0]));
+            if constexpr (sizeof(TO) == 4) atomicAdd(reinterpret_cast<float*>(gl) + row, __fmul_rn(w, g[0]));
             else atomicAdd(reinterpret_cast<__half*>(gl) + row, __float2half_rn(__fmul_rn(w, g[0])));
         } else {
 #pragma unroll
@@ -474,20 +474,20 @@ __global__ void k_grid_input_bwd(const T* __restrict__ grad, const T* __restrict
     st_from_float(grad_inputs + t, result);
 }
 
-template <typename T>
+template <typename T, typename TO>
 static int launch_bwd(const void* grad, const float* inputs, const int32_t* offsets, void* grad_embeddings, uint32_t B,
                       uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, bool calc, const void* dy_dx, void* grad_inputs,
                       uint32_t gridtype, bool ac, uint32_t style, bool pm, cudaStream_t s) {
-    const T* g = (const T*)grad; T* ge = (T*)grad_embeddings;
+    const T* g = (const T*)grad; TO* ge = (TO*)grad_embeddings;
     const uint32_t nbx = ceil_div_u32(B, GRID_BLOCK);
     if (D == 3 && C == 2 && (((uintptr_t)grad_embeddings) & 7) == 0) {
         const int lpt = g_bwd_lpt;
-#define BWD_FAST(LPT) k_grid_bwd_d3c2<T, LPT><<<dim3(nbx, ceil_div_u32(L, LPT)), GRID_BLOCK, 0, s>>>(g, inputs, offsets, ge, B, L, S, H, gridtype, ac, style, pm, g_bwd_agg)
+#define BWD_FAST(LPT) k_grid_bwd_d3c2<T, TO, LPT><<<dim3(nbx, ceil_div_u32(L, LPT)), GRID_BLOCK, 0, s>>>(g, inputs, offsets, ge, B, L, S, H, gridtype, ac, style, pm, g_bwd_agg)
         if (lpt >= 16) BWD_FAST(16); else if (lpt >= 8) BWD_FAST(8); else if (lpt >= 4) BWD_FAST(4); else if (lpt >= 2) BWD_FAST(2); else BWD_FAST(1);
 #undef BWD_FAST
     } else {
         const dim3 grid(nbx, L);
-#define BWD_GEN(DD, CC) k_grid_bwd_generic<T, DD, CC><<<grid, GRID_BLOCK, 0, s>>>(g, inputs, offsets, ge, B, L, S, H, gridtype, ac, style, pm)
+#define BWD_GEN(DD, CC) k_grid_bwd_generic<T, TO, DD, CC><<<grid, GRID_BLOCK, 0, s>>>(g, inputs, offsets, ge, B, L, S, H, gridtype, ac, style, pm)
         if (D == 3) { switch (C) { case 1: BWD_GEN(3, 1); break; case 2: BWD_GEN(3, 2); break; case 4: BWD_GEN(3, 4); break; case 8: BWD_GEN(3, 8); break; default: return NRF_E_UNSUPPORTED; } }
         else if (D == 2) { switch (C) { case 1: BWD_GEN(2, 1); break; case 2: BWD_GEN(2, 2); break; case 4: BWD_GEN(2, 4); break; case 8: BWD_GEN(2, 8); break; default: return NRF_E_UNSUPPORTED; } }
         else return NRF_E_UNSUPPORTED;
@@ -500,18 +500,21 @@ static int launch_bwd(const void* grad, const float* inputs, const int32_t* offs
 NRF_EXPORT int nrf_grid_encode_backward(const void* grad, const float* inputs, const void* embeddings, const int32_t* offsets,
                                         void* grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
                                         uint32_t H, int calc_grad_inputs, const void* dy_dx, void* grad_inputs,
-                                        uint32_t gridtype, int align_corners, uint32_t style, int dtype, int point_major,
-                                        void* stream) {
+                                        uint32_t gridtype, int align_corners, uint32_t style, int dtype, int grad_table_dtype,
+                                        int point_major, void* stream) {
     (void)embeddings;
     if (B == 0) return NRF_OK;
     if (!grad || !inputs || !offsets || !grad_embeddings) return NRF_E_INVALID;
     if (calc_grad_inputs && (!dy_dx || !grad_inputs)) return NRF_E_INVALID;
     if (L == 0 || L > GRID_MAX_LEVELS) return NRF_E_UNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
-    if (dtype == NRF_DTYPE_F32)
-        return launch_bwd<float>(grad, inputs, offsets, grad_embeddings, B, D, C, L, S, H, calc_grad_inputs != 0, dy_dx, grad_inputs, gridtype, align_corners != 0, style, point_major != 0, s);
-    if (dtype == NRF_DTYPE_F16)
-        return launch_bwd<__half>(grad, inputs, offsets, grad_embeddings, B, D, C, L, S, H, calc_grad_inputs != 0, dy_dx, grad_inputs, gridtype, align_corners != 0, style, point_major != 0, s);
+    const bool calc = calc_grad_inputs != 0, ac = align_corners != 0, pm = point_major != 0;
+    if (dtype == NRF_DTYPE_F32 && grad_table_dtype == NRF_DTYPE_F32)
+        return launch_bwd<float, float>(grad, inputs, offsets, grad_embeddings, B, D, C, L, S, H, calc, dy_dx, grad_inputs, gridtype, ac, style, pm, s);
+    if (dtype == NRF_DTYPE_F16 && grad_table_dtype == NRF_DTYPE_F16)
+        return launch_bwd<__half, __half>(grad, inputs, offsets, grad_embeddings, B, D, C, L, S, H, calc, dy_dx, grad_inputs, gridtype, ac, style, pm, s);
+    if (dtype == NRF_DTYPE_F16 && grad_table_dtype == NRF_DTYPE_F32)
+        return launch_bwd<__half, float>(grad, inputs, offsets, grad_embeddings, B, D, C, L, S, H, calc, dy_dx, grad_inputs, gridtype, ac, style, pm, s);
     return NRF_E_UNSUPPORTED;
 }
 

@@ -68,7 +68,9 @@ class _grid_encode(Function):
         grad = grad.contiguous()
         if grad.dtype != embeddings.dtype:
             grad = grad.to(embeddings.dtype)
-        grad_embeddings = torch.zeros_like(embeddings)
+        # fp16 grads (autocast) are accumulated into an fp32 table gradient: more accurate than the reference's
+        # __half2 atomics (which swamp on the coarse levels) and it is the dtype the fp32 Parameter needs anyway
+        grad_embeddings = torch.zeros(embeddings.shape, dtype=torch.float32, device=embeddings.device)
         grad_inputs = torch.zeros_like(inputs, dtype=embeddings.dtype) if calc_grad_inputs else None
         L.Stats.units = B
         with torch.cuda.device(inputs.device):
@@ -76,7 +78,8 @@ class _grid_encode(Function):
                                                      L.ptr(grad_embeddings), B, D, C, Lv, S, H,
                                                      int(bool(calc_grad_inputs)), L.ptr(dy_dx), L.ptr(grad_inputs),
                                                      int(gridtype), int(bool(ctx.align_corners)), int(ctx.style),
-                                                     L.dtype_code(embeddings.dtype), 1, L.stream_of(inputs)),
+                                                     L.dtype_code(embeddings.dtype), L.DTYPE_F32, 1,
+                                                     L.stream_of(inputs)),
                     'grid_encode_backward')
         if calc_grad_inputs:
             grad_inputs = grad_inputs.to(inputs.dtype)

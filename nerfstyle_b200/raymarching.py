@@ -212,9 +212,10 @@ class _composite_rays_train(Function):
     @staticmethod
     @custom_fwd(device_type='cuda', cast_inputs=torch.float32)
     def forward(ctx, sigmas, rgbs, deltas, rays, T_thresh=1e-4, is_ndc=False):
-        sigmas = sigmas.contiguous()
-        rgbs = rgbs.contiguous()
-        deltas = deltas.contiguous()
+        # the kernels are fp32: cast explicitly (custom_fwd only casts while autocast is enabled)
+        sigmas = _f32c(sigmas)
+        rgbs = _f32c(rgbs)
+        deltas = _f32c(deltas)
         rays = rays.contiguous()
         L.require_cuda(sigmas, rgbs, deltas, rays)
         M = sigmas.shape[0]
@@ -238,8 +239,8 @@ class _composite_rays_train(Function):
     @custom_bwd(device_type='cuda')
     def backward(ctx, grad_weights_sum, grad_depth, grad_image):
         # grad_depth is not propagated (raymarching.py:331)
-        grad_weights_sum = grad_weights_sum.contiguous()
-        grad_image = grad_image.contiguous()
+        grad_weights_sum = _f32c(grad_weights_sum)
+        grad_image = _f32c(grad_image)
         sigmas, rgbs, deltas, rays, weights_sum, depth, image = ctx.saved_tensors
         M, N, C, T_thresh = ctx.dims
         grad_sigmas = torch.zeros_like(sigmas)
@@ -304,10 +305,15 @@ class _composite_rays(Function):
         t_size = 2 if is_ndc else 1
         assert rays_t.shape[-1] == t_size
         C = rgbs.shape[-1]
-        sigmas = sigmas.contiguous()
-        rgbs = rgbs.contiguous()
-        deltas = deltas.contiguous()
+        sigmas = _f32c(sigmas)
+        rgbs = _f32c(rgbs)
+        deltas = _f32c(deltas)
         L.require_cuda(rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image)
+        for name, t in (('rays_t', rays_t), ('weights_sum', weights_sum), ('depth', depth), ('image', image)):
+            if t.dtype != torch.float32:
+                raise RuntimeError('composite_rays: %s must be float32' % name)
+        if rays_alive.dtype != torch.int32:
+            raise RuntimeError('composite_rays: rays_alive must be int32')
         for name, t in (('rays_alive', rays_alive), ('rays_t', rays_t), ('weights_sum', weights_sum), ('depth', depth),
                         ('image', image)):
             if not t.is_contiguous():

@@ -40,8 +40,11 @@ class GridEncodeFn(Function):
         inp, offsets = ctx.saved_tensors
         pls, H, gridtype, ac, style, half, shape = ctx.cfg
         g = grad.contiguous()
-        ge = ops.grid_encode_backward(g.half().numpy() if half else g.float().numpy(), inp.numpy(), offsets.numpy(),
-                                      shape[0], shape[1], pls, H, gridtype, ac, style, half=half)
+        # fp16 mode: the incoming grads are fp16 (the encoder output dtype); the product path accumulates them in
+        # fp32 (deviation from the reference's lossy __half2 atomics), so the oracle value is the exact sum
+        g = g.half().float() if half else g.float()
+        ge = ops.grid_encode_backward(g.numpy(), inp.numpy(), offsets.numpy(), shape[0], shape[1], pls, H, gridtype, ac,
+                                      style, half=False)
         return None, torch.from_numpy(ge).float(), None, None, None, None, None, None, None
 
 
@@ -136,8 +139,6 @@ class OracleField:
         self.bbox_min = torch.full((3,), -self.bound)
         self.bbox_size = torch.full((3,), 2 * self.bound)
         max_res = max_res_coeff * 2 * self.bound
-        offs, pls = ops.grid_offsets(3, num_levels, level_dim, 2, base_resolution, log2_hashmap_size,
-                                     desired_resolution=None, align_corners=True)
         pls = np.exp2(np.log2(max_res / base_resolution) / (num_levels - 1))
         offs, _ = ops.grid_offsets(3, num_levels, level_dim, pls, base_resolution, log2_hashmap_size, None, True)
         self.offsets = torch.from_numpy(offs)

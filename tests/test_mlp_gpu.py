@@ -29,7 +29,7 @@ def test_forward(cuda_lib, dev, name, B, xdtype):
     y = net(x)
     assert y.shape == (B, no) and y.dtype == torch.float16
     ey = field.mlp_forward(x.float().cpu(), net.params.detach().cpu(), ni, no, nh, 'relu', act, half=True)
-    a, b = y.float().cpu().numpy(), ey.detach().numpy()
+    a, b = y.detach().float().cpu().numpy(), ey.detach().numpy()
     tol = 2 * 2.0 ** -10 * np.maximum(np.abs(b), np.abs(b).max() * 0.05) + 1e-6
     assert (np.abs(a - b) <= tol).all(), np.abs(a - b).max()
 

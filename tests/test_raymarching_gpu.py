@@ -76,8 +76,6 @@ def test_march_rays_train_bit_exact(cuda_lib, oracle, dev, kind, max_steps, dt_g
     assert xyzs.shape == ex.shape and xyzs.shape[0] % 128 == 0 and xyzs.shape[0] > ec[0]
     for a, b in ((xyzs, ex), (dirs, ed), (deltas, el)):
         assert np.array_equal(a.cpu().numpy().view(np.uint32), b.view(np.uint32))
-    if max_steps == 96:
-        assert (er[:, 2] == 96).any()                                   # the cap was hit
 
 
 def test_march_rays_train_edge_cases(cuda_lib, oracle, dev):
@@ -111,7 +109,29 @@ def test_march_rays_train_edge_cases(cuda_lib, oracle, dev):
     e = torch.zeros(0, 3, device=dev)
     xyzs, dirs, deltas, rays = raymarching.march_rays_train(e, e, None, 2.0, bits, 2, 128, e[:, 0], e[:, 0], None, -1, False,
                                                             128, True, 0., 1024, False)
-    assert rays.shape == (0, 3) and xyzs.shape[0] == 128
+    assert rays.shape == (0, 3) and xyzs.shape[0] == 0           # zeros(0,3)[:128] in the reference
+
+
+def test_march_rays_train_hits_max_steps(cuda_lib, oracle, dev):
+    """Fully occupied grid + rays along the box diagonals: every ray is cut at max_steps samples."""
+    from nerfstyle_b200 import raymarching
+    bits = torch.full((2 * 128 ** 3 // 8,), 255, dtype=torch.uint8, device=dev)
+    g = torch.Generator().manual_seed(0)
+    sgn = (torch.randint(0, 2, (300, 3), generator=g) * 2 - 1).float()
+    o = (sgn * 2.5 + torch.randn(300, 3, generator=g) * 0.01).to(dev)
+    d = (-sgn / 3 ** 0.5).to(dev)
+    aabb = torch.tensor([-2., -2, -2, 2, 2, 2], device=dev)
+    nears, fars = raymarching.near_far_from_aabb(o, d, aabb, 0.2)
+    counter = torch.zeros(2, dtype=torch.int32, device=dev)
+    xyzs, dirs, deltas, rays = raymarching.march_rays_train(o, d, None, 2.0, bits, 2, 128, nears, fars, counter, -1, False, 128,
+                                                            True, 0., 64, False)
+    ec = np.zeros(2, np.int32)
+    ex, ed, el, er = oracle.march_rays_train(o.cpu().numpy(), d.cpu().numpy(), None, 2.0, bits.cpu().numpy(), 2, 128,
+                                             nears.cpu().numpy(), fars.cpu().numpy(), ec, -1, False, 128, True, 0., 64, False)
+    assert (er[:, 2] == 64).all() and np.array_equal(rays.cpu().numpy(), er)
+    assert np.array_equal(xyzs.cpu().numpy().view(np.uint32), ex.view(np.uint32))
+    # N*max_steps samples exactly: the last ray trips the reference's `offset + count >= M` drop rule (:517)
+    assert ec[0] == 300 * 64 and float(xyzs[-64 - 128:-128].abs().sum()) == 0.0
 
 
 def test_golden_fixture_on_gpu(cuda_lib, dev):
@@ -178,52 +198,69 @@ def test_composite_rays_train_fwd_bwd(cuda_lib, oracle, dev, C, sigma_scale):
     assert np.abs(gs - egs)[~bad_s].max() <= 1e-4 * scale + 2e-5
 
 
-def test_inference_loop_matches_oracle(cuda_lib, oracle, dev):
-    """renderer.py:237-293 loop: alive sets identical step by step (exact), accumulators within rel 1e-4."""
+@pytest.mark.parametrize('T_thresh', [0.0, 1e-2])
+def test_inference_loop_matches_oracle(cuda_lib, oracle, dev, T_thresh):
+    """renderer.py:237-293 loop.  T_thresh = 0: nothing depends on the GPU's ex2.approx, so the alive sets are identical
+    step by step (exact) and the accumulators agree to rel 1e-4.  T_thresh = 1e-2: a ray whose transmittance sits on the
+    threshold may die one iteration apart on the two exp implementations; the images must still agree to 2 * T_thresh."""
     from nerfstyle_b200 import raymarching
     N, C = 3000, 5
     o, d = _rays(N, 2, dev)
     bits, _ = _bitfield('analytic', dev)
     aabb = torch.tensor([-2., -2, -2, 2, 2, 2], device=dev)
     nears, fars = raymarching.near_far_from_aabb(o, d, aabb, 0.2)
+    n = lambda x: x.detach().cpu().numpy().copy()      # noqa: E731
+    o_n, d_n, bits_n, nears_n, fars_n = n(o), n(d), n(bits), n(nears), n(fars)
+
+    def field_fn(xyzs, dirs):
+        sig = xyzs.norm(dim=-1) * 3.0 + 0.5
+        rgb = torch.cat([dirs.abs(), xyzs[:, :2].abs()], dim=-1)
+        return sig, rgb
+
+    # GPU loop
     ws = torch.zeros(N, device=dev); depth = torch.zeros(N, device=dev); image = torch.zeros(N, C, device=dev)
     alive = torch.arange(N, dtype=torch.int32, device=dev)
     rays_t = nears.clone()[:, None]
-    n = lambda x: x.detach().cpu().numpy().copy()      # noqa: E731
-    o_n, d_n, bits_n, nears_n, fars_n = n(o), n(d), n(bits), n(nears), n(fars)
-    ews, edepth, eimage = np.zeros(N, np.float32), np.zeros(N, np.float32), np.zeros((N, C), np.float32)
-    ealive = np.arange(N, dtype=np.int32)
-    erays_t = nears_n.copy()[:, None]
-    step, it = 0, 0
-    while step < 1024:
+    gpu_alive_hist, step = [], 0
+    while step < 1024 and len(alive) > 0:
         n_alive = len(alive)
-        assert n_alive == len(ealive)
-        if n_alive <= 0:
-            break
         n_step = max(min(N // n_alive, 8), 1)
         xyzs, dirs, deltas = raymarching.march_rays(n_alive, n_step, alive, rays_t, o, d, None, 2.0, bits, 2, 128, nears, fars,
                                                     128, False, 0., 1024, False)
-        ex, ed, el = oracle.march_rays(n_alive, n_step, ealive, erays_t, o_n, d_n, None, 2.0, bits_n, 2, 128, nears_n, fars_n,
-                                       128, False, 0., 1024, False)
-        assert xyzs.shape == ex.shape
-        assert np.array_equal(n(xyzs).view(np.uint32), ex.view(np.uint32))
-        assert np.array_equal(n(deltas).view(np.uint32), el.view(np.uint32))
-        # synthetic field: density from position, colour from direction
-        sig = (xyzs.norm(dim=-1) * 3.0 + 0.5)
-        rgb = torch.cat([dirs.abs(), xyzs[:, :2].abs()], dim=-1)
-        raymarching.composite_rays(n_alive, n_step, alive, rays_t, sig, rgb, deltas, False, ws, depth, image, 1e-2)
-        oracle.composite_rays(n_alive, n_step, ealive, erays_t, n(sig), n(rgb), el, False, ews, edepth, eimage, 1e-2)
-        a_gpu = n(alive)
-        mism = (a_gpu >= 0) != (ealive >= 0)
-        assert mism.sum() == 0, 'alive set diverged at iteration %d' % it
+        assert xyzs.shape[0] % 128 == 0 and xyzs.shape[0] > n_alive * n_step - 1
+        sig, rgb = field_fn(xyzs, dirs)
+        raymarching.composite_rays(n_alive, n_step, alive, rays_t, sig, rgb, deltas, False, ws, depth, image, T_thresh)
         alive2, k = raymarching.compact_rays_alive(alive)
         alive = alive[alive >= 0]
         assert torch.equal(alive2, alive) and k == len(alive)
-        ealive = np.ascontiguousarray(ealive[ealive >= 0])
+        gpu_alive_hist.append(n(alive))
         step += n_step
-        it += 1
-    assert it > 10
-    np.testing.assert_allclose(n(ws), ews, rtol=1e-4, atol=2e-6)
-    np.testing.assert_allclose(n(image), eimage, rtol=1e-4, atol=2e-6)
-    np.testing.assert_allclose(n(depth), edepth, rtol=1e-4, atol=2e-5)
-    np.testing.assert_allclose(n(rays_t), erays_t, rtol=0, atol=0)
+    # oracle loop
+    ews, edepth, eimage = np.zeros(N, np.float32), np.zeros(N, np.float32), np.zeros((N, C), np.float32)
+    ealive = np.arange(N, dtype=np.int32)
+    erays_t = nears_n.copy()[:, None]
+    cpu_alive_hist, step = [], 0
+    while step < 1024 and len(ealive) > 0:
+        n_alive = len(ealive)
+        n_step = max(min(N // n_alive, 8), 1)
+        ex, ed, el = oracle.march_rays(n_alive, n_step, ealive, erays_t, o_n, d_n, None, 2.0, bits_n, 2, 128, nears_n, fars_n, 128,
+                                       False, 0., 1024, False)
+        sig, rgb = field_fn(torch.from_numpy(ex), torch.from_numpy(ed))
+        oracle.composite_rays(n_alive, n_step, ealive, erays_t, sig.numpy(), rgb.numpy(), el, False, ews, edepth, eimage, T_thresh)
+        ealive = np.ascontiguousarray(ealive[ealive >= 0])
+        cpu_alive_hist.append(ealive.copy())
+        step += n_step
+    assert len(gpu_alive_hist) > 10
+    if T_thresh == 0.0:
+        assert len(gpu_alive_hist) == len(cpu_alive_hist)
+        for a, b in zip(gpu_alive_hist, cpu_alive_hist):
+            assert np.array_equal(a, b)
+        np.testing.assert_allclose(n(ws), ews, rtol=1e-4, atol=2e-6)
+        np.testing.assert_allclose(n(image), eimage, rtol=1e-4, atol=2e-6)
+        np.testing.assert_allclose(n(depth), edepth, rtol=1e-4, atol=2e-5)
+        np.testing.assert_allclose(n(rays_t), erays_t, rtol=0, atol=0)
+    else:
+        close = np.isclose(n(image), eimage, rtol=1e-4, atol=2e-6).all(axis=1)
+        assert (~close).mean() < 0.01                      # a handful of threshold-straddling rays
+        assert np.abs(n(image) - eimage).max() <= 2 * T_thresh * max(1.0, float(np.abs(eimage).max()))
+        assert np.abs(n(ws) - ews).max() <= 2 * T_thresh
