@@ -87,6 +87,19 @@ class TruncExpFn(Function):
         return g * torch.exp(x.clamp(-15, 15))
 
 
+class HalfCast(Function):
+    """An fp16 tensor boundary: the value is rounded to fp16 in forward and so is its gradient in backward (autograd
+    hands an fp16 gradient to the producer of an fp16 tensor)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.half().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.half().float()
+
+
 # ------------------------------------------------------------------------------------------ MLP
 def mlp_layer_shapes(n_in, n_out, n_hidden, width=64):
     pad = lambda n: (n + 15) // 16 * 16  # noqa: E731
@@ -109,11 +122,14 @@ _ACTS = {
 }
 
 
-def mlp_forward(x, params, n_in, n_out, n_hidden, hidden_act='relu', out_act='none', half=True, width=64):
+def mlp_forward(x, params, n_in, n_out, n_hidden, hidden_act='relu', out_act='none', half=True, width=64, x_half=False):
     """Oracle MLP.  x [B, n_in] (any float dtype), params flat fp32 (tcnn layout).  Returns fp32 [B, n_out] holding
-    fp16-representable values when half=True (the kernel's output dtype is fp16)."""
+    fp16-representable values when half=True (the kernel's output dtype is fp16, hence so is the gradient it
+    receives).  x_half: the input tensor is fp16 (so the input gradient is rounded to fp16 too)."""
     Ws = mlp_split(params, n_in, n_out, n_hidden, width)
     h = x.float()
+    if x_half:
+        h = HalfCast.apply(h)
     in_pad = Ws[0].shape[1]
     if in_pad > n_in:
         h = torch.nn.functional.pad(h, (0, in_pad - n_in))
@@ -123,7 +139,7 @@ def mlp_forward(x, params, n_in, n_out, n_hidden, hidden_act='relu', out_act='no
         h = rnd(_ACTS[hidden_act](h @ rnd(W).t()))
     z = h @ rnd(Ws[-1]).t()
     y = _ACTS[out_act](z)[:, :n_out]
-    return rnd(y)
+    return HalfCast.apply(y) if half else y
 
 
 # ------------------------------------------------------------------------------------------ the field
@@ -168,7 +184,10 @@ class OracleField:
 
     def net(self, name, x):
         ni, no, nh, oact = self.nets[name]
-        return mlp_forward(x, self.params[name + '.params'], ni, no, nh, 'relu', oact, half=True)
+        # color2_net always consumes an fp16 tensor (color1's output); the others consume the encoder output, which is
+        # fp16 only under autocast
+        return mlp_forward(x, self.params[name + '.params'], ni, no, nh, 'relu', oact, half=True,
+                           x_half=(self.half or name == 'color2_net'))
 
     def forward(self, pts, dirs=None):
         pts01 = (pts - self.bbox_min) / self.bbox_size          # common.py:288

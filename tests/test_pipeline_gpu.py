@@ -36,7 +36,7 @@ def test_train_step_matches_oracle(cuda_lib, oracle, dev, amp):
     with torch.autocast('cuda', dtype=torch.float16, enabled=amp):
         image, depth, classes = r.render_train(o, d)
         loss = torch.mean((image - target.to(dev)) ** 2) + 0.001 * torch.nn.functional.cross_entropy(classes, tcls.to(dev))
-    scale = 1024.0      # the reference always trains under GradScaler; the fp16 MLP backward needs the headroom
+    scale = 65536.0     # GradScaler's initial scale; the reference always trains under GradScaler; the fp16 MLP backward needs the headroom
     (loss * scale).backward()
     out = field.render_train(of, o.cpu().numpy(), d.cpu().numpy(), bits.cpu().numpy(), 2, 128, 2.0)
     eloss = field.train_step_loss(out, target, tcls)
