@@ -35,20 +35,8 @@ class TrainStep:
         return mse + cls, mse
 
     def allreduce_grads(self):
-        if self.world_size <= 1:
-            return
-        # flatten per dtype into two buckets: tables (100.8 MB fp32) and MLP weights (61 KB)
-        big = [p.grad for p in self.params if p.grad is not None and p.numel() > (1 << 20)]
-        small = [p.grad for p in self.params if p.grad is not None and p.numel() <= (1 << 20)]
-        for g in big:
-            dist.all_reduce(g, op=dist.ReduceOp.SUM)
-        if small:
-            flat = torch.cat([g.reshape(-1) for g in small])
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-            o = 0
-            for g in small:
-                g.copy_(flat[o:o + g.numel()].view_as(g))
-                o += g.numel()
+        from .parallel import allreduce_grads
+        return allreduce_grads(self.params, self.world_size)
 
     def step(self, rays_o, rays_d, target_rgb, target_cls, n_global=None):
         """rays_* [n,3], target_rgb [n,3] f32, target_cls [n] int64 -- all on the device.  Returns the loss tensor
@@ -59,7 +47,7 @@ class TrainStep:
             image, depth, classes = self.renderer.render_train(rays_o, rays_d)
             loss, mse = self.loss_fn(image, classes, target_rgb, target_cls)
         self.optim.zero_grad(set_to_none=True)
-        back = loss * (n_local * self.world_size / n_global) / self.world_size if self.world_size > 1 else loss
+        back = loss * (n_local / n_global) if self.world_size > 1 else loss
         self.scaler.scale(back).backward()
         self.allreduce_grads()
         self.scaler.step(self.optim)

@@ -165,8 +165,9 @@ class OracleField:
         self.params = {}
         self.params['x_density_embedder.embeddings'] = ((torch.rand(n_rows, level_dim, generator=g) * 2 - 1) * table_std)
         self.params['x_color_embedder.embeddings'] = ((torch.rand(n_rows, level_dim, generator=g) * 2 - 1) * table_std)
-        self.nets = {'density_net': (32, 1, 1, 'none'), 'class_net': (32, n_classes, 1, 'none'),
-                     'color1_net': (32, 16, 1, 'none'), 'color2_net': (16, 3, 2, 'sigmoid')}
+        enc_dim = num_levels * level_dim
+        self.nets = {'density_net': (enc_dim, 1, 1, 'none'), 'class_net': (enc_dim, n_classes, 1, 'none'),
+                     'color1_net': (enc_dim, 16, 1, 'none'), 'color2_net': (16, 3, 2, 'sigmoid')}
         for name, (ni, no, nh, _) in self.nets.items():
             chunks = []
             for (o, i) in mlp_layer_shapes(ni, no, nh):

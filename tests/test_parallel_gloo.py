@@ -1,0 +1,89 @@
+"""Data-parallel host logic on CPU: world_size-2 gloo.  The sum over ranks of the shard gradients (loss weighted by
+n_local / n_global) equals the whole-batch gradient, computed with the CPU oracle pipeline; render tiles gather back in
+order.  (The CUDA ops need a GPU; what is tested here is the sharding / exchange code the GPU path uses.)"""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _scene():
+    import oracle
+    from nerfstyle_b200 import scenes
+    H = 32
+    grid = scenes.analytic_density_grid(2, H, 2.0)
+    bits = oracle.packbits(grid.numpy(), 0.5)
+    o, d = scenes.random_rays(49, 3)       # odd count: uneven shards
+    g = torch.Generator().manual_seed(1)
+    return H, bits, o, d, torch.rand(49, 3, generator=g), torch.randint(0, 8, (49,), generator=g)
+
+
+def _grads(o, d, tgt, cls, H, bits, weight):
+    from oracle import field
+    of = field.OracleField(bound=2.0, n_classes=8, half=False, seed=0, table_std=0.3, log2_hashmap_size=12, num_levels=8)
+    out = field.render_train(of, o.numpy(), d.numpy(), bits, 2, H, 2.0, max_steps=128)
+    loss = field.train_step_loss(out, tgt, cls) * weight
+    loss.backward()
+    return of, out
+
+
+def _worker(rank, world, port, ret):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from nerfstyle_b200 import parallel
+    H, bits, o, d, tgt, cls = _scene()
+    so, sd, st, sc = parallel.shard_rays(o, d, rank, world, tgt, cls)
+    of, out = _grads(so, sd, st, sc, H, bits, parallel.local_loss_weight(so.shape[0], o.shape[0]))
+
+    class P:            # allreduce_grads only touches .grad
+        def __init__(self, g):
+            self.grad = g
+    names = sorted(of.params)
+    params = [P(of.params[n].grad) for n in names]
+    nbytes = parallel.allreduce_grads(params, world, bucket_small_below=1 << 14)
+    img = parallel.gather_rows(out['rgb'].detach(), o.shape[0], rank, world)
+    if rank == 0:
+        ret['grads'] = {n: p.grad.clone() for n, p in zip(names, params)}
+        ret['img'] = img
+        ret['nbytes'] = nbytes
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_bounds():
+    from nerfstyle_b200.parallel import shard_bounds
+    for n in (0, 1, 7, 8192, 762048):
+        for w in (1, 2, 3, 8):
+            b = [shard_bounds(n, r, w) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_dp2_gradients_equal_whole_batch():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    H, bits, o, d, tgt, cls = _scene()
+    of, out = _grads(o, d, tgt, cls, H, bits, 1.0)
+    assert ret['nbytes'] > 0
+    for n in sorted(of.params):
+        a, b = ret['grads'][n].numpy(), of.params[n].grad.numpy()
+        assert np.abs(b).max() > 0, n
+        np.testing.assert_allclose(a, b, rtol=2e-4, atol=2e-6 * np.abs(b).max(), err_msg=n)
+    np.testing.assert_allclose(ret['img'].numpy(), out['rgb'].detach().numpy(), rtol=1e-6, atol=1e-7)
