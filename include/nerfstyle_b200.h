@@ -197,6 +197,22 @@ int nrf_nnfm_forward(const void* a_f16, const void* b_f16, uint32_t N1, uint32_t
                      float* min_dist, int32_t* argmin, void* scratch, void* stream);
 uint64_t nrf_nnfm_scratch_bytes(uint32_t N1, uint32_t N2);
 
+/* ------------------------------------------------------------------ fused optimizer (SURVEY 8f NEXT-3) */
+
+/* One pass per parameter tensor replacing GradScaler.unscale_/step + torch.optim.Adam(eps=1e-15) + LambdaLR +
+ * torch_ema (trainers/base.py:216-229,420-426) and producing the fp16 copy the next autocast forward needs.
+ * `state` is a device block of nrf_opt_state_bytes() bytes: {float scale; int found_inf; int growth_tracker;
+ * int good_steps; ...}.  Per step: nrf_grads_check on every gradient, nrf_adam_step on every parameter
+ * (skips itself when an inf/nan was found), nrf_scaler_update once.  No host synchronisation anywhere.
+ * lr = lr0 * 0.1^(good_steps / lr_decay_steps) (LambdaLR of trainers/base.py:222-226; 0 disables the decay);
+ * ema <- ema - ema_one_minus_decay * (ema - param) (torch_ema); ema / param_half may be NULL. */
+uint64_t nrf_opt_state_bytes(void);
+int nrf_grads_check(const float* grad, uint64_t n, void* state, void* stream);
+int nrf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, void* param_half,
+                  uint64_t n, const void* state, float lr0, float lr_decay_steps, float beta1, float beta2, float eps,
+                  float ema_one_minus_decay, void* stream);
+int nrf_scaler_update(void* state, float growth, float backoff, int growth_interval, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

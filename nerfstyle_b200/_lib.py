@@ -51,10 +51,15 @@ SIGNATURES = {
                                 _vp, _vp]),
     'nrf_nnfm_forward': (_i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
     'nrf_nnfm_scratch_bytes': (_u64, [_u32, _u32]),
+    'nrf_opt_state_bytes': (_u64, []),
+    'nrf_grads_check': (_i32, [_vp, _u64, _vp, _vp]),
+    'nrf_adam_step': (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _u64, _vp, _f32, _f32, _f32, _f32, _f32, _f32, _vp]),
+    'nrf_scaler_update': (_i32, [_vp, _f32, _f32, _i32, _vp]),
 }
 # tuning / extension entry points that are not part of the reference-replacing ABI
 EXTRA_SIGNATURES = {
     'nrf_grid_set_tuning': (None, [_i32, _i32, _i32]),
+    'nrf_march_set_mode': (None, [_i32]),
 }
 
 DTYPE_F32, DTYPE_F16 = 0, 1
@@ -65,11 +70,11 @@ _lib = None
 # kernels launched per C call (lower bound; used for the `gpu_launches` claim of bench.py)
 KERNELS_PER_CALL = {
     'nrf_near_far_from_aabb': 1, 'nrf_sph_from_ray': 1, 'nrf_morton3D': 1, 'nrf_morton3D_invert': 1, 'nrf_packbits': 1,
-    'nrf_march_rays_train_count': 3, 'nrf_march_rays_train_write': 1, 'nrf_march_rays_train': 4,
+    'nrf_march_rays_train_count': 4, 'nrf_march_rays_train_write': 1, 'nrf_march_rays_train': 4,
     'nrf_composite_rays_train_forward': 1, 'nrf_composite_rays_train_backward': 1, 'nrf_march_rays': 1,
     'nrf_composite_rays': 1, 'nrf_compact_alive': 3, 'nrf_grid_encode_forward': 1, 'nrf_grid_encode_backward': 1,
     'nrf_grid_initialize': 1, 'nrf_mlp_forward': 1, 'nrf_mlp_backward': 1, 'nrf_nnfm_forward': 3,
-    'nrf_adam_step': 1,
+    'nrf_adam_step': 1, 'nrf_grads_check': 1, 'nrf_scaler_update': 1,
 }
 
 

@@ -287,7 +287,7 @@ k_grid_fwd_generic(const float* __restrict__ inputs, const T* __restrict__ table
 
 static int g_fwd_lpt = 16;   // levels per thread of the fast path (tunable: nrf_grid_set_tuning)
 static int g_bwd_lpt = 16;
-static int g_bwd_agg = 24;   // aggregate when a warp has <= this many distinct cells (0 = never)
+static int g_bwd_agg = 1;    // warp aggregation of the scatter on (1) / off (0)
 NRF_EXPORT void nrf_grid_set_tuning(int fwd_lpt, int bwd_lpt, int bwd_agg) {
     if (fwd_lpt > 0) g_fwd_lpt = fwd_lpt;
     if (bwd_lpt > 0) g_bwd_lpt = bwd_lpt;
@@ -348,18 +348,53 @@ k_grid_bwd_d3c2(const T* __restrict__ grad, const float* __restrict__ inputs, co
                 TO* __restrict__ grad_table, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align_corners,
                 uint32_t style, bool point_major, int agg_max_groups) {
     typedef typename Vec2<T>::type V2;
+    constexpr int WPL = (int)sizeof(V2) / 4;           // 32-bit words per level of one point's gradient
+    constexpr int ROW = LPT * WPL + 1;                 // padded smem row (conflict-free column reads)
     __shared__ LevelP lp[LPT];
+    __shared__ uint32_t sg[GRID_BLOCK * ROW];          // this block's gradients, [point][level] (16.3 / 32.3 KB at LPT=16)
     const uint32_t l0 = blockIdx.y * LPT;
     if (threadIdx.x < LPT && l0 + threadIdx.x < L) level_setup(lp[threadIdx.x], offsets, l0 + threadIdx.x, 3, S, H, gridtype, align_corners, style);
-    __syncthreads();
-    const uint32_t b = blockIdx.x * GRID_BLOCK + threadIdx.x;
+    const uint32_t b0 = blockIdx.x * GRID_BLOCK;
+    const uint32_t b = b0 + threadIdx.x;
     const int lane = threadIdx.x & 31;
+    // ---- stage the block's gradient rows through shared memory with fully coalesced 16-byte loads
+    const uint32_t nlev = min((uint32_t)LPT, L - l0);
+    if (point_major) {
+        constexpr int WORDS = LPT * WPL;               // words per point in this level group
+        const bool vec = (WORDS % 4 == 0) && ((L * WPL) % 4 == 0) && ((l0 * WPL) % 4 == 0) && (nlev == (uint32_t)LPT) &&
+                         (((uintptr_t)grad & 15) == 0);
+        if (vec) {
+            constexpr int CPP = WORDS / 4;             // 16-byte chunks per point
+            for (int c = threadIdx.x; c < GRID_BLOCK * CPP; c += GRID_BLOCK) {
+                const int pt = c / CPP, ch = c - pt * CPP;
+                if (b0 + pt < B) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(grad) + ((size_t)(b0 + pt) * L + l0) * WPL) + ch);
+                    uint32_t* d = sg + pt * ROW + ch * 4;
+                    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+                }
+            }
+        } else {
+            for (int c = threadIdx.x; c < GRID_BLOCK * WORDS; c += GRID_BLOCK) {
+                const int pt = c / WORDS, wd = c - pt * WORDS;
+                if (b0 + pt < B && (uint32_t)(wd / WPL) < nlev)
+                    sg[pt * ROW + wd] = __ldg(reinterpret_cast<const uint32_t*>(grad) + ((size_t)(b0 + pt) * L + l0) * WPL + wd);
+            }
+        }
+    } else {
+        for (uint32_t j = 0; j < nlev; j++) {
+            if (b < B) {
+#pragma unroll
+                for (int w = 0; w < WPL; w++)
+                    sg[threadIdx.x * ROW + j * WPL + w] = __ldg(reinterpret_cast<const uint32_t*>(grad) + ((size_t)(l0 + j) * B + b) * WPL + w);
+            }
+        }
+    }
     float x = -1.0f, y = -1.0f, z = -1.0f;
     if (b < B) { x = __ldg(inputs + 3 * (size_t)b); y = __ldg(inputs + 3 * (size_t)b + 1); z = __ldg(inputs + 3 * (size_t)b + 2); }
     const bool active = !((x < 0 || x > 1) || (y < 0 || y > 1) || (z < 0 || z > 1));   // oob points contribute nothing (:268-273)
+    __syncthreads();
 #pragma unroll 1
-    for (int j = 0; j < LPT; j++) {
-        if (l0 + j >= L) break;            // uniform
+    for (uint32_t j = 0; j < nlev; j++) {
         const LevelP& p = lp[j];
         uint32_t cx = 0, cy = 0, cz = 0; float fx = 0, fy = 0, fz = 0;
         uint32_t rows[8]; float w[8];
@@ -370,28 +405,32 @@ k_grid_bwd_d3c2(const T* __restrict__ grad, const float* __restrict__ inputs, co
             locate1(z, p, align_corners, cz, fz);
             corner_rows_d3(p, cx, cy, cz, rows);
             corner_weights_d3(fx, fy, fz, w);
-            const V2 gvj = point_major ? __ldg(reinterpret_cast<const V2*>(grad) + (size_t)b * L + l0 + j)
-                                       : __ldg(reinterpret_cast<const V2*>(grad) + (size_t)(l0 + j) * B + b);
-            if constexpr (sizeof(T) == 4) { g0 = gvj.x; g1 = gvj.y; }
-            else { const float2 gg = __half22float2(gvj); g0 = gg.x; g1 = gg.y; }
+            if constexpr (sizeof(T) == 4) {
+                g0 = __uint_as_float(sg[threadIdx.x * ROW + j * 2]);
+                g1 = __uint_as_float(sg[threadIdx.x * ROW + j * 2 + 1]);
+            } else {
+                uint32_t u = sg[threadIdx.x * ROW + j];
+                const float2 gg = __half22float2(*reinterpret_cast<__half2*>(&u));
+                g0 = gg.x; g1 = gg.y;
+            }
         }
         TO* gl = grad_table + (size_t)p.offset * 2;
         bool done = false;
         if (agg_max_groups > 0) {
-            // lanes in the same cell share all 8 corner rows
+            // lanes in the same cell share all 8 corner rows: reduce each run of equal cells with shuffles and issue ONE
+            // vector atomic per corner per run.  The butterfly depth adapts to the longest run in the warp (coarse levels:
+            // 5 steps for 1-2 runs; fine levels: 0-2 steps).
             const unsigned long long key = active ? (((unsigned long long)cz << 42) | ((unsigned long long)cy << 21) | (unsigned long long)cx)
                                                   : (0xFFFFFFFF00000000ull | (unsigned)lane);
             const uint32_t mask = __match_any_sync(NRF_FULL_MASK, key);
             const int lo = __ffs(mask) - 1, hi = 31 - __clz(mask);
             const uint32_t span = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
-            const bool contiguous = (mask == span);
-            const int ngroups = __popc(__ballot_sync(NRF_FULL_MASK, lane == lo));
-            if (__all_sync(NRF_FULL_MASK, contiguous) && ngroups <= agg_max_groups) {
+            if (__all_sync(NRF_FULL_MASK, mask == span)) {
+                const int maxlen = (int)__reduce_max_sync(NRF_FULL_MASK, (unsigned)(hi - lo + 1));
                 float v0[8], v1[8];
 #pragma unroll
                 for (int k = 0; k < 8; k++) { v0[k] = active ? __fmul_rn(w[k], g0) : 0.0f; v1[k] = active ? __fmul_rn(w[k], g1) : 0.0f; }
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
+                for (int d = 1; d < maxlen; d <<= 1) {
                     const bool take = (lane + d <= hi);
 #pragma unroll
                     for (int k = 0; k < 8; k++) {

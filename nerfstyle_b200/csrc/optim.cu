@@ -1,0 +1,91 @@
+// Fused optimizer step for the hash tables and MLP weights (SURVEY.md 8f NEXT-3): GradScaler unscale + inf check,
+// Adam(eps=1e-15) with bias correction and the LambdaLR decay, torch_ema update and the fp16 table copy the next
+// forward needs -- ONE pass over each parameter instead of torch's unscale / Adam / EMA / .to(half) passes.
+// Semantics follow trainers/base.py:216-229,420-426 (torch.optim.Adam, GradScaler, LambdaLR, torch_ema).
+// Everything that GradScaler decides on the host (skip on inf, scale growth/back-off, "scheduler.step() only when
+// the scale did not shrink") is decided on the device from a small state block, so the step has no host sync.
+#include "common.cuh"
+
+struct OptState {        // lives in device memory, 8 x 4 bytes
+    float scale;         // current loss scale
+    int found_inf;       // set by k_grads_check for the current step
+    int growth_tracker;  // consecutive finite steps since the last scale change
+    int good_steps;      // optimizer steps actually taken (bias correction / LambdaLR epoch)
+    int pad[4];
+};
+
+__global__ void k_grads_check(const float* __restrict__ g, uint64_t n, OptState* st) {
+    bool bad = false;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float v = g[i];
+        bad |= !(fabsf(v) <= 3.402823466e38f);      // inf or nan
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) st->found_inf = 1;
+}
+
+__global__ void k_adam_ema(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                           float* __restrict__ ema, __half* __restrict__ p_half, uint64_t n, const OptState* __restrict__ st,
+                           float lr0, float lr_decay_steps, float beta1, float beta2, float eps, float ema_one_minus_decay) {
+    const bool skip = st->found_inf != 0;
+    const int t = st->good_steps + 1;
+    const float inv_scale = 1.0f / st->scale;
+    const float lr = (lr_decay_steps > 0.0f) ? lr0 * exp2f(-3.3219280948873623f * ((float)st->good_steps / lr_decay_steps)) : lr0;
+    const float bc1 = 1.0f - powf(beta1, (float)t);
+    const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)t));
+    const float step_size = lr / bc1;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        float pi = p[i];
+        if (!skip) {
+            const float gi = g[i] * inv_scale;
+            const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+            const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+            m[i] = mi;
+            v[i] = vi;
+            pi -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+            p[i] = pi;
+            if (p_half) p_half[i] = __float2half_rn(pi);
+        }
+        if (ema) { const float e = ema[i]; ema[i] = e - ema_one_minus_decay * (e - pi); }
+    }
+}
+
+// GradScaler.update(): back off on inf, grow after `growth_interval` finite steps; count the optimizer steps taken
+__global__ void k_scaler_update(OptState* st, float growth, float backoff, int growth_interval) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (st->found_inf) {
+        st->scale *= backoff;
+        st->growth_tracker = 0;
+    } else {
+        st->good_steps += 1;
+        if (++st->growth_tracker == growth_interval) { st->scale *= growth; st->growth_tracker = 0; }
+    }
+    st->found_inf = 0;
+}
+
+NRF_EXPORT uint64_t nrf_opt_state_bytes(void) { return sizeof(OptState); }
+
+NRF_EXPORT int nrf_grads_check(const float* grad, uint64_t n, void* state, void* stream) {
+    if (n == 0) return NRF_OK;
+    if (!grad || !state) return NRF_E_INVALID;
+    const uint32_t nb = (uint32_t)min((uint64_t)148 * 8, (n + 1023) / 1024);
+    k_grads_check<<<nb, 256, 0, (cudaStream_t)stream>>>(grad, n, (OptState*)state);
+    return nrf_check_launch();
+}
+
+NRF_EXPORT int nrf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, void* param_half,
+                             uint64_t n, const void* state, float lr0, float lr_decay_steps, float beta1, float beta2,
+                             float eps, float ema_one_minus_decay, void* stream) {
+    if (n == 0) return NRF_OK;
+    if (!param || !grad || !exp_avg || !exp_avg_sq || !state) return NRF_E_INVALID;
+    const uint32_t nb = (uint32_t)min((uint64_t)148 * 16, (n + 255) / 256);
+    k_adam_ema<<<nb, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, ema, (__half*)param_half, n,
+                                                    (const OptState*)state, lr0, lr_decay_steps, beta1, beta2, eps,
+                                                    ema_one_minus_decay);
+    return nrf_check_launch();
+}
+
+NRF_EXPORT int nrf_scaler_update(void* state, float growth, float backoff, int growth_interval, void* stream) {
+    if (!state) return NRF_E_INVALID;
+    k_scaler_update<<<1, 32, 0, (cudaStream_t)stream>>>((OptState*)state, growth, backoff, growth_interval);
+    return nrf_check_launch();
+}

@@ -247,12 +247,175 @@ __device__ __forceinline__ bool march_visit(const MarchCtx& c, const uint8_t* __
     return false;
 }
 
+// Occupancy test at t without advancing: x,y,z,dt = the sample; tt = exit time of the cell when it is empty.
+__device__ __forceinline__ bool march_eval(const MarchCtx& c, const uint8_t* __restrict__ grid, float t,
+                                           float& x, float& y, float& z, float& dt, float& tt) {
+    x = nrf_clamp(__fmaf_rn(c.dx, t, c.ox), c.nbound, c.bound);
+    y = nrf_clamp(__fmaf_rn(c.dy, t, c.oy), c.nbound, c.bound);
+    z = nrf_clamp(__fmaf_rn(c.dz, t, c.oz), c.nbound, c.bound);
+    dt = nrf_clamp(__fmul_rn(t, c.dt_gamma), c.dt_min, c.dt_max);
+    const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+    const int level = max(mip_exponent(mx, c.Cm1), mip_exponent(__fmul_rn(dt, c.Hf) * 0.5f, c.Cm1));
+    const float mip_bound = fminf(__uint_as_float((uint32_t)(127 + level) << 23), c.bound);
+    const float mip_rbound = __fdiv_rn(1.0f, mip_bound);
+    const int nx = (int)nrf_clamp(__fmul_rn(0.5f * __fmaf_rn(x, mip_rbound, 1.0f), c.Hf), 0.0f, c.Hm1);
+    const int ny = (int)nrf_clamp(__fmul_rn(0.5f * __fmaf_rn(y, mip_rbound, 1.0f), c.Hf), 0.0f, c.Hm1);
+    const int nz = (int)nrf_clamp(__fmul_rn(0.5f * __fmaf_rn(z, mip_rbound, 1.0f), c.Hf), 0.0f, c.Hm1);
+    const uint32_t index = (uint32_t)__fmaf_rn(c.H3, (float)level, (float)morton3D_dev((uint32_t)nx, (uint32_t)ny, (uint32_t)nz));
+    const bool occ = (__ldg(grid + (index >> 3)) >> (index & 7u)) & 1u;
+    const float tx = __fmul_rn(c.rdx, __fsub_rn(__fmul_rn(mip_bound, __fmaf_rn(__fmul_rn(c.rH, __fadd_rn(c.sx, __fadd_rn((float)nx, 0.5f))), 2.0f, -1.0f)), x));
+    const float ty = __fmul_rn(c.rdy, __fsub_rn(__fmul_rn(mip_bound, __fmaf_rn(__fmul_rn(c.rH, __fadd_rn(c.sy, __fadd_rn((float)ny, 0.5f))), 2.0f, -1.0f)), y));
+    const float tz = __fmul_rn(c.rdz, __fsub_rn(__fmul_rn(mip_bound, __fmaf_rn(__fmul_rn(c.rH, __fadd_rn(c.sz, __fadd_rn((float)nz, 0.5f))), 2.0f, -1.0f)), z));
+    tt = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
+    return occ;
+}
+
+__device__ __forceinline__ float march_next_t(const MarchCtx& c, float t) {
+    return __fadd_rn(t, nrf_clamp(__fmul_rn(t, c.dt_gamma), c.dt_min, c.dt_max));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-per-ray walker.  The candidate times t_0, t_1 = t_0 + dt(t_0), ... do not depend on the occupancy
+// (occupied: t += dt; empty: t += dt until t >= exit time), so a warp tests 32 consecutive candidates at
+// once: every lane runs the (cheap, strictly sequential) float recurrence and keeps its own t_i, tests its
+// cell with one byte load, and the data-dependent skipping ("after an empty cell jump to the first
+// candidate past its exit time") is resolved with warp ballots / or-reductions by pointer doubling over the
+// per-lane successor indices.  Visited-and-occupied lanes are compacted with a prefix popcount.  Bit-exact
+// with the sequential walk (same float ops in the same order for every value that is kept).
+// ------------------------------------------------------------------------------------------------
+#define MW_WARPS 4
+
+template <bool WRITE>
+__global__ void __launch_bounds__(MW_WARPS * 32)
+k_march_warp(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const uint8_t* __restrict__ grid,
+             float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, uint32_t rows,
+             const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ noises,
+             int32_t* __restrict__ rays, float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas) {
+    __shared__ float s_t[MW_WARPS][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t n = blockIdx.x * MW_WARPS + wib;
+    if (n >= N) return;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t limit = max_steps, point_index = 0;
+    if (WRITE) {
+        point_index = (uint32_t)rays[3 * (size_t)n + 1];
+        limit = (uint32_t)rays[3 * (size_t)n + 2];
+        if (limit == 0) return;
+        if (point_index + limit >= M) {      // dropped ray (raymarching.cu:517): its slots stay zero
+            for (uint32_t i = point_index + lane; i < min(point_index + limit, rows); i += 32) {
+                xyzs[3 * (size_t)i] = 0; xyzs[3 * (size_t)i + 1] = 0; xyzs[3 * (size_t)i + 2] = 0;
+                dirs[3 * (size_t)i] = 0; dirs[3 * (size_t)i + 1] = 0; dirs[3 * (size_t)i + 2] = 0;
+                reinterpret_cast<float4*>(deltas)[i] = make_float4(0, 0, 0, 0);
+            }
+            return;
+        }
+    }
+    MarchCtx c;
+    march_init(c, rays_o + 3 * (size_t)n, rays_d + 3 * (size_t)n, bound, dt_gamma, max_steps, C, H);
+    const float far = fars[n];
+    float cur_t = march_t0(c, nears[n], noises ? noises[n] : 0.0f);
+    float last_t = cur_t;
+    uint32_t count = 0;
+    while (cur_t < far && count < limit) {
+        // 32 consecutive candidates; lane i keeps t_i, tc ends as t_32
+        float tc = cur_t, my_t = cur_t;
+#pragma unroll
+        for (int i = 0; i < 32; i++) { if (lane == i) my_t = tc; tc = march_next_t(c, tc); }
+        const bool valid = my_t < far;
+        float x, y, z, dt, tt;
+        const bool occ = march_eval(c, grid, my_t, x, y, z, dt, tt);
+        s_t[wib][lane] = my_t;
+        __syncwarp();
+        int nxt = lane + 1;
+        if (!occ) {      // first j >= lane+1 whose t_j is not < tt (the do/while of raymarching.cu:497-499)
+            int lo_ = lane + 1, hi_ = 32;
+            while (lo_ < hi_) { const int mid = (lo_ + hi_) >> 1; if (!(s_t[wib][mid] < tt)) hi_ = mid; else lo_ = mid + 1; }
+            nxt = lo_;
+        }
+        __syncwarp();
+        // which lanes does the sequential walk visit?  pointer doubling from lane 0
+        bool marked = (lane == 0) && valid;
+        int jump = nxt;
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+            const uint32_t m = __reduce_or_sync(NRF_FULL_MASK, (marked && jump < 32) ? (1u << jump) : 0u);
+            if (((m >> lane) & 1u) && valid) marked = true;
+            const int j2 = __shfl_sync(NRF_FULL_MASK, jump, min(jump, 31));
+            jump = (jump < 32) ? j2 : 32;
+        }
+        const uint32_t V = __ballot_sync(NRF_FULL_MASK, marked);
+        uint32_t E = __ballot_sync(NRF_FULL_MASK, marked && occ);
+        const uint32_t remaining = limit - count;
+        bool finished = false;
+        if ((uint32_t)__popc(E) >= remaining) {          // the step cap falls inside this chunk: keep the first `remaining`
+            const uint32_t pos = __fns(E, 0, (int)remaining + 1);
+            if (pos != 0xffffffffu) E &= (1u << pos) - 1u;
+            finished = true;
+        }
+        if (WRITE) {
+            const float t_after = __fadd_rn(my_t, dt);
+            const uint32_t before = E & lt_mask;
+            const int src = before ? (31 - __clz(before)) : lane;
+            const float prev_after = __shfl_sync(NRF_FULL_MASK, t_after, src);
+            if ((E >> lane) & 1u) {
+                const size_t o = (size_t)point_index + count + __popc(before);
+                xyzs[3 * o] = x; xyzs[3 * o + 1] = y; xyzs[3 * o + 2] = z;
+                dirs[3 * o] = c.dx; dirs[3 * o + 1] = c.dy; dirs[3 * o + 2] = c.dz;
+                reinterpret_cast<float4*>(deltas)[o] = make_float4(dt, __fsub_rn(t_after, before ? prev_after : last_t), 0.0f, 0.0f);
+            }
+            if (E) last_t = __shfl_sync(NRF_FULL_MASK, t_after, 31 - __clz(E));
+        }
+        count += __popc(E);
+        if (finished) break;
+        const int Lv = 31 - __clz(V);                       // V != 0: lane 0 is valid inside the loop
+        const int nxtL = __shfl_sync(NRF_FULL_MASK, nxt, Lv);
+        const bool occL = __shfl_sync(NRF_FULL_MASK, (int)occ, Lv) != 0;
+        const float ttL = __shfl_sync(NRF_FULL_MASK, tt, Lv);
+        if (nxtL < 32) break;                               // the successor exists in this chunk but is past `far`
+        cur_t = tc;
+        if (!occL) { while (cur_t < ttL) cur_t = march_next_t(c, cur_t); }
+    }
+    if (!WRITE && lane == 0) {
+        rays[3 * (size_t)n + 0] = (int32_t)n;
+        rays[3 * (size_t)n + 1] = 0;
+        rays[3 * (size_t)n + 2] = (int32_t)count;
+    }
+}
+
+// block-local exclusive scan of the per-ray counts (rays[:,2]) into rays[:,1]; block totals to block_sums
+#define SCAN_BLOCK 1024
+__global__ void __launch_bounds__(SCAN_BLOCK)
+k_scan_counts_local(int32_t* __restrict__ rays, uint32_t N, uint32_t* __restrict__ block_sums) {
+    __shared__ uint32_t warp_tot[SCAN_BLOCK / 32];
+    const uint32_t n = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t v = n < N ? (uint32_t)rays[3 * (size_t)n + 2] : 0u;
+    const uint32_t incl = warp_scan_add_u32(v, lane);
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = warp_tot[lane];
+        const uint32_t wi = warp_scan_add_u32(w, lane);
+        warp_tot[lane] = wi - w;
+        if (lane == 31) block_sums[blockIdx.x] = wi;
+    }
+    __syncthreads();
+    if (n < N) rays[3 * (size_t)n + 1] = (int32_t)(warp_tot[warp] + incl - v);
+}
+__global__ void k_add_block_offsets_g(int32_t* __restrict__ rays, const uint32_t* __restrict__ block_offs, uint32_t N, uint32_t per_block) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    rays[3 * (size_t)n + 1] += (int32_t)block_offs[n / per_block];
+}
+
 // ------------------------------------------------------------------------------------------------
 // march_rays_train: count -> scan -> write   (reference: one kernel, two passes + 2 atomics per ray,
 // raymarching.cu:411-589; here offsets are the exclusive scan in ray order = one valid schedule of the
 // reference's racing atomicAdd, and deterministic).
 // ------------------------------------------------------------------------------------------------
 #define MARCH_BLOCK 64
+static int g_march_warp_per_ray = 1;   // 1: warp-per-ray walker (default), 0: thread-per-ray (also used for NDC)
+NRF_EXPORT void nrf_march_set_mode(int warp_per_ray) { g_march_warp_per_ray = warp_per_ray ? 1 : 0; }
 
 // rays[n] = (n, block-local exclusive offset, count); block_sums[blockIdx.x] = sum of counts
 __global__ void __launch_bounds__(MARCH_BLOCK)
@@ -338,8 +501,17 @@ NRF_EXPORT int nrf_march_rays_train_count(const float* rays_o, const float* rays
     if (!rays_o || !rays_d || !grid || !nears || !fars || !rays || !scratch) return NRF_E_INVALID;
     if (C < 1 || C > 24 || H < 1 || H > 1024) return NRF_E_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
-    const uint32_t nb = ceil_div_u32(N, MARCH_BLOCK);
     uint32_t* block_sums = (uint32_t*)scratch;
+    if (g_march_warp_per_ray) {
+        k_march_warp<false><<<ceil_div_u32(N, MW_WARPS), MW_WARPS * 32, 0, s>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H,
+                                                                              0, 0, nears, fars, noises, rays, nullptr, nullptr, nullptr);
+        const uint32_t nb = ceil_div_u32(N, SCAN_BLOCK);
+        k_scan_counts_local<<<nb, SCAN_BLOCK, 0, s>>>(rays, N, block_sums);
+        k_scan_block_sums<<<1, 1024, 0, s>>>(block_sums, nb, counter, N);
+        k_add_block_offsets_g<<<ceil_div_u32(N, 256), 256, 0, s>>>(rays, block_sums, N, SCAN_BLOCK);
+        return nrf_check_launch();
+    }
+    const uint32_t nb = ceil_div_u32(N, MARCH_BLOCK);
     k_march_count<<<nb, MARCH_BLOCK, 0, s>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, block_sums);
     k_scan_block_sums<<<1, 1024, 0, s>>>(block_sums, nb, counter, N);
     k_add_block_offsets<<<ceil_div_u32(N, 256), 256, 0, s>>>(rays, block_sums, N);
@@ -420,6 +592,12 @@ NRF_EXPORT int nrf_march_rays_train_write(const float* rays_o, const float* rays
     if ((((uintptr_t)deltas) & 15) != 0) return NRF_E_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
     if (zero_from < rows) k_zero_rows<<<ceil_div_u32(rows - zero_from, 256), 256, 0, s>>>(xyzs, dirs, deltas, zero_from, rows);
+    if (g_march_warp_per_ray && !is_ndc) {
+        k_march_warp<true><<<ceil_div_u32(N, MW_WARPS), MW_WARPS * 32, 0, s>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M,
+                                                                             rows, nears, fars, noises, const_cast<int32_t*>(rays), xyzs, dirs,
+                                                                             deltas);
+        return nrf_check_launch();
+    }
     k_march_write<<<ceil_div_u32(N, MARCH_BLOCK), MARCH_BLOCK, 0, s>>>(rays_o, rays_d, z_hats, grid, bound, dt_gamma, max_steps,
                                                                   is_ndc != 0, N, C, H, M, rows, nears, fars, noises, rays,
                                                                   xyzs, dirs, deltas);

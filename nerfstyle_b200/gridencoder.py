@@ -37,7 +37,8 @@ class _grid_encode(Function):
         H = int(base_resolution)
         # grid.py:42-43: half-precision tables under autocast when C is even
         if torch.is_autocast_enabled('cuda') and C % 2 == 0:
-            embeddings = embeddings.to(torch.half)
+            shadow = getattr(embeddings, '_nrf_half_copy', None)      # kept current by nerfstyle_b200.optim.FusedAdamEMA
+            embeddings = shadow if shadow is not None else embeddings.to(torch.half)
         embeddings = embeddings.contiguous()
         offsets = offsets.contiguous()
         dt = L.dtype_code(embeddings.dtype)

@@ -13,11 +13,23 @@ import torch.nn.functional as F
 
 class TrainStep:
     def __init__(self, renderer, lr=0.01, mlp_lr=None, lr_decay=30000, ema_decay=0.95, class_lambda=0.001, enable_amp=True,
-                 fused_adam=True, world_size=1):
+                 fused_adam=True, world_size=1, fused_optimizer=True):
         self.renderer = renderer
         self.model = renderer.model
         params = list(self.model.parameters())
         self.params = params
+        self.enable_amp = enable_amp
+        self.class_lambda = class_lambda
+        self.world_size = world_size
+        self.iter_ctr = 0
+        self.fused = None
+        if fused_optimizer:
+            # GradScaler + Adam + LambdaLR + EMA + fp16 table copies in one device pass per tensor, no host sync
+            from .optim import FusedAdamEMA
+            self.fused = FusedAdamEMA(params, lr=lr, eps=1e-15, lr_decay_steps=lr_decay, ema_decay=ema_decay,
+                                      enable_amp=enable_amp)
+            self.ema = self.fused.ema
+            return
         self.optim = torch.optim.Adam([{'params': params}], lr=lr, betas=(0.9, 0.999), eps=1e-15, fused=fused_adam)
         self.scheduler = torch.optim.lr_scheduler.LambdaLR(
             self.optim, (lambda it: 0.1 ** (it / lr_decay)) if lr_decay > 0 else (lambda it: 1.0))
@@ -46,8 +58,15 @@ class TrainStep:
         with torch.autocast('cuda', dtype=torch.float16, enabled=self.enable_amp):
             image, depth, classes = self.renderer.render_train(rays_o, rays_d)
             loss, mse = self.loss_fn(image, classes, target_rgb, target_cls)
-        self.optim.zero_grad(set_to_none=True)
         back = loss * (n_local / n_global) if self.world_size > 1 else loss
+        if self.fused is not None:
+            self.fused.zero_grad()
+            self.fused.scale_loss(back).backward()
+            self.allreduce_grads()
+            self.fused.step()
+            self.iter_ctr += 1
+            return loss.detach()
+        self.optim.zero_grad(set_to_none=True)
         self.scaler.scale(back).backward()
         self.allreduce_grads()
         self.scaler.step(self.optim)

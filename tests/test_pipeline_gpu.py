@@ -101,3 +101,46 @@ def test_update_state_and_steps(cuda_lib, dev):
         losses.append(float(loss))
     assert r.local_step == 6 and r.mean_density > 0 and int(r.density_bitfield.count_nonzero()) > 0
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+def test_fused_optimizer_matches_torch(cuda_lib, dev):
+    """FusedAdamEMA == GradScaler + torch.optim.Adam(eps=1e-15) + LambdaLR + torch_ema-style EMA, incl. inf-skip."""
+    from nerfstyle_b200.optim import FusedAdamEMA
+    torch.manual_seed(0)
+    shapes = [(2_000_003,), (3072,), (50, 7)]
+    pa = [torch.nn.Parameter(torch.randn(s, device=dev) * 0.1) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    fused = FusedAdamEMA(pa, lr=0.01, lr_decay_steps=50, ema_decay=0.95, init_scale=1024.0, growth_interval=3,
+                         half_copy_min_numel=1 << 20)
+    opt = torch.optim.Adam(pb, lr=0.01, betas=(0.9, 0.999), eps=1e-15)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda it: 0.1 ** (it / 50))
+    scaler = torch.amp.GradScaler('cuda', init_scale=1024.0, growth_interval=3)
+    ema = [p.detach().clone() for p in pb]
+    n_upd = 0
+    for it in range(9):
+        grads = [torch.randn_like(p) for p in pa]
+        if it == 4:
+            grads[1][5] = float('inf')                  # this step must be skipped and the scale halved
+        s_a = float(fused.scale.item())
+        for p, q, g in zip(pa, pb, grads):
+            p.grad = g * s_a
+            q.grad = g * scaler.get_scale()
+        assert s_a == scaler.get_scale()
+        fused.step()
+        scaler.step(opt)
+        old = scaler.get_scale()
+        scaler.update()
+        if old <= scaler.get_scale():
+            sched.step()
+        n_upd += 1
+        decay = min(0.95, (1 + n_upd) / (10 + n_upd))
+        with torch.no_grad():
+            for e, q in zip(ema, pb):
+                e.sub_((1 - decay) * (e - q))
+    for p, q in zip(pa, pb):
+        torch.testing.assert_close(p, q, rtol=2e-5, atol=2e-6)
+    for e, f in zip(ema, fused.ema):
+        torch.testing.assert_close(f, e, rtol=2e-5, atol=2e-6)
+    assert int(fused.good_steps.item()) == 8
+    torch.testing.assert_close(pa[0]._nrf_half_copy.float(), pa[0].detach().half().float())
+    assert not hasattr(pa[1], '_nrf_half_copy')

@@ -78,6 +78,38 @@ def test_march_rays_train_bit_exact(cuda_lib, oracle, dev, kind, max_steps, dt_g
         assert np.array_equal(a.cpu().numpy().view(np.uint32), b.view(np.uint32))
 
 
+@pytest.mark.parametrize('mode', [0, 1])
+def test_march_modes_and_ndc(cuda_lib, oracle, dev, mode):
+    """thread-per-ray (0) and warp-per-ray (1) walkers give identical bits; NDC deltas (thread walker) match the oracle."""
+    from nerfstyle_b200 import raymarching
+    cuda_lib.nrf_march_set_mode(mode)
+    try:
+        N = 3001
+        o, d = _rays(N, 5, dev)
+        o = o * 3.0                                    # some origins outside the box
+        bits, _ = _bitfield('bernoulli', dev)
+        aabb = torch.tensor([-2., -2, -2, 2, 2, 2], device=dev)
+        nears, fars = raymarching.near_far_from_aabb(o, d, aabb, 0.05)
+        for is_ndc in (False, True):
+            z_hats = (torch.rand(N, generator=torch.Generator().manual_seed(1)) + 0.5).to(dev) if is_ndc else None
+            counter = torch.zeros(2, dtype=torch.int32, device=dev)
+            xyzs, dirs, deltas, rays = raymarching.march_rays_train(o, d, z_hats, 2.0, bits, 2, 128, nears, fars, counter, -1,
+                                                                    False, 128, True, 1.0 / 256, 1024, is_ndc)
+            ec = np.zeros(2, np.int32)
+            ex, ed, el, er = oracle.march_rays_train(o.cpu().numpy(), d.cpu().numpy(),
+                                                     z_hats.cpu().numpy() if is_ndc else None, 2.0, bits.cpu().numpy(), 2, 128,
+                                                     nears.cpu().numpy(), fars.cpu().numpy(), ec, -1, False, 128, True, 1.0 / 256,
+                                                     1024, is_ndc)
+            assert np.array_equal(rays.cpu().numpy(), er) and np.array_equal(counter.cpu().numpy(), ec)
+            assert np.array_equal(xyzs.cpu().numpy().view(np.uint32), ex.view(np.uint32))
+            a, b = deltas.cpu().numpy(), el
+            assert np.array_equal(a[:, :2].view(np.uint32), b[:, :2].view(np.uint32))
+            if is_ndc:
+                np.testing.assert_allclose(a[:, 2:], b[:, 2:], rtol=1e-5, atol=1e-6)
+    finally:
+        cuda_lib.nrf_march_set_mode(1)
+
+
 def test_march_rays_train_edge_cases(cuda_lib, oracle, dev):
     from nerfstyle_b200 import raymarching
     bits, _ = _bitfield('analytic', dev)

@@ -48,6 +48,9 @@ def bench_march():
     def f():
         c = torch.zeros(2, dtype=torch.int32, device=dev)
         return raymarching.march_rays_train(o, d, None, 2.0, bits, 2, 128, nears, fars, c, -1, False, 128, True, 0., 1024, False)
+    for mode in (0, 1):
+        lib.nrf_march_set_mode(mode)
+        print('march mode %d (0 thread-per-ray, 1 warp-per-ray): %.3f ms' % (mode, timeit(f)))
     xyzs, dirs, deltas, rays = f()
     print('march_rays_train (count+sync+write): %.3f ms for %d rays, %d samples' % (timeit(f), o.shape[0], xyzs.shape[0]))
     N = o.shape[0]
@@ -88,12 +91,12 @@ def bench_grid(xyzs):
             print('grid fwd  half=%d lpt=%2d: %.3f ms  %.0f GB/s algorithmic' % (half, lpt, t, B * fb / t / 1e6))
         lib.nrf_grid_set_tuning(16, 0, -1)
         for lpt in (16, 4, 1):
-            for agg in (0, 8, 16, 24, 32):
+            for agg in (0, 1):
                 lib.nrf_grid_set_tuning(0, lpt, agg)
                 t = timeit(lambda: lib.nrf_grid_encode_backward(grad.data_ptr(), pts.data_ptr(), None, enc.offsets.data_ptr(),
                                                                 ge.data_ptr(), B, 3, 2, 16, S, 16, 0, None, None, 0, 1, 0, dt, 0, 1, st))
                 print('grid bwd  half=%d lpt=%2d agg=%2d: %.3f ms  %.0f GB/s algorithmic' % (half, lpt, agg, t, B * bb / t / 1e6))
-        lib.nrf_grid_set_tuning(0, 16, 24)
+        lib.nrf_grid_set_tuning(0, 16, 1)
 
 
 def bench_mlp(B):
