@@ -37,7 +37,7 @@ WORKLOAD = 'llff_room_train_step_8192rays_504x378'
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=32)
+    ap.add_argument('--steps', type=int, default=64)
     ap.add_argument('--warmup', type=int, default=8)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--rays', type=int, default=N_RAYS)
@@ -50,22 +50,62 @@ def parse():
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
-        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    """SM clock / throttle reasons sampled DURING the timed region.  In-process NVML (pynvml) on a background thread:
+    spawning `nvidia-smi` every 200 ms costs ~1 s of CPU per call and takes driver locks that stall kernel launches
+    (it made the timed region itself 10-100 % slower); nvidia-smi is only the fallback when pynvml is missing."""
+    NAMES = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap'}
 
-    def __init__(self, index=0, period=0.2):
-        self.index, self.period, self.rows, self._stop, self._t = index, period, [], threading.Event(), None
+    def __init__(self, index=0, period=0.1):
+        self.index, self.period, self.sm, self.reasons, self.power = index, period, [], set(), []
+        self.max_mhz, self._stop, self._t, self.h, self.nv = None, threading.Event(), None, None, None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            pr = torch.cuda.get_device_properties(index)
+            bus = '%08x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nv = pynvml
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _sample(self):
+        if self.nv is not None:
+            nv = self.nv
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            try:
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            try:
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in self.NAMES.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        else:
+            q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+                'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+            out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
+                                 capture_output=True, text=True, timeout=5).stdout.strip().split(',')
+            self.sm.append(float(out[0]))
+            self.max_mhz = float(out[1])
+            for n, v in zip(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], out[2:6]):
+                if v.strip().lower().startswith('active'):
+                    self.reasons.add(n)
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(',')])
+                self._sample()
             except Exception:
                 pass
-            self._stop.wait(self.period)
+            self._stop.wait(self.period if self.nv is not None else 1.0)
 
     def start(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -75,16 +115,10 @@ class ClockSampler:
         self._stop.set()
         if self._t:
             self._t.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
-        reasons = set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
-            for n, v in zip(names, r[3:7]):
-                if v.lower().startswith('active'):
-                    reasons.add(n)
-        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(self.rows)}
+        return {'sm_mhz': statistics.median(self.sm) if self.sm else None, 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(self.reasons), 'samples': len(self.sm),
+                'power_w_max': round(max(self.power), 1) if self.power else None,
+                'source': 'pynvml' if self.nv is not None else 'nvidia-smi'}
 
 
 # ------------------------------------------------------------------------------------------------ workload

@@ -117,6 +117,7 @@ def test_fused_optimizer_matches_torch(cuda_lib, dev):
     scaler = torch.amp.GradScaler('cuda', init_scale=1024.0, growth_interval=3)
     ema = [p.detach().clone() for p in pb]
     n_upd = 0
+    scaler.scale(torch.ones(1, device=dev))        # lazily initialises the scaler's device state
     for it in range(9):
         grads = [torch.randn_like(p) for p in pa]
         if it == 4:

@@ -137,3 +137,32 @@ if __name__ == '__main__':
         bench_mlp(xyzs.shape[0])
     if what in ('composite', 'all'):
         bench_composite(deltas, rays)
+
+
+def bench_update_state():
+    import bench as B
+    for fused in (True, False):
+        from nerfstyle_b200.trainer import TrainStep
+        ts = B.build_trainer(dev, True, 1)
+        if not fused:
+            ts = TrainStep(ts.renderer, enable_amp=True, world_size=1, fused_optimizer=False)
+        host, devb = B.make_batches(40, 8192, 0, 1, dev)
+        r = ts.renderer
+        with torch.autocast('cuda', dtype=torch.float16):
+            t_up = timeit(lambda: r.update_state(), iters=5, warm=2)
+        r.update_occ = True
+        for s in range(4):
+            ts.step(*B.unpack(devb[s]))
+        torch.cuda.synchronize()
+        # steps without occupancy updates
+        r.update_occ = False
+        t0 = time.perf_counter()
+        for s in range(4, 36):
+            ts.step(*B.unpack(devb[s]))
+        torch.cuda.synchronize()
+        t_step = (time.perf_counter() - t0) / 32 * 1e3
+        print('fused_optimizer=%s: update_state %.2f ms per call; train step without update %.3f ms' % (fused, t_up, t_step))
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'update':
+    bench_update_state()
