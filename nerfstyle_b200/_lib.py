@@ -60,6 +60,8 @@ SIGNATURES = {
 EXTRA_SIGNATURES = {
     'nrf_grid_set_tuning': (None, [_i32, _i32, _i32]),
     'nrf_march_set_mode': (None, [_i32]),
+    'nrf_mlp_set_mode': (None, [_i32]),
+    'nrf_mlp_set_tuning': (None, [_i32, _i32]),
 }
 
 DTYPE_F32, DTYPE_F16 = 0, 1

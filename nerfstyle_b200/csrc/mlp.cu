@@ -427,6 +427,18 @@ k_mlp_bwd(const XT* __restrict__ x, const __half* __restrict__ params, const DYT
 // ------------------------------------------------------------------------------------------------
 // host dispatch
 // ------------------------------------------------------------------------------------------------
+// mlp_tc.cu: the tcgen05 / TMEM implementation (default); the mma.sync kernels above stay as the selectable
+// second implementation (nrf_mlp_set_mode(1)) that the parity tests run side by side.
+int nrf_mlp_tc_forward(const void* x, int x_dtype, const void* params_f16, uint32_t B, uint32_t n_in, uint32_t n_out, uint32_t n_hidden,
+                       int hidden_act, int out_act, void* y, int y_dtype, cudaStream_t s);
+int nrf_mlp_tc_backward(const void* x, int x_dtype, const void* params_f16, const void* dy, int dy_dtype, uint32_t B, uint32_t n_in,
+                        uint32_t n_out, uint32_t n_hidden, int hidden_act, int out_act, float loss_scale, void* dx, float* dparams,
+                        cudaStream_t s);
+void nrf_mlp_tc_set_ctas(int fwd_per_sm, int bwd_per_sm);
+static int g_mlp_mode = 0;      // 0 = tcgen05 (mlp_tc.cu), 1 = mma.sync (this file)
+NRF_EXPORT void nrf_mlp_set_mode(int mode) { g_mlp_mode = mode; }
+NRF_EXPORT void nrf_mlp_set_tuning(int fwd_ctas_per_sm, int bwd_ctas_per_sm) { nrf_mlp_tc_set_ctas(fwd_ctas_per_sm, bwd_ctas_per_sm); }
+
 static int g_sm_count = 0;
 static int sm_count() {
     if (g_sm_count == 0) {
@@ -468,6 +480,9 @@ NRF_EXPORT int nrf_mlp_forward(const void* x, int x_dtype, const void* params_f1
     if (width != MLP_WIDTH || n_in == 0 || n_in > 64 || n_out == 0 || n_out > 16 || n_hidden < 1 || n_hidden > 2) return NRF_E_UNSUPPORTED;
     if (hidden_act != NRF_ACT_RELU && hidden_act != NRF_ACT_NONE) return NRF_E_UNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
+    if (x_dtype != NRF_DTYPE_F16 && x_dtype != NRF_DTYPE_F32) return NRF_E_UNSUPPORTED;
+    if (y_dtype != NRF_DTYPE_F16 && y_dtype != NRF_DTYPE_F32) return NRF_E_UNSUPPORTED;
+    if (g_mlp_mode == 0) return nrf_mlp_tc_forward(x, x_dtype, params_f16, B, n_in, n_out, n_hidden, hidden_act, out_act, y, y_dtype, s);
     const int kt = (int)((n_in + 15) / 16), nt = n_out <= 8 ? 1 : 2;
 #define FWD_CASE(K, H, N) if (kt == K && (int)n_hidden == H && nt == N) return launch_fwd_dt<K, H, N>(x, x_dtype, params_f16, B, n_in, n_out, hidden_act, out_act, y, y_dtype, s)
     FWD_CASE(1, 1, 1); FWD_CASE(1, 1, 2); FWD_CASE(1, 2, 1); FWD_CASE(1, 2, 2);
@@ -514,6 +529,11 @@ NRF_EXPORT int nrf_mlp_backward(const void* x, int x_dtype, const void* params_f
     if (hidden_act != NRF_ACT_RELU && hidden_act != NRF_ACT_NONE) return NRF_E_UNSUPPORTED;
     if (!(loss_scale > 0.0f)) return NRF_E_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
+    if (g_mlp_mode == 0) {
+        if (dx && dx_dtype != x_dtype) return NRF_E_UNSUPPORTED;
+        if ((x_dtype != NRF_DTYPE_F16 && x_dtype != NRF_DTYPE_F32) || (dy_dtype != NRF_DTYPE_F16 && dy_dtype != NRF_DTYPE_F32)) return NRF_E_UNSUPPORTED;
+        return nrf_mlp_tc_backward(x, x_dtype, params_f16, dy, dy_dtype, B, n_in, n_out, n_hidden, hidden_act, out_act, loss_scale, dx, dparams, s);
+    }
     const int kt = (int)((n_in + 15) / 16), nt = n_out <= 8 ? 1 : 2;
 #define BWD_CASE(K, H, N) if (kt == K && (int)n_hidden == H && nt == N) return launch_bwd_dt<K, H, N>(x, x_dtype, params_f16, dy, dy_dtype, B, n_in, n_out, hidden_act, out_act, loss_scale, dx, dx_dtype, dparams, s)
     BWD_CASE(1, 1, 1); BWD_CASE(1, 1, 2); BWD_CASE(1, 2, 1); BWD_CASE(1, 2, 2);

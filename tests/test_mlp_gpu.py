@@ -7,6 +7,18 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+
+
+@pytest.fixture(params=['tcgen05', 'mma_sync'], autouse=True)
+def mlp_impl(request, cuda_lib):
+    """Every test runs on both implementations behind nrf_mlp_forward / nrf_mlp_backward: the tcgen05 + TMEM kernels
+    (mlp_tc.cu, the default) and the mma.sync kernels (mlp.cu)."""
+    from nerfstyle_b200 import _lib
+    _lib.lib().nrf_mlp_set_mode(0 if request.param == 'tcgen05' else 1)
+    yield request.param
+    _lib.lib().nrf_mlp_set_mode(0)
+
+
 NETS = {'density': (32, 1, 1, 'None'), 'class': (32, 8, 1, 'None'), 'color1': (32, 16, 1, 'None'),
         'color2': (16, 3, 2, 'Sigmoid'), 'odd': (27, 5, 2, 'None'), 'wide_in': (64, 12, 1, 'Sigmoid')}
 
@@ -68,3 +80,25 @@ def test_grad_accumulation_and_no_input_grad(cuda_lib, dev):
     net(x).sum().backward()
     torch.testing.assert_close(net.params.grad, 2 * g1, rtol=1e-5, atol=1e-6)
     assert net(torch.zeros(0, ni, device=dev).half()).shape == (0, no)
+
+
+def test_large_batch_many_tiles_per_cta(cuda_lib, dev):
+    """> 148 * ctas_per_sm tiles: every persistent CTA loops (weight gradients accumulate in TMEM across tiles)."""
+    from oracle import field
+    net, (ni, no, nh, act) = _net('color2', dev)
+    B = 128 * 1500 + 77
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, ni, generator=g).to(dev).half().requires_grad_(True)
+    dy = (torch.randn(B, no, generator=g) * 0.05).to(dev).half()
+    y = net(x)
+    y.backward(dy)
+    xc = x.detach().float().cpu().requires_grad_(True)
+    pc = net.params.detach().cpu().requires_grad_(True)
+    ey = field.mlp_forward(xc, pc, ni, no, nh, 'relu', act, half=True, x_half=True)
+    ey.backward(dy.float().cpu())
+    a, b = y.detach().float().cpu().numpy(), ey.detach().numpy()
+    assert np.abs(a - b).max() <= 4 * 2.0 ** -10
+    gx, egx = x.grad.float().cpu().numpy(), xc.grad.numpy()
+    gp, egp = net.params.grad.cpu().numpy(), pc.grad.numpy()
+    assert np.abs(gx - egx).max() <= 2e-2 * np.abs(egx).max()     # max over 3 M elements of fp16-rounded dH
+    assert np.abs(gp - egp).max() <= 1e-2 * np.abs(egp).max()
