@@ -62,6 +62,7 @@ EXTRA_SIGNATURES = {
     'nrf_march_set_mode': (None, [_i32]),
     'nrf_mlp_set_mode': (None, [_i32]),
     'nrf_mlp_set_tuning': (None, [_i32, _i32]),
+    'nrf_mlp_set_profile': (None, [_vp]),
 }
 
 DTYPE_F32, DTYPE_F16 = 0, 1

@@ -3,21 +3,25 @@
 // Same contract as mlp.cu (call sites /root/reference/networks/style_nerf.py:44-98):
 // y = act_out(W_n relu(... relu(W_1 x))), f16 operands, f32 accumulation, hidden activations rounded to f16.
 //
-// Design (one CTA = 128 threads = one 128-row tile at a time, persistent over tiles, several CTAs per SM):
-//   * thread t owns row t of the tile == TMEM lane t.  Every operand tile lives in shared memory in the "chunked"
-//     SWIZZLE_NONE layout of tc05.cuh, which is a legal K-major AND MN-major UMMA operand, so the backward forms
-//     dH = dZ W, dX = dH W1 and dW = dH^T X from the very same tiles with no transposed copy;
-//   * one elected thread issues tcgen05.mma (M=128 for activations, M=64 for weight gradients), the f32 accumulator
-//     sits in TMEM; after the commit lands on an mbarrier every thread pulls its row with tcgen05.ld, applies
-//     relu / act', rounds to f16 and writes the next layer's operand back to shared memory (generic -> async proxy fence);
-//   * the weight gradients are accumulated IN TMEM across all tiles of the persistent CTA (f32), read out once at the
-//     end and flushed with one float atomic per weight per CTA.  The dW MMAs of a tile run on the tensor pipe while
-//     the threads are already busy with the next epilogue (separate mbarrier, waited on at the top of the next tile);
-//   * the backward recomputes the hidden activations from x (nothing but x is saved by the forward); relu masks are
-//     kept as 64-bit register masks per row.
+// Design (one CTA = one 128-row tile at a time, persistent over tiles, several CTAs resident per SM):
+//   * warps 0-3 are the row owners: thread t owns row t of the tile == TMEM lane t.  Warp 4 is the MMA issuer (one
+//     elected lane).  Row owners and issuer hand tiles back and forth through mbarriers only (`ready`: 128 arrivals,
+//     operands written / accumulator drained;  `done`: tcgen05.commit of the MMAs a row owner waits for).
+//   * every operand tile lives in shared memory in the "chunked" SWIZZLE_NONE layout of tc05.cuh, which is a legal
+//     K-major AND MN-major UMMA operand: the backward forms dH = dZ W, dX = dH W1 and dW = dH^T X from the very same
+//     tiles with no transposed copy;
+//   * accumulators sit in TMEM; a row owner pulls its row with tcgen05.ld, rounds to f16, applies relu / relu' on packed
+//     halfs (HMNMX2 / HSET2+LOP3) and writes the next layer's operand back to shared memory;
+//   * measured on B200 every tcgen05.mma costs >= 45 cycles whatever its shape below N=64 (tools/tc_probe.cu), so the
+//     kernel minimises the NUMBER of MMAs: the weight gradients of a tile are ONE stacked product
+//     [dH1 | Hlast]^T [X | dZ]  (M=128, N=in+16, K=128 rows: 8 MMAs) whose diagonal blocks are dW1 and dWo^T; it is
+//     accumulated in TMEM across all tiles of the persistent CTA and flushed once with float atomics.  It runs on the
+//     tensor pipe while the row owners are already in the next epilogue (own mbarrier `wdone`);
+//   * the backward recomputes the hidden activations from x (nothing but x is saved by the forward); for a linear
+//     output layer dZ = loss_scale * dy needs no recomputation of Z, which removes one MMA round trip;
+//   * the rows of tile i+1 (x, dy) are fetched from HBM into registers while tile i is processed.
 // The tensor pipe is nearly idle by design (a 64-wide MLP is ~20 FLOP/B): what the tcgen05 path buys is that the
-// accumulators, transposes and weight-gradient reductions leave the register file / LSU, so the kernel runs at the
-// rate rows stream through HBM.
+// accumulators, transposes and weight-gradient reductions leave the register file / LSU.
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -26,12 +30,13 @@ namespace {
 constexpr uint32_t CH = 2048;    // chunk stride of 128-row activation tiles
 constexpr uint32_t CHW = 1024;   // chunk stride of 64-row weight tiles (W1, Wh)
 constexpr uint32_t CHO = 256;    // chunk stride of the 16-row output weight tile
-constexpr int TC_THREADS = 128;
+constexpr int TC_ROWS = 128;     // row-owner threads (warps 0-3)
+constexpr int TC_THREADS = 160;  // + the issuer warp
 
 __device__ __forceinline__ float tact_fwd(float z, int act) {
     switch (act) {
         case NRF_ACT_RELU: return fmaxf(z, 0.0f);
-        case NRF_ACT_SIGMOID: return 1.0f / (1.0f + __expf(-z));
+        case NRF_ACT_SIGMOID: return __frcp_rn(1.0f + __expf(-z));
         case NRF_ACT_EXP: return __expf(z);
         default: return z;
     }
@@ -39,7 +44,7 @@ __device__ __forceinline__ float tact_fwd(float z, int act) {
 __device__ __forceinline__ float tact_bwd(float z, int act) {
     switch (act) {
         case NRF_ACT_RELU: return z > 0.0f ? 1.0f : 0.0f;
-        case NRF_ACT_SIGMOID: { const float y = 1.0f / (1.0f + __expf(-z)); return y * (1.0f - y); }
+        case NRF_ACT_SIGMOID: { const float y = __frcp_rn(1.0f + __expf(-z)); return y * (1.0f - y); }
         case NRF_ACT_EXP: return __expf(z);
         default: return 1.0f;
     }
@@ -48,8 +53,11 @@ __device__ __forceinline__ uint32_t tpack(float lo, float hi) {
     __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ uint32_t h2bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ __half2 bits2h(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
 
-// columns [8c, 8c+8) of row `row` of a row-major [B, n] matrix (f16 or f32) as 8 packed halfs; zero outside
+// columns [8c, 8c+8) of row `row` of a row-major [B, n] matrix (f16 or f32) as 8 packed halfs; zero outside.
+// On the vectorised f16 path the result is the raw load (no dependent instruction: usable as a prefetch).
 __device__ __forceinline__ uint4 load_chunk(const void* __restrict__ base, int dt, size_t row, uint32_t c, uint32_t n, bool row_ok,
                                             bool vec_ok) {
     uint4 r = make_uint4(0u, 0u, 0u, 0u);
@@ -95,9 +103,51 @@ __device__ __forceinline__ void store_chunk(void* __restrict__ base, int dt, siz
     for (int j = 0; j < 8; j++) if (8 * c + j < n) p[j] = v[j];
 }
 
-__device__ __forceinline__ bool vec_ok_for(const void* base, int dt, uint32_t n) {
+__device__ __forceinline__ bool vec_ok_for(const void* base, uint32_t n) {
     if (!base) return false;
     return (n % 8 == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+}
+
+// this row's output gradient (<= 16 values), RAW (one register per element, or two uint4 on the vector path): no
+// instruction depends on the loaded data until dy_convert(), so the load can stay in flight for a whole tile
+__device__ __forceinline__ void dy_load_raw(const void* __restrict__ dy, int dy_dt, size_t row, uint32_t n_out, bool row_ok, bool vec_ok,
+                                            uint32_t (&raw)[16]) {
+#pragma unroll
+    for (int j = 0; j < 16; j++) raw[j] = 0u;
+    if (!row_ok) return;
+    if (dy_dt == NRF_DTYPE_F16) {
+        const __half* p = reinterpret_cast<const __half*>(dy) + row * n_out;
+        if (vec_ok) {                                  // n_out in {8, 16}
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+            raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w;
+            if (n_out > 8) { const uint4 b = __ldg(reinterpret_cast<const uint4*>(p) + 1); raw[4] = b.x; raw[5] = b.y; raw[6] = b.z; raw[7] = b.w; }
+            return;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j++) if ((uint32_t)j < n_out) raw[j] = (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p) + j);
+        return;
+    }
+    const float* p = reinterpret_cast<const float*>(dy) + row * n_out;
+#pragma unroll
+    for (int j = 0; j < 16; j++) if ((uint32_t)j < n_out) raw[j] = __float_as_uint(__ldg(p + j));
+}
+// raw -> loss_scale * dy as 8 packed f16x2
+__device__ __forceinline__ void dy_convert(const uint32_t (&raw)[16], int dy_dt, bool vec_ok, float loss_scale, uint32_t (&out)[8]) {
+    if (dy_dt == NRF_DTYPE_F16 && vec_ok) {
+        const __half2 ls = __float2half2_rn(loss_scale);
+#pragma unroll
+        for (int q = 0; q < 8; q++) out[q] = h2bits(__hmul2(bits2h(raw[q]), ls));
+        return;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        float a, b;
+        if (dy_dt == NRF_DTYPE_F16) {
+            a = __half2float(__ushort_as_half((unsigned short)raw[2 * q]));
+            b = __half2float(__ushort_as_half((unsigned short)raw[2 * q + 1]));
+        } else { a = __uint_as_float(raw[2 * q]); b = __uint_as_float(raw[2 * q + 1]); }
+        out[q] = tpack(a * loss_scale, b * loss_scale);
+    }
 }
 
 // stage a row-major f16 [rows, cols] weight matrix into the chunked layout (chunk stride ch), 16 bytes per step
@@ -109,12 +159,11 @@ __device__ __forceinline__ void stage_weight(uint8_t* dst, uint32_t ch, const __
     }
 }
 
-// hidden-layer epilogue: 64 f32 accumulator columns of this thread's row -> act -> f16 chunks in `dst` (+ sign mask)
-// MASKED = false: forward relu (or identity) and the mask of positive pre-activations is returned
-// MASKED = true : values are zeroed where `mask` is clear (back-propagation through relu)
-template <bool MASKED>
-__device__ __forceinline__ unsigned long long hidden_epilogue(uint32_t tacc_lane, uint8_t* dst_row, bool relu, unsigned long long mask) {
-    unsigned long long out_mask = 0ull;
+// forward hidden-layer epilogue: 64 f32 accumulator columns of this thread's row -> f16 -> relu -> chunks of `dst_row`.
+// relu is applied AFTER the rounding on packed halfs (rounding is monotonic and sign-preserving: same result, half the
+// instructions: one cvt.rn.f16x2.f32 + one HMNMX2 per pair of columns).
+__device__ __forceinline__ void hidden_fwd_epilogue(uint32_t tacc_lane, uint8_t* dst_row, bool relu) {
+    const __half2 zero = __float2half2_rn(0.0f);
 #pragma unroll
     for (int half = 0; half < 2; half++) {
         uint32_t v[32];
@@ -122,32 +171,57 @@ __device__ __forceinline__ unsigned long long hidden_epilogue(uint32_t tacc_lane
         tc05::tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            float f[8];
+            uint32_t p[4];
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                float a = __uint_as_float(v[8 * c + j]);
-                const int bit = 32 * half + 8 * c + j;
-                if (MASKED) {
-                    if (relu && !((mask >> bit) & 1ull)) a = 0.0f;
-                } else {
-                    if (a > 0.0f) out_mask |= (1ull << bit);
-                    if (relu) a = fmaxf(a, 0.0f);
-                }
-                f[j] = a;
+            for (int q = 0; q < 4; q++) {
+                __half2 h = __floats2half2_rn(__uint_as_float(v[8 * c + 2 * q]), __uint_as_float(v[8 * c + 2 * q + 1]));
+                if (relu) h = __hmax2(h, zero);
+                p[q] = h2bits(h);
             }
-            *reinterpret_cast<uint4*>(dst_row + (4 * half + c) * CH) =
-                make_uint4(tpack(f[0], f[1]), tpack(f[2], f[3]), tpack(f[4], f[5]), tpack(f[6], f[7]));
+            *reinterpret_cast<uint4*>(dst_row + (4 * half + c) * CH) = make_uint4(p[0], p[1], p[2], p[3]);
         }
     }
-    return out_mask;
 }
 
-// publish this thread's shared-memory / TMEM accesses to the MMA-issuing thread, then block barrier
+// backward hidden-layer epilogue: dH = round_f16(acc) masked by relu'(h), where h is this row of the recomputed
+// activation tile in shared memory (h > 0 <=> pre-activation > 0): one cvt + one HSET2 + one LOP3 per pair of columns.
+__device__ __forceinline__ void hidden_bwd_epilogue(uint32_t tacc_lane, const uint8_t* h_row, uint8_t* dst_row, bool relu) {
+    const __half2 zero = __float2half2_rn(0.0f);
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        uint32_t v[32];
+        tc05::tmem_ld32(tacc_lane + 32 * half, v);
+        tc05::tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const uint4 hv = *reinterpret_cast<const uint4*>(h_row + (4 * half + c) * CH);
+            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+            uint32_t p[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                p[q] = h2bits(__floats2half2_rn(__uint_as_float(v[8 * c + 2 * q]), __uint_as_float(v[8 * c + 2 * q + 1])));
+                if (relu) p[q] &= __hgt2_mask(bits2h(hw[q]), zero);
+            }
+            *reinterpret_cast<uint4*>(dst_row + (4 * half + c) * CH) = make_uint4(p[0], p[1], p[2], p[3]);
+        }
+    }
+}
+
+// row owner -> issuer: my operand writes (generic proxy) and my TMEM reads are done
+__device__ __forceinline__ void publish(uint64_t* ready) {
+    tc05::fence_async_smem();
+    tc05::fence_before_sync();
+    tc05::mbar_arrive(ready);
+}
+// block-wide variant used in the prologue / teardown
 __device__ __forceinline__ void publish_and_sync() {
     tc05::fence_async_smem();
     tc05::fence_before_sync();
     __syncthreads();
 }
+
+// advance the start-address field of a shared-memory descriptor by `bytes` (no carry out of the 14-bit field: smem < 256 KB)
+__device__ __forceinline__ uint64_t dadv(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
 
 struct TcSmem { uint32_t W1, Wh, Wo, X, H1, H2, dZ, dH1, dH2, total; };
 
@@ -163,6 +237,8 @@ __host__ __device__ constexpr TcSmem fwd_smem() {
     s.total = o;
     return s;
 }
+// The backward keeps tiles that are multiplied as ONE stacked operand adjacent (chunk stride CH continues across them):
+//   NH=1:  [X | dZ]  and  [dH1 | H1]          NH=2:  [X | H1]  and  [dH1 | dH2]
 template <int IN_KT, int NH>
 __host__ __device__ constexpr TcSmem bwd_smem() {
     TcSmem s{};
@@ -170,12 +246,20 @@ __host__ __device__ constexpr TcSmem bwd_smem() {
     s.W1 = o; o += IN_KT * 2 * CHW;
     s.Wh = o; o += (NH - 1) * 8 * CHW;
     s.Wo = o; o += 8 * CHO;
-    s.X = o;  o += IN_KT * 2 * CH;
-    s.H1 = o; o += 8 * CH;
-    s.H2 = o; o += (NH - 1) * 8 * CH;
-    s.dZ = o; o += 2 * CH;
-    s.dH1 = o; o += 8 * CH;
-    s.dH2 = o; o += (NH - 1) * 8 * CH;
+    if (NH == 1) {
+        s.X = o;   o += IN_KT * 2 * CH;
+        s.dZ = o;  o += 2 * CH;
+        s.dH1 = o; o += 8 * CH;
+        s.H1 = o;  o += 8 * CH;
+        s.H2 = o; s.dH2 = o;
+    } else {
+        s.X = o;   o += IN_KT * 2 * CH;
+        s.H1 = o;  o += 8 * CH;
+        s.dZ = o;  o += 2 * CH;
+        s.dH1 = o; o += 8 * CH;
+        s.dH2 = o; o += 8 * CH;
+        s.H2 = o;  o += 8 * CH;
+    }
     s.total = o;
     return s;
 }
@@ -189,79 +273,98 @@ k_mlp_fwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ pa
     constexpr TcSmem L = fwd_smem<IN_KT, NH>();
     constexpr uint32_t TCOLS = 64;
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t bar_ready, bar_done;
     __shared__ uint32_t tmem_slot;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     stage_weight(smem + L.W1, CHW, params, 64, IN_PAD);
     if constexpr (NH == 2) stage_weight(smem + L.Wh, CHW, params + 64 * IN_PAD, 64, 64);
     stage_weight(smem + L.Wo, CHO, params + 64 * IN_PAD + (NH - 1) * 64 * 64, 16, 64);
     if (warp == 0) { tc05::tmem_alloc(&tmem_slot, TCOLS); tc05::tmem_relinquish(); }
-    if (tid == 0) { tc05::mbar_init(&bar, 1); tc05::fence_mbar_init(); }
+    if (tid == 0) { tc05::mbar_init(&bar_ready, TC_ROWS); tc05::mbar_init(&bar_done, 1); tc05::fence_mbar_init(); }
     publish_and_sync();
     tc05::fence_after_sync();
     const uint32_t tacc = tmem_slot;
-    const uint32_t tacc_lane = tacc + ((uint32_t)(warp * 32) << 16);
-    const uint32_t sW1 = tc05::smem_u32(smem + L.W1), sWh = tc05::smem_u32(smem + L.Wh), sWo = tc05::smem_u32(smem + L.Wo);
-    const uint32_t sX = tc05::smem_u32(smem + L.X), sH = tc05::smem_u32(smem + L.H1);
-    constexpr uint32_t ID_H = tc05::idesc_f16(128, 64, false, false);
-    constexpr uint32_t ID_O = tc05::idesc_f16(128, 16, false, false);
-    const bool relu = hidden_act == NRF_ACT_RELU;
-    const bool x_vec = vec_ok_for(x, x_dt, n_in) && (x_dt == NRF_DTYPE_F16 || (reinterpret_cast<uintptr_t>(x) & 15) == 0);
-    const bool y_vec = vec_ok_for(y, y_dt, n_out);
     const uint32_t ntiles = (B + 127) / 128;
-    uint32_t phase = 0;
-    uint8_t* xrow = smem + L.X + tid * 16;
-    uint8_t* hrow = smem + L.H1 + tid * 16;
 
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const size_t row = (size_t)tile * 128 + tid;
-        const bool row_ok = row < B;
+    if (warp == 4) {
+        // ================================================================ MMA issuer (one lane)
+        if (lane == 0) {
+            const uint64_t dX = tc05::desc_kmajor(tc05::smem_u32(smem + L.X), CH), dH = tc05::desc_kmajor(tc05::smem_u32(smem + L.H1), CH);
+            const uint64_t dW1 = tc05::desc_kmajor(tc05::smem_u32(smem + L.W1), CHW), dWh = tc05::desc_kmajor(tc05::smem_u32(smem + L.Wh), CHW);
+            const uint64_t dWo = tc05::desc_kmajor(tc05::smem_u32(smem + L.Wo), CHO);
+            constexpr uint32_t ID_H = tc05::idesc_f16(128, 64, false, false);
+            constexpr uint32_t ID_O = tc05::idesc_f16(128, 16, false, false);
+            uint32_t ph = 0;
+            for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                tc05::mbar_wait(&bar_ready, ph); ph ^= 1; tc05::fence_after_sync();
 #pragma unroll
-        for (int c = 0; c < IN_PAD / 8; c++) *reinterpret_cast<uint4*>(xrow + c * CH) = load_chunk(x, x_dt, row, c, n_in, row_ok, x_vec);
-        publish_and_sync();
-        if (tid == 0) {
-            tc05::fence_after_sync();
+                for (int k = 0; k < IN_KT; k++) tc05::mma_f16(tacc, dadv(dX, k * 2 * CH), dadv(dW1, k * 2 * CHW), ID_H, k > 0);
+                tc05::mma_commit(&bar_done);
+                if constexpr (NH == 2) {
+                    tc05::mbar_wait(&bar_ready, ph); ph ^= 1; tc05::fence_after_sync();
 #pragma unroll
-            for (int k = 0; k < IN_KT; k++)
-                tc05::mma_f16(tacc, tc05::desc_kmajor(sX + k * 2 * CH, CH), tc05::desc_kmajor(sW1 + k * 2 * CHW, CHW), ID_H, k > 0);
-            tc05::mma_commit(&bar);
-        }
-        tc05::mbar_wait(&bar, phase); phase ^= 1;
-        tc05::fence_after_sync();
-#pragma unroll
-        for (int l = 0; l < NH; l++) {
-            hidden_epilogue<false>(tacc_lane, hrow, relu, 0ull);
-            publish_and_sync();
-            if (tid == 0) {
-                tc05::fence_after_sync();
-                if (l < NH - 1) {
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        tc05::mma_f16(tacc, tc05::desc_kmajor(sH + k * 2 * CH, CH), tc05::desc_kmajor(sWh + k * 2 * CHW, CHW), ID_H, k > 0);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        tc05::mma_f16(tacc, tc05::desc_kmajor(sH + k * 2 * CH, CH), tc05::desc_kmajor(sWo + k * 2 * CHO, CHO), ID_O, k > 0);
+                    for (int k = 0; k < 4; k++) tc05::mma_f16(tacc, dadv(dH, k * 2 * CH), dadv(dWh, k * 2 * CHW), ID_H, k > 0);
+                    tc05::mma_commit(&bar_done);
                 }
-                tc05::mma_commit(&bar);
-            }
-            tc05::mbar_wait(&bar, phase); phase ^= 1;
-            tc05::fence_after_sync();
-        }
-        uint32_t z[16];
-        tc05::tmem_ld16(tacc_lane, z);
-        tc05::tmem_ld_wait();
-        if (row_ok) {
+                tc05::mbar_wait(&bar_ready, ph); ph ^= 1; tc05::fence_after_sync();
 #pragma unroll
-            for (int c = 0; c < 2; c++) {
-                float f[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) f[j] = tact_fwd(__uint_as_float(z[8 * c + j]), out_act);
-                store_chunk(y, y_dt, row, c, n_out, f, y_vec);
+                for (int k = 0; k < 4; k++) tc05::mma_f16(tacc, dadv(dH, k * 2 * CH), dadv(dWo, k * 2 * CHO), ID_O, k > 0);
+                tc05::mma_commit(&bar_done);
             }
         }
-        // the next tile's publish_and_sync orders these TMEM reads before the next MMA overwrites the accumulator
+        __syncwarp();
+    } else {
+        // ================================================================ row owners
+        const uint32_t tacc_lane = tacc + ((uint32_t)(warp * 32) << 16);
+        const bool relu = hidden_act == NRF_ACT_RELU;
+        const bool x_vec = vec_ok_for(x, n_in);
+        const bool y_vec = vec_ok_for(y, n_out);
+        uint32_t phase = 0;
+        uint8_t* xrow = smem + L.X + tid * 16;
+        uint8_t* hrow = smem + L.H1 + tid * 16;
+        uint4 xr[IN_PAD / 8];
+        {
+            const size_t row0 = (size_t)blockIdx.x * 128 + tid;
+#pragma unroll
+            for (int c = 0; c < IN_PAD / 8; c++) xr[c] = load_chunk(x, x_dt, row0, c, n_in, row0 < B, x_vec);
+        }
+        for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const size_t row = (size_t)tile * 128 + tid;
+            const bool row_ok = row < B;
+#pragma unroll
+            for (int c = 0; c < IN_PAD / 8; c++) *reinterpret_cast<uint4*>(xrow + c * CH) = xr[c];
+            publish(&bar_ready);
+            {   // prefetch the next tile's rows (in flight until the top of the next iteration)
+                const uint32_t nt = tile + gridDim.x;
+                const size_t nrow = (size_t)nt * 128 + tid;
+                const bool nok = nt < ntiles && nrow < B;
+#pragma unroll
+                for (int c = 0; c < IN_PAD / 8; c++) xr[c] = load_chunk(x, x_dt, nrow, c, n_in, nok, x_vec);
+            }
+#pragma unroll
+            for (int l = 0; l < NH; l++) {
+                tc05::mbar_wait(&bar_done, phase); phase ^= 1; tc05::fence_after_sync();
+                hidden_fwd_epilogue(tacc_lane, hrow, relu);
+                publish(&bar_ready);
+            }
+            tc05::mbar_wait(&bar_done, phase); phase ^= 1; tc05::fence_after_sync();
+            uint32_t z[16];
+            tc05::tmem_ld16(tacc_lane, z);
+            tc05::tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    if (8u * c < n_out) {
+                        float f[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) f[j] = tact_fwd(__uint_as_float(z[8 * c + j]), out_act);
+                        store_chunk(y, y_dt, row, c, n_out, f, y_vec);
+                    }
+                }
+            }
+            // the next tile's publish() orders these TMEM reads before the issuer overwrites the accumulator
+        }
     }
     publish_and_sync();
     if (warp == 0) tc05::tmem_dealloc(tacc, TCOLS);
@@ -270,7 +373,8 @@ k_mlp_fwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ pa
 // ------------------------------------------------------------------------------------------------ backward
 template <int IN_KT, int NH>
 __host__ __device__ constexpr uint32_t bwd_tmem_cols() {
-    const uint32_t need = 64 + IN_KT * 16 + 16 + (NH - 1) * 64;
+    // accumulator (64) + stacked weight gradient (in + 16 | in + 64) + dWo^T (16, NH == 2 only)
+    const uint32_t need = 64 + IN_KT * 16 + (NH == 1 ? 16 : 64 + 16);
     return need <= 128 ? 128u : 256u;
 }
 
@@ -278,228 +382,276 @@ template <int IN_KT, int NH>
 __global__ void __launch_bounds__(TC_THREADS, (NH == 2 || IN_KT == 4) ? 2 : 4)
 k_mlp_bwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ params, const void* __restrict__ dy, int dy_dt,
              uint32_t B, uint32_t n_in, uint32_t n_out, int hidden_act, int out_act, float loss_scale, void* __restrict__ dx,
-             float* __restrict__ dparams) {
+             float* __restrict__ dparams, unsigned long long* __restrict__ prof) {
     constexpr int IN_PAD = IN_KT * 16;
     constexpr TcSmem L = bwd_smem<IN_KT, NH>();
     constexpr uint32_t TCOLS = bwd_tmem_cols<IN_KT, NH>();
-    constexpr uint32_t T_W1 = 64, T_WO = 64 + IN_PAD, T_WH = 64 + IN_PAD + 16;     // TMEM columns of the dW accumulators
+    constexpr uint32_t NS = IN_PAD + (NH == 1 ? 16 : 64);       // N of the stacked weight-gradient product
+    constexpr uint32_t T_S = 64, T_WO = 64 + NS;                 // TMEM columns: stacked dW, dWo^T (NH == 2)
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[2];      // [0]: epilogue-critical MMAs, [1]: weight-gradient MMAs of a tile
+    __shared__ __align__(8) uint64_t bar_ready, bar_done, bar_wdone;
     __shared__ uint32_t tmem_slot;
+    __shared__ long long s_prof[16];           // per-phase cycle counters of thread 0 (tools/mlp_bench.py), off by default
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     stage_weight(smem + L.W1, CHW, params, 64, IN_PAD);
     if constexpr (NH == 2) stage_weight(smem + L.Wh, CHW, params + 64 * IN_PAD, 64, 64);
     stage_weight(smem + L.Wo, CHO, params + 64 * IN_PAD + (NH - 1) * 64 * 64, 16, 64);
     if (warp == 0) { tc05::tmem_alloc(&tmem_slot, TCOLS); tc05::tmem_relinquish(); }
-    if (tid == 0) { tc05::mbar_init(&bars[0], 1); tc05::mbar_init(&bars[1], 1); tc05::fence_mbar_init(); }
+    if (tid == 0) {
+        tc05::mbar_init(&bar_ready, TC_ROWS); tc05::mbar_init(&bar_done, 1); tc05::mbar_init(&bar_wdone, 1);
+        tc05::fence_mbar_init();
+    }
     publish_and_sync();
     tc05::fence_after_sync();
     const uint32_t tacc = tmem_slot;
-    const uint32_t tacc_lane = tacc + ((uint32_t)(warp * 32) << 16);
-    const uint32_t sW1 = tc05::smem_u32(smem + L.W1), sWh = tc05::smem_u32(smem + L.Wh), sWo = tc05::smem_u32(smem + L.Wo);
-    const uint32_t sX = tc05::smem_u32(smem + L.X), sH1 = tc05::smem_u32(smem + L.H1), sH2 = tc05::smem_u32(smem + L.H2);
-    const uint32_t sdZ = tc05::smem_u32(smem + L.dZ), sdH1 = tc05::smem_u32(smem + L.dH1), sdH2 = tc05::smem_u32(smem + L.dH2);
-    const uint32_t sHlast = (NH == 2) ? sH2 : sH1, sdHlast = (NH == 2) ? sdH2 : sdH1;
-    constexpr uint32_t ID_H = tc05::idesc_f16(128, 64, false, false);        // X W1^T, H1 Wh^T      (A K-major, B K-major)
-    constexpr uint32_t ID_O = tc05::idesc_f16(128, 16, false, false);        // Hlast Wo^T
-    constexpr uint32_t ID_DH = tc05::idesc_f16(128, 64, false, true);        // dZ Wo, dH2 Wh        (B MN-major)
-    constexpr uint32_t ID_DX = tc05::idesc_f16(128, IN_PAD, false, true);    // dH1 W1
-    constexpr uint32_t ID_GW1 = tc05::idesc_f16(64, IN_PAD, true, true);     // dH1^T X
-    constexpr uint32_t ID_GWH = tc05::idesc_f16(64, 64, true, true);         // dH2^T H1
-    constexpr uint32_t ID_GWO = tc05::idesc_f16(64, 16, true, true);         // Hlast^T dZ  (= dWo^T)
-    const bool relu = hidden_act == NRF_ACT_RELU;
-    const bool x_vec = vec_ok_for(x, x_dt, n_in) && (x_dt == NRF_DTYPE_F16 || (reinterpret_cast<uintptr_t>(x) & 15) == 0);
-    const bool dx_vec = vec_ok_for(dx, x_dt, n_in);
-    const float inv_scale = 1.0f / loss_scale;
     const uint32_t ntiles = (B + 127) / 128;
     const bool want_dw = dparams != nullptr;
-    uint32_t phase = 0, phase_w = 0;
-    bool first = true;
+    const bool linear_out = out_act == NRF_ACT_NONE;       // dZ = loss_scale * dy: no need to recompute Z
+    const bool worked = blockIdx.x < ntiles;
 
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const size_t row = (size_t)tile * 128 + tid;
-        const bool row_ok = row < B;
-        // ---- global loads of this tile's rows first (they overlap the previous tile's weight-gradient MMAs)
-        uint4 xr[IN_PAD / 8];
+    if (warp == 4) {
+        // ================================================================ MMA issuer (one lane)
+        if (lane == 0) {
+            const uint32_t aX = tc05::smem_u32(smem + L.X), aH1 = tc05::smem_u32(smem + L.H1), aH2 = tc05::smem_u32(smem + L.H2);
+            const uint32_t adZ = tc05::smem_u32(smem + L.dZ), adH1 = tc05::smem_u32(smem + L.dH1), adH2 = tc05::smem_u32(smem + L.dH2);
+            const uint32_t aW1 = tc05::smem_u32(smem + L.W1), aWh = tc05::smem_u32(smem + L.Wh), aWo = tc05::smem_u32(smem + L.Wo);
+            const uint32_t aHlast = (NH == 2) ? aH2 : aH1;
+            // k = K-major view, m = MN-major view of a chunked tile
+            const uint64_t kX = tc05::desc_kmajor(aX, CH), mX = tc05::desc_mnmajor(aX, CH);
+            const uint64_t kH1 = tc05::desc_kmajor(aH1, CH);
+            const uint64_t kHlast = tc05::desc_kmajor(aHlast, CH), mHlast = tc05::desc_mnmajor(aHlast, CH);
+            const uint64_t kdZ = tc05::desc_kmajor(adZ, CH), mdZ = tc05::desc_mnmajor(adZ, CH);
+            const uint64_t kdH1 = tc05::desc_kmajor(adH1, CH), mdH1 = tc05::desc_mnmajor(adH1, CH);
+            const uint64_t kdH2 = tc05::desc_kmajor(adH2, CH);
+            const uint64_t kW1 = tc05::desc_kmajor(aW1, CHW), mW1 = tc05::desc_mnmajor(aW1, CHW);
+            const uint64_t kWh = tc05::desc_kmajor(aWh, CHW), mWh = tc05::desc_mnmajor(aWh, CHW);
+            const uint64_t kWo = tc05::desc_kmajor(aWo, CHO), mWo = tc05::desc_mnmajor(aWo, CHO);
+            constexpr uint32_t ID_H = tc05::idesc_f16(128, 64, false, false);        // X W1^T, H1 Wh^T      (A K-major, B K-major)
+            constexpr uint32_t ID_O = tc05::idesc_f16(128, 16, false, false);        // Hlast Wo^T
+            constexpr uint32_t ID_DH = tc05::idesc_f16(128, 64, false, true);        // dZ Wo, dH2 Wh        (B MN-major)
+            constexpr uint32_t ID_DX = tc05::idesc_f16(128, IN_PAD, false, true);    // dH1 W1
+            constexpr uint32_t ID_GS = tc05::idesc_f16(128, NS, true, true);         // stacked weight gradient
+            constexpr uint32_t ID_GWO = tc05::idesc_f16(64, 16, true, true);         // H2^T dZ (= dWo^T), NH == 2
+            uint32_t ph = 0;
+            bool first = true;
+            for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                // ---- H1 = act(X W1^T)
+                tc05::mbar_wait(&bar_ready, ph); ph ^= 1; tc05::fence_after_sync();
 #pragma unroll
-        for (int c = 0; c < IN_PAD / 8; c++) xr[c] = load_chunk(x, x_dt, row, c, n_in, row_ok, x_vec);
-        float dyr[16];
+                for (int k = 0; k < IN_KT; k++) tc05::mma_f16(tacc, dadv(kX, k * 2 * CH), dadv(kW1, k * 2 * CHW), ID_H, k > 0);
+                tc05::mma_commit(&bar_done);
+                if constexpr (NH == 2) {
+                    tc05::mbar_wait(&bar_ready, ph); ph ^= 1; tc05::fence_after_sync();
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-            float v = 0.0f;
-            if (row_ok && (uint32_t)j < n_out)
-                v = (dy_dt == NRF_DTYPE_F16) ? __half2float(reinterpret_cast<const __half*>(dy)[row * n_out + j])
-                                             : reinterpret_cast<const float*>(dy)[row * n_out + j];
-            dyr[j] = v;
-        }
-        if (!first) { tc05::mbar_wait(&bars[1], phase_w); phase_w ^= 1; tc05::fence_after_sync(); }   // operand tiles are free again
+                    for (int k = 0; k < 4; k++) tc05::mma_f16(tacc, dadv(kH1, k * 2 * CH), dadv(kWh, k * 2 * CHW), ID_H, k > 0);
+                    tc05::mma_commit(&bar_done);
+                }
+                if (!linear_out) {
+                    // ---- Z = Hlast Wo^T
+                    tc05::mbar_wait(&bar_ready, ph); ph ^= 1; tc05::fence_after_sync();
 #pragma unroll
-        for (int c = 0; c < IN_PAD / 8; c++) *reinterpret_cast<uint4*>(smem + L.X + c * CH + tid * 16) = xr[c];
-        publish_and_sync();
-        // ---- recompute: H1 = act(X W1^T)
-        if (tid == 0) {
-            tc05::fence_after_sync();
+                    for (int k = 0; k < 4; k++) tc05::mma_f16(tacc, dadv(kHlast, k * 2 * CH), dadv(kWo, k * 2 * CHO), ID_O, k > 0);
+                    tc05::mma_commit(&bar_done);
+                }
+                // ---- dHlast_pre = dZ Wo   (| dWo^T += H2^T dZ when NH == 2)
+                tc05::mbar_wait(&bar_ready, ph); ph ^= 1; tc05::fence_after_sync();
+                tc05::mma_f16(tacc, kdZ, mWo, ID_DH, 0);
+                tc05::mma_commit(&bar_done);
+                if constexpr (NH == 2) {
+                    if (want_dw) {
 #pragma unroll
-            for (int k = 0; k < IN_KT; k++)
-                tc05::mma_f16(tacc, tc05::desc_kmajor(sX + k * 2 * CH, CH), tc05::desc_kmajor(sW1 + k * 2 * CHW, CHW), ID_H, k > 0);
-            tc05::mma_commit(&bars[0]);
-        }
-        tc05::mbar_wait(&bars[0], phase); phase ^= 1;
-        tc05::fence_after_sync();
-        const unsigned long long m1 = hidden_epilogue<false>(tacc_lane, smem + L.H1 + tid * 16, relu, 0ull);
-        publish_and_sync();
-        unsigned long long m2 = 0ull;
-        if constexpr (NH == 2) {
-            if (tid == 0) {
-                tc05::fence_after_sync();
+                        for (int k = 0; k < 8; k++) tc05::mma_f16(tacc + T_WO, dadv(mHlast, k * 256), dadv(mdZ, k * 256), ID_GWO, (!first || k > 0) ? 1u : 0u);
+                    }
+                    // ---- dH1_pre = dH2 Wh
+                    tc05::mbar_wait(&bar_ready, ph); ph ^= 1; tc05::fence_after_sync();
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    tc05::mma_f16(tacc, tc05::desc_kmajor(sH1 + k * 2 * CH, CH), tc05::desc_kmajor(sWh + k * 2 * CHW, CHW), ID_H, k > 0);
-                tc05::mma_commit(&bars[0]);
-            }
-            tc05::mbar_wait(&bars[0], phase); phase ^= 1;
-            tc05::fence_after_sync();
-            m2 = hidden_epilogue<false>(tacc_lane, smem + L.H2 + tid * 16, relu, 0ull);
-            publish_and_sync();
-        }
-        // ---- Z = Hlast Wo^T, dZ = loss_scale * dy * act'(Z)
-        if (tid == 0) {
-            tc05::fence_after_sync();
+                    for (int k = 0; k < 4; k++) tc05::mma_f16(tacc, dadv(kdH2, k * 2 * CH), dadv(mWh, k * 256), ID_DH, k > 0);
+                    tc05::mma_commit(&bar_done);
+                }
+                // ---- dX = dH1 W1   |   stacked weight gradient  [dH1 | Hlast or dH2]^T [X | dZ or H1]
+                tc05::mbar_wait(&bar_ready, ph); ph ^= 1; tc05::fence_after_sync();
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-                tc05::mma_f16(tacc, tc05::desc_kmajor(sHlast + k * 2 * CH, CH), tc05::desc_kmajor(sWo + k * 2 * CHO, CHO), ID_O, k > 0);
-            tc05::mma_commit(&bars[0]);
-        }
-        tc05::mbar_wait(&bars[0], phase); phase ^= 1;
-        tc05::fence_after_sync();
-        {
-            uint32_t z[16];
-            tc05::tmem_ld16(tacc_lane, z);
-            tc05::tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
-                float f[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) f[j] = dyr[8 * c + j] * loss_scale * tact_bwd(__uint_as_float(z[8 * c + j]), out_act);
-                *reinterpret_cast<uint4*>(smem + L.dZ + c * CH + tid * 16) =
-                    make_uint4(tpack(f[0], f[1]), tpack(f[2], f[3]), tpack(f[4], f[5]), tpack(f[6], f[7]));
-            }
-        }
-        publish_and_sync();
-        // ---- dHlast = (dZ Wo) . relu'   |   dWo^T += Hlast^T dZ
-        if (tid == 0) {
-            tc05::fence_after_sync();
-            tc05::mma_f16(tacc, tc05::desc_kmajor(sdZ, CH), tc05::desc_mnmajor(sWo, CHO), ID_DH, 0);
-            tc05::mma_commit(&bars[0]);
-            if (want_dw) {
-#pragma unroll
-                for (int k = 0; k < 8; k++)
-                    tc05::mma_f16(tacc + T_WO, tc05::desc_mnmajor(sHlast + k * 256, CH), tc05::desc_mnmajor(sdZ + k * 256, CH), ID_GWO,
-                                  (!first || k > 0) ? 1u : 0u);
-            }
-        }
-        tc05::mbar_wait(&bars[0], phase); phase ^= 1;
-        tc05::fence_after_sync();
-        hidden_epilogue<true>(tacc_lane, smem + ((NH == 2) ? L.dH2 : L.dH1) + tid * 16, relu, (NH == 2) ? m2 : m1);
-        publish_and_sync();
-        if constexpr (NH == 2) {
-            // ---- dH1 = (dH2 Wh) . relu'   |   dWh += dH2^T H1
-            if (tid == 0) {
-                tc05::fence_after_sync();
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    tc05::mma_f16(tacc, tc05::desc_kmajor(sdH2 + k * 2 * CH, CH), tc05::desc_mnmajor(sWh + k * 256, CHW), ID_DH, k > 0);
-                tc05::mma_commit(&bars[0]);
+                for (int k = 0; k < 4; k++) tc05::mma_f16(tacc, dadv(kdH1, k * 2 * CH), dadv(mW1, k * 256), ID_DX, k > 0);
+                tc05::mma_commit(&bar_done);
                 if (want_dw) {
 #pragma unroll
-                    for (int k = 0; k < 8; k++)
-                        tc05::mma_f16(tacc + T_WH, tc05::desc_mnmajor(sdH2 + k * 256, CH), tc05::desc_mnmajor(sH1 + k * 256, CH), ID_GWH,
-                                      (!first || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < 8; k++) tc05::mma_f16(tacc + T_S, dadv(mdH1, k * 256), dadv(mX, k * 256), ID_GS, (!first || k > 0) ? 1u : 0u);
                 }
+                tc05::mma_commit(&bar_wdone);
+                first = false;
             }
-            tc05::mbar_wait(&bars[0], phase); phase ^= 1;
-            tc05::fence_after_sync();
-            hidden_epilogue<true>(tacc_lane, smem + L.dH1 + tid * 16, relu, m1);
-            publish_and_sync();
         }
-        // ---- dX = dH1 W1   |   dW1 += dH1^T X
-        if (tid == 0) {
-            tc05::fence_after_sync();
+        __syncwarp();
+    } else {
+        // ================================================================ row owners
+        long long plast = 0;
+        if (prof && tid == 0) { for (int i = 0; i < 16; i++) s_prof[i] = 0; plast = clock64(); }
+#define PROF_MARK(i) do { if (prof && tid == 0) { const long long t_ = clock64(); s_prof[i] += t_ - plast; plast = t_; } } while (0)
+        const uint32_t tacc_lane = tacc + ((uint32_t)(warp * 32) << 16);
+        const bool relu = hidden_act == NRF_ACT_RELU;
+        const bool x_vec = vec_ok_for(x, n_in);
+        const bool dx_vec = vec_ok_for(dx, n_in);
+        const bool dy_vec = vec_ok_for(dy, n_out);
+        const float inv_scale = 1.0f / loss_scale;
+        uint32_t phase = 0, phase_w = 0;
+        bool first = true;
+        uint8_t* const xrow = smem + L.X + tid * 16;
+        uint8_t* const h1row = smem + L.H1 + tid * 16;
+        uint8_t* const h2row = smem + L.H2 + tid * 16;
+        uint8_t* const dzrow = smem + L.dZ + tid * 16;
+        uint8_t* const dh1row = smem + L.dH1 + tid * 16;
+        uint8_t* const dh2row = smem + L.dH2 + tid * 16;
+        uint8_t* const hlastrow = (NH == 2) ? h2row : h1row;
+        uint8_t* const dhlastrow = (NH == 2) ? dh2row : dh1row;
+
+        // software pipeline: rows of tile i+1 are fetched from HBM while tile i is processed
+        uint4 xr[IN_PAD / 8];
+        uint32_t dyraw[16];
+        {
+            const size_t row0 = (size_t)blockIdx.x * 128 + tid;
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-                tc05::mma_f16(tacc, tc05::desc_kmajor(sdH1 + k * 2 * CH, CH), tc05::desc_mnmajor(sW1 + k * 256, CHW), ID_DX, k > 0);
-            tc05::mma_commit(&bars[0]);
-            if (want_dw) {
+            for (int c = 0; c < IN_PAD / 8; c++) xr[c] = load_chunk(x, x_dt, row0, c, n_in, row0 < B, x_vec);
+            dy_load_raw(dy, dy_dt, row0, n_out, row0 < B, dy_vec, dyraw);
+        }
+        for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const size_t row = (size_t)tile * 128 + tid;
+            const bool row_ok = row < B;
+            uint32_t dyc[8];
+            dy_convert(dyraw, dy_dt, dy_vec, loss_scale, dyc);
+            PROF_MARK(0);
+            if (!first) { tc05::mbar_wait(&bar_wdone, phase_w); phase_w ^= 1; }      // operand tiles are free again
+            PROF_MARK(1);      // previous tile's weight-gradient MMAs done
 #pragma unroll
-                for (int k = 0; k < 8; k++)
-                    tc05::mma_f16(tacc + T_W1, tc05::desc_mnmajor(sdH1 + k * 256, CH), tc05::desc_mnmajor(sX + k * 256, CH), ID_GW1,
-                                  (!first || k > 0) ? 1u : 0u);
+            for (int c = 0; c < IN_PAD / 8; c++) *reinterpret_cast<uint4*>(xrow + c * CH) = xr[c];
+            if (linear_out) {
+                *reinterpret_cast<uint4*>(dzrow) = make_uint4(dyc[0], dyc[1], dyc[2], dyc[3]);
+                *reinterpret_cast<uint4*>(dzrow + CH) = make_uint4(dyc[4], dyc[5], dyc[6], dyc[7]);
             }
-            tc05::mma_commit(&bars[1]);
-        }
-        tc05::mbar_wait(&bars[0], phase); phase ^= 1;
-        tc05::fence_after_sync();
-        if (dx != nullptr) {
+            publish(&bar_ready);
+            {   // prefetch the next tile's rows
+                const uint32_t nt = tile + gridDim.x;
+                const size_t nrow = (size_t)nt * 128 + tid;
+                const bool nok = nt < ntiles && nrow < B;
 #pragma unroll
-            for (int g = 0; g < IN_PAD / 16; g++) {
-                uint32_t v[16];
-                tc05::tmem_ld16(tacc_lane + 16 * g, v);
+                for (int c = 0; c < IN_PAD / 8; c++) xr[c] = load_chunk(x, x_dt, nrow, c, n_in, nok, x_vec);
+                dy_load_raw(dy, dy_dt, nrow, n_out, nok, dy_vec, dyraw);
+            }
+            PROF_MARK(2);      // operands staged, prefetch issued
+            tc05::mbar_wait(&bar_done, phase); phase ^= 1; tc05::fence_after_sync();
+            PROF_MARK(3);      // H1 MMA round trip
+            hidden_fwd_epilogue(tacc_lane, h1row, relu);
+            publish(&bar_ready);
+            PROF_MARK(4);      // H1 epilogue
+            if constexpr (NH == 2) {
+                tc05::mbar_wait(&bar_done, phase); phase ^= 1; tc05::fence_after_sync();
+                hidden_fwd_epilogue(tacc_lane, h2row, relu);
+                publish(&bar_ready);
+            }
+            PROF_MARK(5);      // H2 round trip + epilogue
+            if (!linear_out) {
+                tc05::mbar_wait(&bar_done, phase); phase ^= 1; tc05::fence_after_sync();
+                PROF_MARK(6);  // Z MMA round trip
+                uint32_t z[16];
+                tc05::tmem_ld16(tacc_lane, z);
                 tc05::tmem_ld_wait();
-                if (row_ok) {
 #pragma unroll
-                    for (int c = 0; c < 2; c++) {
-                        float f[8];
+                for (int c = 0; c < 2; c++) {
+                    uint32_t p[4] = {0u, 0u, 0u, 0u};
+                    if (8u * c < n_out) {
 #pragma unroll
-                        for (int j = 0; j < 8; j++) f[j] = __uint_as_float(v[8 * c + j]) * inv_scale;
-                        store_chunk(dx, x_dt, row, 2 * g + c, n_in, f, dx_vec);
+                        for (int q = 0; q < 4; q++) {
+                            const float2 d = __half22float2(bits2h(dyc[4 * c + q]));
+                            p[q] = tpack(d.x * tact_bwd(__uint_as_float(z[8 * c + 2 * q]), out_act),
+                                         d.y * tact_bwd(__uint_as_float(z[8 * c + 2 * q + 1]), out_act));
+                        }
+                    }
+                    *reinterpret_cast<uint4*>(dzrow + c * CH) = make_uint4(p[0], p[1], p[2], p[3]);
+                }
+                publish(&bar_ready);
+                PROF_MARK(7);  // dZ epilogue
+            }
+            tc05::mbar_wait(&bar_done, phase); phase ^= 1; tc05::fence_after_sync();
+            PROF_MARK(8);      // dHlast MMA round trip
+            hidden_bwd_epilogue(tacc_lane, hlastrow, dhlastrow, relu);
+            publish(&bar_ready);
+            PROF_MARK(9);      // dHlast epilogue
+            if constexpr (NH == 2) {
+                tc05::mbar_wait(&bar_done, phase); phase ^= 1; tc05::fence_after_sync();
+                hidden_bwd_epilogue(tacc_lane, h1row, dh1row, relu);
+                publish(&bar_ready);
+            }
+            tc05::mbar_wait(&bar_done, phase); phase ^= 1; tc05::fence_after_sync();
+            PROF_MARK(10);     // (dH1 round trip + epilogue,) dX MMA round trip
+            if (dx != nullptr) {
+#pragma unroll
+                for (int g = 0; g < IN_PAD / 16; g++) {
+                    uint32_t v[16];
+                    tc05::tmem_ld16(tacc_lane + 16 * g, v);
+                    tc05::tmem_ld_wait();
+                    if (row_ok) {
+#pragma unroll
+                        for (int c = 0; c < 2; c++) {
+                            float f[8];
+#pragma unroll
+                            for (int j = 0; j < 8; j++) f[j] = __uint_as_float(v[8 * c + j]) * inv_scale;
+                            store_chunk(dx, x_dt, row, 2 * g + c, n_in, f, dx_vec);
+                        }
                     }
                 }
             }
+            first = false;
+            PROF_MARK(11);     // dX epilogue
+            // the next tile's publish() orders these TMEM reads before the issuer overwrites the accumulator
         }
-        first = false;
-        // the next tile's publish_and_sync orders these TMEM reads before its first MMA
-    }
-    // ---- flush the weight gradients accumulated in TMEM (M=64 layout: row m lives in lane (m % 16) + 32 * (m / 16))
-    if (!first) { tc05::mbar_wait(&bars[1], phase_w); tc05::fence_after_sync(); }
-    if (want_dw && !first) {
-        // tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only lanes 0-15 hold rows of an M=64 accumulator
-        const int m = warp * 16 + (lane & 15);
-        const bool owner = lane < 16;
-        float* dW1 = dparams;
-        float* dWh = dparams + 64 * IN_PAD;
-        float* dWo = dWh + (NH - 1) * 64 * 64;
+        // ---- flush the weight gradients accumulated in TMEM
+        if (worked) { tc05::mbar_wait(&bar_wdone, phase_w); tc05::fence_after_sync(); }
+        if (want_dw && worked) {
+            float* dW1 = dparams;
+            float* dWh = dparams + 64 * IN_PAD;
+            float* dWo = dWh + (NH - 1) * 64 * 64;
+            // stacked product (M=128 layout: row m in lane m): rows 0-63 x cols [0, in) = dW1; rows 64-127 x cols [in, NS) =
+            // dWo^T (NH == 1) or dWh (NH == 2).  tcgen05.ld is warp-collective: the branch below is warp-uniform.
+            if (tid < 64) {
 #pragma unroll 1
-        for (int g = 0; g < IN_PAD / 16; g++) {        // dW1[m][:]
-            uint32_t v[16];
-            tc05::tmem_ld16(tacc_lane + T_W1 + 16 * g, v);
-            tc05::tmem_ld_wait();
-            if (owner) {
+                for (int g = 0; g < IN_PAD / 16; g++) {
+                    uint32_t v[16];
+                    tc05::tmem_ld16(tacc_lane + T_S + 16 * g, v);
+                    tc05::tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; j++) atomicAdd(dW1 + m * IN_PAD + 16 * g + j, __uint_as_float(v[j]) * inv_scale);
-            }
-        }
-        if constexpr (NH == 2) {
-#pragma unroll 1
-            for (int g = 0; g < 4; g++) {              // dWh[m][:]
+                    for (int j = 0; j < 16; j++) atomicAdd(dW1 + tid * IN_PAD + 16 * g + j, __uint_as_float(v[j]) * inv_scale);
+                }
+            } else if constexpr (NH == 1) {
                 uint32_t v[16];
-                tc05::tmem_ld16(tacc_lane + T_WH + 16 * g, v);
+                tc05::tmem_ld16(tacc_lane + T_S + IN_PAD, v);
                 tc05::tmem_ld_wait();
-                if (owner) {
 #pragma unroll
-                    for (int j = 0; j < 16; j++) atomicAdd(dWh + m * 64 + 16 * g + j, __uint_as_float(v[j]) * inv_scale);
+                for (int j = 0; j < 16; j++) atomicAdd(dWo + j * 64 + (tid - 64), __uint_as_float(v[j]) * inv_scale);
+            } else {
+#pragma unroll 1
+                for (int g = 0; g < 4; g++) {
+                    uint32_t v[16];
+                    tc05::tmem_ld16(tacc_lane + T_S + IN_PAD + 16 * g, v);
+                    tc05::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; j++) atomicAdd(dWh + (tid - 64) * 64 + 16 * g + j, __uint_as_float(v[j]) * inv_scale);
+                }
+            }
+            if constexpr (NH == 2) {
+                // dWo^T (M=64 layout: row m in lane (m % 16) + 32 * (m / 16)); every lane loads, lanes 0-15 own rows
+                uint32_t v[16];
+                tc05::tmem_ld16(tacc_lane + T_WO, v);
+                tc05::tmem_ld_wait();
+                if (lane < 16) {
+                    const int m = warp * 16 + lane;
+#pragma unroll
+                    for (int j = 0; j < 16; j++) atomicAdd(dWo + j * 64 + m, __uint_as_float(v[j]) * inv_scale);
                 }
             }
         }
-        {                                              // dWo^T[m][o] -> dWo[o][m]
-            uint32_t v[16];
-            tc05::tmem_ld16(tacc_lane + T_WO, v);
-            tc05::tmem_ld_wait();
-            if (owner) {
-#pragma unroll
-                for (int j = 0; j < 16; j++) atomicAdd(dWo + j * 64 + m, __uint_as_float(v[j]) * inv_scale);
-            }
-        }
+        PROF_MARK(12);         // dW flush
+        if (prof && tid == 0 && blockIdx.x == 0) { for (int i = 0; i < 16; i++) prof[i] = (unsigned long long)s_prof[i]; }
+#undef PROF_MARK
     }
     publish_and_sync();
     if (warp == 0) tc05::tmem_dealloc(tacc, TCOLS);
@@ -515,7 +667,8 @@ int tc_sm_count() {
     return n;
 }
 
-int g_fwd_ctas_per_sm = 5, g_bwd_ctas_per_sm = 4;
+int g_fwd_ctas_per_sm = 6, g_bwd_ctas_per_sm = 4;
+unsigned long long* g_prof = nullptr;
 
 template <int IN_KT, int NH>
 int launch_fwd(const void* x, int xdt, const void* params, uint32_t B, uint32_t n_in, uint32_t n_out, int hact, int oact, void* y, int ydt,
@@ -540,7 +693,7 @@ int launch_bwd(const void* x, int xdt, const void* params, const void* dy, int d
     const uint32_t ntiles = ceil_div_u32(B, 128);
     const uint32_t per_sm = (uint32_t)max(1, min(min(g_bwd_ctas_per_sm, (int)(220 * 1024 / (L.total + 1024))), (int)(512 / TCOLS)));
     const uint32_t grid = (uint32_t)min((uint64_t)ntiles, (uint64_t)tc_sm_count() * per_sm);
-    kern<<<grid, TC_THREADS, L.total, s>>>(x, xdt, (const __half*)params, dy, dydt, B, n_in, n_out, hact, oact, ls, dx, dparams);
+    kern<<<grid, TC_THREADS, L.total, s>>>(x, xdt, (const __half*)params, dy, dydt, B, n_in, n_out, hact, oact, ls, dx, dparams, g_prof);
     return nrf_check_launch();
 }
 
@@ -567,6 +720,8 @@ int nrf_mlp_tc_backward(const void* x, int x_dtype, const void* params_f16, cons
 #undef TC_BWD
     return NRF_E_UNSUPPORTED;
 }
+
+void nrf_mlp_tc_set_prof(unsigned long long* buf16) { g_prof = buf16; }
 
 void nrf_mlp_tc_set_ctas(int fwd_per_sm, int bwd_per_sm) {
     if (fwd_per_sm > 0) g_fwd_ctas_per_sm = fwd_per_sm;

@@ -30,6 +30,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // Bounded spin: a lost arrival (bad descriptor, missing commit) becomes a trap -> CUDA error, never a hung GPU.
 // NOTE parity waits alias after two phases: every use in this library has a block barrier between consecutive phases.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {

@@ -176,6 +176,53 @@ __global__ void __launch_bounds__(128) k_time(long long* out, int iters, int mod
     if (warp == 0) tc05::tmem_dealloc(tbase, 128);
 }
 
+
+// ---------------------------------------------------------------------------------------------- MMA throughput by shape / major
+__global__ void __launch_bounds__(128) k_mma_rate(long long* out, int n_mma, uint32_t idesc, uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo,
+                                                  uint32_t b_sbo) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    for (uint32_t i = threadIdx.x; i < 65536 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) { tc05::tmem_alloc(&tmem_slot, 128); tc05::tmem_relinquish(); }
+    if (threadIdx.x == 0) { tc05::mbar_init(&bar, 1); tc05::fence_mbar_init(); }
+    tc05::fence_async_smem();
+    tc05::fence_before_sync();
+    __syncthreads();
+    tc05::fence_after_sync();
+    const uint32_t tbase = tmem_slot;
+    const uint64_t ad = tc05::smem_desc(tc05::smem_u32(smem), a_lbo, a_sbo), bd = tc05::smem_desc(tc05::smem_u32(smem) + 32768, b_lbo, b_sbo);
+    long long t0 = clock64();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < n_mma; i++) tc05::mma_f16(tbase, ad, bd, idesc, 1);
+        tc05::mma_commit(&bar);
+    }
+    tc05::mbar_wait(&bar, 0);
+    tc05::fence_after_sync();
+    long long t1 = clock64();
+    if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+    tc05::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc05::tmem_dealloc(tbase, 128);
+}
+
+static void mma_rate(const char* name, int M, int N, bool a_mn, bool b_mn, uint32_t cha, uint32_t chb) {
+    long long* d; CK(cudaMalloc(&d, 8 * 1024));
+    CK(cudaFuncSetAttribute(k_mma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    const uint32_t idesc = tc05::idesc_f16(M, N, a_mn, b_mn);
+    const uint32_t a_lbo = a_mn ? 128 : cha, a_sbo = a_mn ? cha : 128, b_lbo = b_mn ? 128 : chb, b_sbo = b_mn ? chb : 128;
+    long long r[2];
+    for (int pass = 0; pass < 2; pass++) {
+        const int n = pass == 0 ? 16 : 272;
+        k_mma_rate<<<1, 128, 65536>>>(d, n, idesc, a_lbo, a_sbo, b_lbo, b_sbo);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(&r[pass], d, 8, cudaMemcpyDeviceToHost));
+    }
+    printf("mma rate: %-40s %6.1f cycles/MMA  (16 MMAs + commit + wait: %lld cycles)\n", name, (double)(r[1] - r[0]) / 256.0, r[0]);
+    cudaFree(d);
+}
+
 int main() {
     setvbuf(stdout, nullptr, _IONBF, 0);
     int dev = 0; cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, dev));
@@ -257,6 +304,22 @@ int main() {
             printf("time: %-50s grid %4d: %8.1f cycles/iter (block 0), kernel %.3f ms -> %.1f ns/iter\n", names[mode], grid, (double)h[0] / iters, ms, ms * 1e6 / iters);
         }
     }
+    mma_rate("M128 N64 A:K  B:K", 128, 64, false, false, 2048, 1024);
+    mma_rate("M128 N64 A:K  B:MN", 128, 64, false, true, 2048, 1024);
+    mma_rate("M128 N32 A:K  B:MN (dX)", 128, 32, false, true, 2048, 1024);
+    mma_rate("M128 N16 A:K  B:K  (Z)", 128, 16, false, false, 2048, 256);
+    mma_rate("M64  N32 A:MN B:MN (dW1)", 64, 32, true, true, 2048, 2048);
+    mma_rate("M64  N16 A:MN B:MN (dWo)", 64, 16, true, true, 2048, 2048);
+    mma_rate("M64  N64 A:MN B:MN (dWh)", 64, 64, true, true, 2048, 2048);
+    mma_rate("M64  N32 A:K  B:K", 64, 32, false, false, 2048, 1024);
+    mma_rate("M64  N32 A:MN B:K", 64, 32, true, false, 2048, 1024);
+    mma_rate("M64  N32 A:K  B:MN", 64, 32, false, true, 2048, 2048);
+    mma_rate("M128 N32 A:MN B:MN", 128, 32, true, true, 2048, 2048);
+    mma_rate("M128 N48 A:MN B:MN (dW1|dWo stacked)", 128, 48, true, true, 2048, 2048);
+    mma_rate("M128 N64 A:MN B:MN", 128, 64, true, true, 2048, 2048);
+    mma_rate("M128 N128 A:MN B:MN", 128, 128, true, true, 2048, 2048);
+    mma_rate("M128 N128 A:K B:K", 128, 128, false, false, 2048, 2048);
+    mma_rate("M128 N256 A:K B:K", 128, 256, false, false, 2048, 4096);
     printf(fails ? "PROBE FAILED (%d)\n" : "PROBE OK\n", fails);
     return fails ? 1 : 0;
 }
