@@ -50,6 +50,7 @@ extern "C" {
 #define NRF_ACT_RELU     1
 #define NRF_ACT_SIGMOID  2
 #define NRF_ACT_EXP      3
+#define NRF_ACT_TRUNC_EXP 4   /* y = exp(f16(z)) in f32; dy/dz = exp(clamp(f16(z), -15, 15)) (networks/tcnn_nerf.py:55-69) */
 
 const char* nrf_error_string(int code);
 int  nrf_last_cuda_error(void);          /* cudaError_t of the last NRF_E_CUDA on this thread */
@@ -184,6 +185,21 @@ int nrf_mlp_backward(const void* x, int x_dtype, const void* params_f16, const v
                      uint32_t B, uint32_t n_in, uint32_t n_out, uint32_t n_hidden, uint32_t width,
                      int hidden_act, int out_act, float loss_scale, void* dx, int dx_dtype, float* dparams,
                      void* stream);
+
+/* Extended forms used by the fused field heads of the host mirror (nerfstyle_b200/model.py): the output may be a
+ * column block of a wider row-major matrix (ld_y / ld_dy = row stride in elements, 0 = n_out), which removes the
+ * torch.cat of networks/style_nerf.py:139-141 and the dtype-cast / slice copies of its backward; dx_accumulate != 0
+ * ADDS the input gradient into dx (vector reductions, no read-modify-write pass) so that two networks sharing an
+ * input (class_net / color1_net, style_nerf.py:136-138) need no separate add.  An f32 y holds the f16 network output
+ * widened (tcnn's output precision), except NRF_ACT_TRUNC_EXP which fuses networks/tcnn_nerf.py:55-69.
+ * These extensions run on the tcgen05 implementation only. */
+int nrf_mlp_forward_ex(const void* x, int x_dtype, const void* params_f16, uint32_t B, uint32_t n_in,
+                       uint32_t n_out, uint32_t n_hidden, uint32_t width, int hidden_act, int out_act,
+                       void* y, int y_dtype, uint32_t ld_y, void* stream);
+int nrf_mlp_backward_ex(const void* x, int x_dtype, const void* params_f16, const void* dy, int dy_dtype,
+                        uint32_t ld_dy, uint32_t B, uint32_t n_in, uint32_t n_out, uint32_t n_hidden,
+                        uint32_t width, int hidden_act, int out_act, float loss_scale, void* dx, int dx_dtype,
+                        int dx_accumulate, float* dparams, void* stream);
 
 /* ------------------------------------------------------------------ nearest-neighbour feature matching */
 

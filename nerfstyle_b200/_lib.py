@@ -49,6 +49,9 @@ SIGNATURES = {
     'nrf_mlp_forward': (_i32, [_vp, _i32, _vp, _u32, _u32, _u32, _u32, _u32, _i32, _i32, _vp, _i32, _vp]),
     'nrf_mlp_backward': (_i32, [_vp, _i32, _vp, _vp, _i32, _u32, _u32, _u32, _u32, _u32, _i32, _i32, _f32, _vp, _i32,
                                 _vp, _vp]),
+    'nrf_mlp_forward_ex': (_i32, [_vp, _i32, _vp, _u32, _u32, _u32, _u32, _u32, _i32, _i32, _vp, _i32, _u32, _vp]),
+    'nrf_mlp_backward_ex': (_i32, [_vp, _i32, _vp, _vp, _i32, _u32, _u32, _u32, _u32, _u32, _u32, _i32, _i32, _f32, _vp, _i32,
+                                   _i32, _vp, _vp]),
     'nrf_nnfm_forward': (_i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
     'nrf_nnfm_scratch_bytes': (_u64, [_u32, _u32]),
     'nrf_opt_state_bytes': (_u64, []),
@@ -66,7 +69,7 @@ EXTRA_SIGNATURES = {
 }
 
 DTYPE_F32, DTYPE_F16 = 0, 1
-ACT = {'none': 0, 'relu': 1, 'sigmoid': 2, 'exponential': 3}
+ACT = {'none': 0, 'relu': 1, 'sigmoid': 2, 'exponential': 3, 'trunc_exp': 4}
 
 _lib = None
 
@@ -76,7 +79,7 @@ KERNELS_PER_CALL = {
     'nrf_march_rays_train_count': 4, 'nrf_march_rays_train_write': 1, 'nrf_march_rays_train': 4,
     'nrf_composite_rays_train_forward': 1, 'nrf_composite_rays_train_backward': 1, 'nrf_march_rays': 1,
     'nrf_composite_rays': 1, 'nrf_compact_alive': 3, 'nrf_grid_encode_forward': 1, 'nrf_grid_encode_backward': 1,
-    'nrf_grid_initialize': 1, 'nrf_mlp_forward': 1, 'nrf_mlp_backward': 1, 'nrf_nnfm_forward': 3,
+    'nrf_grid_initialize': 1, 'nrf_mlp_forward': 1, 'nrf_mlp_backward': 1, 'nrf_mlp_forward_ex': 1, 'nrf_mlp_backward_ex': 1, 'nrf_nnfm_forward': 3,
     'nrf_adam_step': 1, 'nrf_grads_check': 1, 'nrf_scaler_update': 1,
 }
 

@@ -430,10 +430,10 @@ k_mlp_bwd(const XT* __restrict__ x, const __half* __restrict__ params, const DYT
 // mlp_tc.cu: the tcgen05 / TMEM implementation (default); the mma.sync kernels above stay as the selectable
 // second implementation (nrf_mlp_set_mode(1)) that the parity tests run side by side.
 int nrf_mlp_tc_forward(const void* x, int x_dtype, const void* params_f16, uint32_t B, uint32_t n_in, uint32_t n_out, uint32_t n_hidden,
-                       int hidden_act, int out_act, void* y, int y_dtype, cudaStream_t s);
-int nrf_mlp_tc_backward(const void* x, int x_dtype, const void* params_f16, const void* dy, int dy_dtype, uint32_t B, uint32_t n_in,
-                        uint32_t n_out, uint32_t n_hidden, int hidden_act, int out_act, float loss_scale, void* dx, float* dparams,
-                        cudaStream_t s);
+                       int hidden_act, int out_act, void* y, int y_dtype, uint32_t ld_y, cudaStream_t s);
+int nrf_mlp_tc_backward(const void* x, int x_dtype, const void* params_f16, const void* dy, int dy_dtype, uint32_t ld_dy, uint32_t B,
+                        uint32_t n_in, uint32_t n_out, uint32_t n_hidden, int hidden_act, int out_act, float loss_scale, void* dx,
+                        int dx_accumulate, float* dparams, cudaStream_t s);
 void nrf_mlp_tc_set_ctas(int fwd_per_sm, int bwd_per_sm);
 void nrf_mlp_tc_set_prof(unsigned long long* buf16);
 static int g_mlp_mode = 0;      // 0 = tcgen05 (mlp_tc.cu), 1 = mma.sync (this file)
@@ -474,17 +474,28 @@ static int launch_fwd_dt(const void* x, int xdt, const void* params, uint32_t B,
     return NRF_E_UNSUPPORTED;
 }
 
+NRF_EXPORT int nrf_mlp_forward_ex(const void* x, int x_dtype, const void* params_f16, uint32_t B, uint32_t n_in, uint32_t n_out,
+                                  uint32_t n_hidden, uint32_t width, int hidden_act, int out_act, void* y, int y_dtype,
+                                  uint32_t ld_y, void* stream);
 NRF_EXPORT int nrf_mlp_forward(const void* x, int x_dtype, const void* params_f16, uint32_t B, uint32_t n_in, uint32_t n_out,
                                uint32_t n_hidden, uint32_t width, int hidden_act, int out_act, void* y, int y_dtype,
                                void* stream) {
+    return nrf_mlp_forward_ex(x, x_dtype, params_f16, B, n_in, n_out, n_hidden, width, hidden_act, out_act, y, y_dtype, n_out, stream);
+}
+NRF_EXPORT int nrf_mlp_forward_ex(const void* x, int x_dtype, const void* params_f16, uint32_t B, uint32_t n_in, uint32_t n_out,
+                                  uint32_t n_hidden, uint32_t width, int hidden_act, int out_act, void* y, int y_dtype,
+                                  uint32_t ld_y, void* stream) {
     if (B == 0) return NRF_OK;
+    if (ld_y == 0) ld_y = n_out;
+    if (ld_y < n_out) return NRF_E_INVALID;
     if (!x || !params_f16 || !y) return NRF_E_INVALID;
     if (width != MLP_WIDTH || n_in == 0 || n_in > 64 || n_out == 0 || n_out > 16 || n_hidden < 1 || n_hidden > 2) return NRF_E_UNSUPPORTED;
     if (hidden_act != NRF_ACT_RELU && hidden_act != NRF_ACT_NONE) return NRF_E_UNSUPPORTED;
     cudaStream_t s = (cudaStream_t)stream;
     if (x_dtype != NRF_DTYPE_F16 && x_dtype != NRF_DTYPE_F32) return NRF_E_UNSUPPORTED;
     if (y_dtype != NRF_DTYPE_F16 && y_dtype != NRF_DTYPE_F32) return NRF_E_UNSUPPORTED;
-    if (g_mlp_mode == 0) return nrf_mlp_tc_forward(x, x_dtype, params_f16, B, n_in, n_out, n_hidden, hidden_act, out_act, y, y_dtype, s);
+    if (g_mlp_mode == 0) return nrf_mlp_tc_forward(x, x_dtype, params_f16, B, n_in, n_out, n_hidden, hidden_act, out_act, y, y_dtype, ld_y, s);
+    if (ld_y != n_out || out_act == NRF_ACT_TRUNC_EXP) return NRF_E_UNSUPPORTED;      // extensions exist on the tcgen05 path only
     const int kt = (int)((n_in + 15) / 16), nt = n_out <= 8 ? 1 : 2;
 #define FWD_CASE(K, H, N) if (kt == K && (int)n_hidden == H && nt == N) return launch_fwd_dt<K, H, N>(x, x_dtype, params_f16, B, n_in, n_out, hidden_act, out_act, y, y_dtype, s)
     FWD_CASE(1, 1, 1); FWD_CASE(1, 1, 2); FWD_CASE(1, 2, 1); FWD_CASE(1, 2, 2);
@@ -522,10 +533,23 @@ static int launch_bwd_dt(const void* x, int xdt, const void* params, const void*
     return NRF_E_UNSUPPORTED;
 }
 
+NRF_EXPORT int nrf_mlp_backward_ex(const void* x, int x_dtype, const void* params_f16, const void* dy, int dy_dtype, uint32_t ld_dy,
+                                   uint32_t B, uint32_t n_in, uint32_t n_out, uint32_t n_hidden, uint32_t width, int hidden_act,
+                                   int out_act, float loss_scale, void* dx, int dx_dtype, int dx_accumulate, float* dparams,
+                                   void* stream);
 NRF_EXPORT int nrf_mlp_backward(const void* x, int x_dtype, const void* params_f16, const void* dy, int dy_dtype, uint32_t B,
                                 uint32_t n_in, uint32_t n_out, uint32_t n_hidden, uint32_t width, int hidden_act, int out_act,
                                 float loss_scale, void* dx, int dx_dtype, float* dparams, void* stream) {
+    return nrf_mlp_backward_ex(x, x_dtype, params_f16, dy, dy_dtype, n_out, B, n_in, n_out, n_hidden, width, hidden_act, out_act,
+                               loss_scale, dx, dx_dtype, 0, dparams, stream);
+}
+NRF_EXPORT int nrf_mlp_backward_ex(const void* x, int x_dtype, const void* params_f16, const void* dy, int dy_dtype, uint32_t ld_dy,
+                                   uint32_t B, uint32_t n_in, uint32_t n_out, uint32_t n_hidden, uint32_t width, int hidden_act,
+                                   int out_act, float loss_scale, void* dx, int dx_dtype, int dx_accumulate, float* dparams,
+                                   void* stream) {
     if (B == 0) return NRF_OK;
+    if (ld_dy == 0) ld_dy = n_out;
+    if (ld_dy < n_out) return NRF_E_INVALID;
     if (!x || !params_f16 || !dy) return NRF_E_INVALID;
     if (width != MLP_WIDTH || n_in == 0 || n_in > 64 || n_out == 0 || n_out > 16 || n_hidden < 1 || n_hidden > 2) return NRF_E_UNSUPPORTED;
     if (hidden_act != NRF_ACT_RELU && hidden_act != NRF_ACT_NONE) return NRF_E_UNSUPPORTED;
@@ -534,8 +558,10 @@ NRF_EXPORT int nrf_mlp_backward(const void* x, int x_dtype, const void* params_f
     if (g_mlp_mode == 0) {
         if (dx && dx_dtype != x_dtype) return NRF_E_UNSUPPORTED;
         if ((x_dtype != NRF_DTYPE_F16 && x_dtype != NRF_DTYPE_F32) || (dy_dtype != NRF_DTYPE_F16 && dy_dtype != NRF_DTYPE_F32)) return NRF_E_UNSUPPORTED;
-        return nrf_mlp_tc_backward(x, x_dtype, params_f16, dy, dy_dtype, B, n_in, n_out, n_hidden, hidden_act, out_act, loss_scale, dx, dparams, s);
+        return nrf_mlp_tc_backward(x, x_dtype, params_f16, dy, dy_dtype, ld_dy, B, n_in, n_out, n_hidden, hidden_act, out_act, loss_scale, dx,
+                                   dx_accumulate, dparams, s);
     }
+    if (ld_dy != n_out || dx_accumulate || out_act == NRF_ACT_TRUNC_EXP) return NRF_E_UNSUPPORTED;     // tcgen05 path only
     const int kt = (int)((n_in + 15) / 16), nt = n_out <= 8 ? 1 : 2;
 #define BWD_CASE(K, H, N) if (kt == K && (int)n_hidden == H && nt == N) return launch_bwd_dt<K, H, N>(x, x_dtype, params_f16, dy, dy_dtype, B, n_in, n_out, hidden_act, out_act, loss_scale, dx, dx_dtype, dparams, s)
     BWD_CASE(1, 1, 1); BWD_CASE(1, 1, 2); BWD_CASE(1, 2, 1); BWD_CASE(1, 2, 2);

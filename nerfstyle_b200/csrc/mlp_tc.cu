@@ -38,6 +38,7 @@ __device__ __forceinline__ float tact_fwd(float z, int act) {
         case NRF_ACT_RELU: return fmaxf(z, 0.0f);
         case NRF_ACT_SIGMOID: return __frcp_rn(1.0f + __expf(-z));
         case NRF_ACT_EXP: return __expf(z);
+        case NRF_ACT_TRUNC_EXP: return __expf(__half2float(__float2half_rn(z)));      // trunc_exp of the f16 network output
         default: return z;
     }
 }
@@ -46,6 +47,7 @@ __device__ __forceinline__ float tact_bwd(float z, int act) {
         case NRF_ACT_RELU: return z > 0.0f ? 1.0f : 0.0f;
         case NRF_ACT_SIGMOID: { const float y = __frcp_rn(1.0f + __expf(-z)); return y * (1.0f - y); }
         case NRF_ACT_EXP: return __expf(z);
+        case NRF_ACT_TRUNC_EXP: return __expf(fminf(fmaxf(__half2float(__float2half_rn(z)), -15.0f), 15.0f));   // tcnn_nerf.py:66-68
         default: return 1.0f;
     }
 }
@@ -82,18 +84,18 @@ __device__ __forceinline__ uint4 load_chunk(const void* __restrict__ base, int d
     return make_uint4(tpack(v[0], v[1]), tpack(v[2], v[3]), tpack(v[4], v[5]), tpack(v[6], v[7]));
 }
 
-// 8 consecutive f32 values -> columns [8c, 8c+8) of row `row` of a row-major [B, n] matrix (f16 or f32)
-__device__ __forceinline__ void store_chunk(void* __restrict__ base, int dt, size_t row, uint32_t c, uint32_t n, const float (&v)[8],
-                                            bool vec_ok) {
+// 8 consecutive f32 values -> columns [8c, 8c+8) of row `row` of a row-major matrix with n columns and row stride ld
+__device__ __forceinline__ void store_chunk(void* __restrict__ base, int dt, size_t row, uint32_t c, uint32_t n, uint32_t ld,
+                                            const float (&v)[8], bool vec_ok) {
     if (8 * c >= n) return;
     if (dt == NRF_DTYPE_F16) {
-        __half* p = reinterpret_cast<__half*>(base) + row * n + 8 * c;
+        __half* p = reinterpret_cast<__half*>(base) + row * ld + 8 * c;
         if (vec_ok) { *reinterpret_cast<uint4*>(p) = make_uint4(tpack(v[0], v[1]), tpack(v[2], v[3]), tpack(v[4], v[5]), tpack(v[6], v[7])); return; }
 #pragma unroll
         for (int j = 0; j < 8; j++) if (8 * c + j < n) p[j] = __float2half_rn(v[j]);
         return;
     }
-    float* p = reinterpret_cast<float*>(base) + row * n + 8 * c;
+    float* p = reinterpret_cast<float*>(base) + row * ld + 8 * c;
     if (vec_ok) {
         reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
         reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
@@ -102,21 +104,46 @@ __device__ __forceinline__ void store_chunk(void* __restrict__ base, int dt, siz
 #pragma unroll
     for (int j = 0; j < 8; j++) if (8 * c + j < n) p[j] = v[j];
 }
+// same, but ADDED to what is there with fire-and-forget vector reductions (REDG.ADD.F16x8 / F32x4): lets two networks that
+// share an input accumulate their input gradients into one buffer without a read-modify-write pass
+__device__ __forceinline__ void red_chunk(void* __restrict__ base, int dt, size_t row, uint32_t c, uint32_t n, uint32_t ld,
+                                          const float (&v)[8], bool vec_ok) {
+    if (8 * c >= n) return;
+    if (dt == NRF_DTYPE_F16) {
+        __half* p = reinterpret_cast<__half*>(base) + row * ld + 8 * c;
+        if (vec_ok) {
+            asm volatile("red.global.add.noftz.v4.f16x2 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(tpack(v[0], v[1])), "r"(tpack(v[2], v[3])),
+                         "r"(tpack(v[4], v[5])), "r"(tpack(v[6], v[7])) : "memory");
+            return;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) if (8 * c + j < n) atomicAdd(p + j, __float2half_rn(v[j]));
+        return;
+    }
+    float* p = reinterpret_cast<float*>(base) + row * ld + 8 * c;
+    if (vec_ok) {
+        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) if (8 * c + j < n) atomicAdd(p + j, v[j]);
+}
 
-__device__ __forceinline__ bool vec_ok_for(const void* base, uint32_t n) {
+__device__ __forceinline__ bool vec_ok_for(const void* base, uint32_t n, uint32_t ld) {
     if (!base) return false;
-    return (n % 8 == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+    return (n % 8 == 0) && (ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
 }
 
 // this row's output gradient (<= 16 values), RAW (one register per element, or two uint4 on the vector path): no
 // instruction depends on the loaded data until dy_convert(), so the load can stay in flight for a whole tile
-__device__ __forceinline__ void dy_load_raw(const void* __restrict__ dy, int dy_dt, size_t row, uint32_t n_out, bool row_ok, bool vec_ok,
-                                            uint32_t (&raw)[16]) {
+__device__ __forceinline__ void dy_load_raw(const void* __restrict__ dy, int dy_dt, size_t row, uint32_t n_out, uint32_t ld, bool row_ok,
+                                            bool vec_ok, uint32_t (&raw)[16]) {
 #pragma unroll
     for (int j = 0; j < 16; j++) raw[j] = 0u;
     if (!row_ok) return;
     if (dy_dt == NRF_DTYPE_F16) {
-        const __half* p = reinterpret_cast<const __half*>(dy) + row * n_out;
+        const __half* p = reinterpret_cast<const __half*>(dy) + row * ld;
         if (vec_ok) {                                  // n_out in {8, 16}
             const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
             raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w;
@@ -127,7 +154,7 @@ __device__ __forceinline__ void dy_load_raw(const void* __restrict__ dy, int dy_
         for (int j = 0; j < 16; j++) if ((uint32_t)j < n_out) raw[j] = (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p) + j);
         return;
     }
-    const float* p = reinterpret_cast<const float*>(dy) + row * n_out;
+    const float* p = reinterpret_cast<const float*>(dy) + row * ld;
 #pragma unroll
     for (int j = 0; j < 16; j++) if ((uint32_t)j < n_out) raw[j] = __float_as_uint(__ldg(p + j));
 }
@@ -268,7 +295,7 @@ __host__ __device__ constexpr TcSmem bwd_smem() {
 template <int IN_KT, int NH>
 __global__ void __launch_bounds__(TC_THREADS, 5)
 k_mlp_fwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ params, uint32_t B, uint32_t n_in, uint32_t n_out,
-             int hidden_act, int out_act, void* __restrict__ y, int y_dt) {
+             int hidden_act, int out_act, void* __restrict__ y, int y_dt, uint32_t ld_y) {
     constexpr int IN_PAD = IN_KT * 16;
     constexpr TcSmem L = fwd_smem<IN_KT, NH>();
     constexpr uint32_t TCOLS = 64;
@@ -318,8 +345,11 @@ k_mlp_fwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ pa
         // ================================================================ row owners
         const uint32_t tacc_lane = tacc + ((uint32_t)(warp * 32) << 16);
         const bool relu = hidden_act == NRF_ACT_RELU;
-        const bool x_vec = vec_ok_for(x, n_in);
-        const bool y_vec = vec_ok_for(y, n_out);
+        const bool x_vec = vec_ok_for(x, n_in, n_in);
+        const bool y_vec = vec_ok_for(y, n_out, ld_y);
+        // the network's output precision is f16 (tcnn); an f32 `y` holds that f16 value widened, except for TRUNC_EXP
+        // whose exp is evaluated in f32 on the f16-rounded pre-activation (tcnn_nerf.py:55-62)
+        const bool round_y = y_dt == NRF_DTYPE_F32 && out_act != NRF_ACT_TRUNC_EXP;
         uint32_t phase = 0;
         uint8_t* xrow = smem + L.X + tid * 16;
         uint8_t* hrow = smem + L.H1 + tid * 16;
@@ -358,8 +388,11 @@ k_mlp_fwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ pa
                     if (8u * c < n_out) {
                         float f[8];
 #pragma unroll
-                        for (int j = 0; j < 8; j++) f[j] = tact_fwd(__uint_as_float(z[8 * c + j]), out_act);
-                        store_chunk(y, y_dt, row, c, n_out, f, y_vec);
+                        for (int j = 0; j < 8; j++) {
+                            f[j] = tact_fwd(__uint_as_float(z[8 * c + j]), out_act);
+                            if (round_y) f[j] = __half2float(__float2half_rn(f[j]));
+                        }
+                        store_chunk(y, y_dt, row, c, n_out, ld_y, f, y_vec);
                     }
                 }
             }
@@ -381,8 +414,8 @@ __host__ __device__ constexpr uint32_t bwd_tmem_cols() {
 template <int IN_KT, int NH>
 __global__ void __launch_bounds__(TC_THREADS, (NH == 2 || IN_KT == 4) ? 2 : 4)
 k_mlp_bwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ params, const void* __restrict__ dy, int dy_dt,
-             uint32_t B, uint32_t n_in, uint32_t n_out, int hidden_act, int out_act, float loss_scale, void* __restrict__ dx,
-             float* __restrict__ dparams, unsigned long long* __restrict__ prof) {
+             uint32_t ld_dy, uint32_t B, uint32_t n_in, uint32_t n_out, int hidden_act, int out_act, float loss_scale,
+             void* __restrict__ dx, int dx_accumulate, float* __restrict__ dparams, unsigned long long* __restrict__ prof) {
     constexpr int IN_PAD = IN_KT * 16;
     constexpr TcSmem L = bwd_smem<IN_KT, NH>();
     constexpr uint32_t TCOLS = bwd_tmem_cols<IN_KT, NH>();
@@ -490,9 +523,9 @@ k_mlp_bwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ pa
 #define PROF_MARK(i) do { if (prof && tid == 0) { const long long t_ = clock64(); s_prof[i] += t_ - plast; plast = t_; } } while (0)
         const uint32_t tacc_lane = tacc + ((uint32_t)(warp * 32) << 16);
         const bool relu = hidden_act == NRF_ACT_RELU;
-        const bool x_vec = vec_ok_for(x, n_in);
-        const bool dx_vec = vec_ok_for(dx, n_in);
-        const bool dy_vec = vec_ok_for(dy, n_out);
+        const bool x_vec = vec_ok_for(x, n_in, n_in);
+        const bool dx_vec = vec_ok_for(dx, n_in, n_in);
+        const bool dy_vec = vec_ok_for(dy, n_out, ld_dy);
         const float inv_scale = 1.0f / loss_scale;
         uint32_t phase = 0, phase_w = 0;
         bool first = true;
@@ -512,7 +545,7 @@ k_mlp_bwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ pa
             const size_t row0 = (size_t)blockIdx.x * 128 + tid;
 #pragma unroll
             for (int c = 0; c < IN_PAD / 8; c++) xr[c] = load_chunk(x, x_dt, row0, c, n_in, row0 < B, x_vec);
-            dy_load_raw(dy, dy_dt, row0, n_out, row0 < B, dy_vec, dyraw);
+            dy_load_raw(dy, dy_dt, row0, n_out, ld_dy, row0 < B, dy_vec, dyraw);
         }
         for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const size_t row = (size_t)tile * 128 + tid;
@@ -535,7 +568,7 @@ k_mlp_bwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ pa
                 const bool nok = nt < ntiles && nrow < B;
 #pragma unroll
                 for (int c = 0; c < IN_PAD / 8; c++) xr[c] = load_chunk(x, x_dt, nrow, c, n_in, nok, x_vec);
-                dy_load_raw(dy, dy_dt, nrow, n_out, nok, dy_vec, dyraw);
+                dy_load_raw(dy, dy_dt, nrow, n_out, ld_dy, nok, dy_vec, dyraw);
             }
             PROF_MARK(2);      // operands staged, prefetch issued
             tc05::mbar_wait(&bar_done, phase); phase ^= 1; tc05::fence_after_sync();
@@ -595,7 +628,8 @@ k_mlp_bwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ pa
                             float f[8];
 #pragma unroll
                             for (int j = 0; j < 8; j++) f[j] = __uint_as_float(v[8 * c + j]) * inv_scale;
-                            store_chunk(dx, x_dt, row, 2 * g + c, n_in, f, dx_vec);
+                            if (dx_accumulate) red_chunk(dx, x_dt, row, 2 * g + c, n_in, n_in, f, dx_vec);
+                            else store_chunk(dx, x_dt, row, 2 * g + c, n_in, n_in, f, dx_vec);
                         }
                     }
                 }
@@ -672,20 +706,20 @@ unsigned long long* g_prof = nullptr;
 
 template <int IN_KT, int NH>
 int launch_fwd(const void* x, int xdt, const void* params, uint32_t B, uint32_t n_in, uint32_t n_out, int hact, int oact, void* y, int ydt,
-               cudaStream_t s) {
+               uint32_t ld_y, cudaStream_t s) {
     constexpr TcSmem L = fwd_smem<IN_KT, NH>();
     auto kern = k_mlp_fwd_tc<IN_KT, NH>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
     const uint32_t ntiles = ceil_div_u32(B, 128);
     const uint32_t per_sm = (uint32_t)max(1, min(min(g_fwd_ctas_per_sm, (int)(220 * 1024 / (L.total + 1024))), 8));
     const uint32_t grid = (uint32_t)min((uint64_t)ntiles, (uint64_t)tc_sm_count() * per_sm);
-    kern<<<grid, TC_THREADS, L.total, s>>>(x, xdt, (const __half*)params, B, n_in, n_out, hact, oact, y, ydt);
+    kern<<<grid, TC_THREADS, L.total, s>>>(x, xdt, (const __half*)params, B, n_in, n_out, hact, oact, y, ydt, ld_y);
     return nrf_check_launch();
 }
 
 template <int IN_KT, int NH>
-int launch_bwd(const void* x, int xdt, const void* params, const void* dy, int dydt, uint32_t B, uint32_t n_in, uint32_t n_out, int hact,
-               int oact, float ls, void* dx, float* dparams, cudaStream_t s) {
+int launch_bwd(const void* x, int xdt, const void* params, const void* dy, int dydt, uint32_t ld_dy, uint32_t B, uint32_t n_in, uint32_t n_out,
+               int hact, int oact, float ls, void* dx, int dx_acc, float* dparams, cudaStream_t s) {
     constexpr TcSmem L = bwd_smem<IN_KT, NH>();
     constexpr uint32_t TCOLS = bwd_tmem_cols<IN_KT, NH>();
     auto kern = k_mlp_bwd_tc<IN_KT, NH>;
@@ -693,7 +727,7 @@ int launch_bwd(const void* x, int xdt, const void* params, const void* dy, int d
     const uint32_t ntiles = ceil_div_u32(B, 128);
     const uint32_t per_sm = (uint32_t)max(1, min(min(g_bwd_ctas_per_sm, (int)(220 * 1024 / (L.total + 1024))), (int)(512 / TCOLS)));
     const uint32_t grid = (uint32_t)min((uint64_t)ntiles, (uint64_t)tc_sm_count() * per_sm);
-    kern<<<grid, TC_THREADS, L.total, s>>>(x, xdt, (const __half*)params, dy, dydt, B, n_in, n_out, hact, oact, ls, dx, dparams, g_prof);
+    kern<<<grid, TC_THREADS, L.total, s>>>(x, xdt, (const __half*)params, dy, dydt, ld_dy, B, n_in, n_out, hact, oact, ls, dx, dx_acc, dparams, g_prof);
     return nrf_check_launch();
 }
 
@@ -701,20 +735,20 @@ int launch_bwd(const void* x, int xdt, const void* params, const void* dy, int d
 
 // entry points used by mlp.cu's dispatcher (same argument meaning as nrf_mlp_forward / nrf_mlp_backward)
 int nrf_mlp_tc_forward(const void* x, int x_dtype, const void* params_f16, uint32_t B, uint32_t n_in, uint32_t n_out, uint32_t n_hidden,
-                       int hidden_act, int out_act, void* y, int y_dtype, cudaStream_t s) {
+                       int hidden_act, int out_act, void* y, int y_dtype, uint32_t ld_y, cudaStream_t s) {
     const int kt = (int)((n_in + 15) / 16);
-#define TC_FWD(K, H) if (kt == K && (int)n_hidden == H) return launch_fwd<K, H>(x, x_dtype, params_f16, B, n_in, n_out, hidden_act, out_act, y, y_dtype, s)
+#define TC_FWD(K, H) if (kt == K && (int)n_hidden == H) return launch_fwd<K, H>(x, x_dtype, params_f16, B, n_in, n_out, hidden_act, out_act, y, y_dtype, ld_y, s)
     TC_FWD(1, 1); TC_FWD(2, 1); TC_FWD(3, 1); TC_FWD(4, 1);
     TC_FWD(1, 2); TC_FWD(2, 2); TC_FWD(3, 2); TC_FWD(4, 2);
 #undef TC_FWD
     return NRF_E_UNSUPPORTED;
 }
 
-int nrf_mlp_tc_backward(const void* x, int x_dtype, const void* params_f16, const void* dy, int dy_dtype, uint32_t B, uint32_t n_in,
-                        uint32_t n_out, uint32_t n_hidden, int hidden_act, int out_act, float loss_scale, void* dx, float* dparams,
-                        cudaStream_t s) {
+int nrf_mlp_tc_backward(const void* x, int x_dtype, const void* params_f16, const void* dy, int dy_dtype, uint32_t ld_dy, uint32_t B,
+                        uint32_t n_in, uint32_t n_out, uint32_t n_hidden, int hidden_act, int out_act, float loss_scale, void* dx,
+                        int dx_accumulate, float* dparams, cudaStream_t s) {
     const int kt = (int)((n_in + 15) / 16);
-#define TC_BWD(K, H) if (kt == K && (int)n_hidden == H) return launch_bwd<K, H>(x, x_dtype, params_f16, dy, dy_dtype, B, n_in, n_out, hidden_act, out_act, loss_scale, dx, dparams, s)
+#define TC_BWD(K, H) if (kt == K && (int)n_hidden == H) return launch_bwd<K, H>(x, x_dtype, params_f16, dy, dy_dtype, ld_dy, B, n_in, n_out, hidden_act, out_act, loss_scale, dx, dx_accumulate, dparams, s)
     TC_BWD(1, 1); TC_BWD(2, 1); TC_BWD(3, 1); TC_BWD(4, 1);
     TC_BWD(1, 2); TC_BWD(2, 2); TC_BWD(3, 2); TC_BWD(4, 2);
 #undef TC_BWD

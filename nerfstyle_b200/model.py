@@ -65,8 +65,11 @@ class StyleTCNerf(nn.Module):
     """networks/style_nerf.py:12-159, use_dir=False."""
 
     def __init__(self, bbox_min, bbox_max, class_dim, density_hidden_layers=1, rgb_hidden_layers=2, network_seed=80000,
-                 **enc_kwargs):
+                 fused_heads=True, **enc_kwargs):
         super().__init__()
+        # fused_heads: same math as the reference's op-by-op glue below, with trunc_exp / cat / casts folded into the
+        # MLP kernels (tcnn.density_head / tcnn.color_heads); False runs the reference's exact op sequence
+        self.fused_heads = fused_heads
         self.register_buffer('bbox_min', torch.as_tensor(bbox_min, dtype=torch.float32))
         self.register_buffer('bbox_size', torch.as_tensor(bbox_max, dtype=torch.float32) - self.bbox_min)
         self.class_dim = class_dim
@@ -87,6 +90,12 @@ class StyleTCNerf(nn.Module):
     def _forward(self, pts, dirs=None):
         pts = (pts - self.bbox_min) / self.bbox_size            # BBox.normalize, common.py:288
         x_embedded = self.x_density_embedder(pts)
+        if self.fused_heads and x_embedded.is_cuda:
+            sigmas = tcnn.density_head(x_embedded, self.density_net)
+            if dirs is None:
+                return sigmas
+            rgbs = tcnn.color_heads(self.x_color_embedder(pts), self.class_net, self.color1_net, self.color2_net)
+            return rgbs, sigmas
         density_output = self.density_net(x_embedded)
         sigmas = trunc_exp(density_output)
         if dirs is None:

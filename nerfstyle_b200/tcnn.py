@@ -71,6 +71,112 @@ class _mlp_function(Function):
         return dx, dparams, None
 
 
+def _fwd_ex(net, x, params_h, y, col, n_out, out_act):
+    """y[:, col:col+n_out] = net(x) through the extended C entry point (y may be wider than n_out; f16 or f32)."""
+    L.check(L.lib().nrf_mlp_forward_ex(L.ptr(x), L.dtype_code(x.dtype), L.ptr(params_h), x.shape[0], net.n_input_dims, n_out,
+                                       net.n_hidden_layers, net.n_neurons, net.hidden_act, out_act,
+                                       y.data_ptr() + col * y.element_size(), L.dtype_code(y.dtype), y.shape[1],
+                                       L.stream_of(x)), 'mlp_forward_ex')
+
+
+def _bwd_ex(net, x, params_h, dy, col, n_out, out_act, dx, dx_accumulate, dparams):
+    L.check(L.lib().nrf_mlp_backward_ex(L.ptr(x), L.dtype_code(x.dtype), L.ptr(params_h),
+                                        dy.data_ptr() + col * dy.element_size(), L.dtype_code(dy.dtype), dy.shape[1],
+                                        x.shape[0], net.n_input_dims, n_out, net.n_hidden_layers, net.n_neurons,
+                                        net.hidden_act, out_act, float(net.loss_scale), L.ptr(dx), L.dtype_code(x.dtype),
+                                        int(dx_accumulate), L.ptr(dparams), L.stream_of(x)), 'mlp_backward_ex')
+
+
+class _density_head(Function):
+    """sigma = trunc_exp(density_net(enc)) as ONE kernel per direction: the exp (tcnn_nerf.py:55-69) is the output
+    activation of the fused MLP (NRF_ACT_TRUNC_EXP), f32 out; replaces the f16->f32 cast + exp (+ 4 backward kernels)."""
+
+    @staticmethod
+    def forward(ctx, enc, params, net):
+        L.require_cuda(enc, params)
+        enc = enc.contiguous()
+        params_h = params.detach().to(torch.float16).contiguous()
+        y = torch.empty(enc.shape[0], 1, dtype=torch.float32, device=enc.device)
+        with torch.cuda.device(enc.device):
+            _fwd_ex(net, enc, params_h, y, 0, 1, L.ACT['trunc_exp'])
+        ctx.save_for_backward(enc, params_h)
+        ctx.net = net
+        ctx.need = (ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        enc, params_h = ctx.saved_tensors
+        net = ctx.net
+        g = g.contiguous()
+        if g.dtype not in (torch.float16, torch.float32):
+            g = g.float()
+        dx = torch.empty_like(enc) if ctx.need[0] else None
+        dp = torch.zeros(params_h.shape, dtype=torch.float32, device=enc.device) if ctx.need[1] else None
+        with torch.cuda.device(enc.device):
+            _bwd_ex(net, enc, params_h, g, 0, 1, L.ACT['trunc_exp'], dx, False, dp)
+        return dx, dp, None
+
+
+class _color_heads(Function):
+    """rgbs = cat(color2_net(color1_net(enc)), class_net(enc)) (style_nerf.py:136-141) without the cat, the f16->f32 cast
+    of the compositing input and the slice / cast copies of its backward: the two output networks write column blocks
+    of one f32 [B, 3+K] matrix, the backward reads column blocks of its gradient, and class_net ADDS its input gradient
+    into color1_net's (REDG vector reductions) instead of a separate add over [B, 32]."""
+
+    @staticmethod
+    def forward(ctx, enc, p_class, p_c1, p_c2, class_net, color1_net, color2_net):
+        L.require_cuda(enc, p_class, p_c1, p_c2)
+        enc = enc.contiguous()
+        B = enc.shape[0]
+        K = class_net.n_output_dims
+        hp = [p.detach().to(torch.float16).contiguous() for p in (p_class, p_c1, p_c2)]
+        c1 = torch.empty(B, color1_net.n_output_dims, dtype=torch.float16, device=enc.device)
+        rgbs = torch.empty(B, 3 + K, dtype=torch.float32, device=enc.device)
+        with torch.cuda.device(enc.device):
+            _fwd_ex(color1_net, enc, hp[1], c1, 0, color1_net.n_output_dims, color1_net.out_act)
+            _fwd_ex(color2_net, c1, hp[2], rgbs, 0, 3, color2_net.out_act)
+            _fwd_ex(class_net, enc, hp[0], rgbs, 3, K, class_net.out_act)
+        ctx.save_for_backward(enc, c1, *hp)
+        ctx.nets = (class_net, color1_net, color2_net)
+        ctx.need = ctx.needs_input_grad[:4]
+        return rgbs
+
+    @staticmethod
+    def backward(ctx, g):
+        enc, c1, h_class, h_c1, h_c2 = ctx.saved_tensors
+        class_net, color1_net, color2_net = ctx.nets
+        K = class_net.n_output_dims
+        g = g.contiguous()
+        if g.dtype not in (torch.float16, torch.float32):
+            g = g.float()
+        dev = enc.device
+        z = lambda h, need: torch.zeros(h.shape, dtype=torch.float32, device=dev) if need else None
+        dp_class, dp_c1, dp_c2 = z(h_class, ctx.need[1]), z(h_c1, ctx.need[2]), z(h_c2, ctx.need[3])
+        need_dx = ctx.need[0]
+        dc1 = torch.empty_like(c1) if (need_dx or ctx.need[2]) else None
+        dx = torch.empty_like(enc) if need_dx else None
+        with torch.cuda.device(dev):
+            if dc1 is not None or dp_c2 is not None:
+                _bwd_ex(color2_net, c1, h_c2, g, 0, 3, color2_net.out_act, dc1, False, dp_c2)
+            if dc1 is not None:
+                _bwd_ex(color1_net, enc, h_c1, dc1, 0, color1_net.n_output_dims, color1_net.out_act, dx, False, dp_c1)
+            if dx is not None or dp_class is not None:
+                _bwd_ex(class_net, enc, h_class, g, 3, K, class_net.out_act, dx, dx is not None, dp_class)
+        return dx, dp_class, dp_c1, dp_c2, None, None, None
+
+
+def density_head(enc, net):
+    """trunc_exp(net(enc)) fused (f32 [B, 1])."""
+    return _density_head.apply(enc.reshape(-1, net.n_input_dims), net.params, net)
+
+
+def color_heads(enc, class_net, color1_net, color2_net):
+    """cat(color2_net(color1_net(enc)), class_net(enc)) fused (f32 [B, 3 + K])."""
+    return _color_heads.apply(enc.reshape(-1, class_net.n_input_dims), class_net.params, color1_net.params, color2_net.params,
+                              class_net, color1_net, color2_net)
+
+
 class Network(nn.Module):
     """tcnn.Network look-alike (FullyFusedMLP / CutlassMLP otypes map to the same fused kernel)."""
 

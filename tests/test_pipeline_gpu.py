@@ -9,11 +9,11 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _build(dev, half_tables, n_rays=4096, table_std=0.5):
+def _build(dev, half_tables, n_rays=4096, table_std=0.5, fused_heads=True):
     from nerfstyle_b200 import model as M, raymarching, scenes
     from oracle import field
     of = field.OracleField(bound=2.0, n_classes=8, half=half_tables, seed=0, table_std=table_std)
-    m = M.StyleTCNerf([-2., -2., -2.], [2., 2., 2.], class_dim=8).to(dev)
+    m = M.StyleTCNerf([-2., -2., -2.], [2., 2., 2.], class_dim=8, fused_heads=fused_heads).to(dev)
     with torch.no_grad():
         for n, p in m.named_parameters():
             p.copy_(of.params[n].detach().to(dev))
@@ -26,10 +26,13 @@ def _build(dev, half_tables, n_rays=4096, table_std=0.5):
     return of, m, r, o, d, bits
 
 
+@pytest.mark.parametrize('fused_heads', [True, False])
 @pytest.mark.parametrize('amp', [False, True])
-def test_train_step_matches_oracle(cuda_lib, oracle, dev, amp):
+def test_train_step_matches_oracle(cuda_lib, oracle, dev, amp, fused_heads):
+    """fused_heads=False is the reference's exact op sequence on the drop-in modules; True folds trunc_exp / cat / casts
+    into the MLP kernels (tcnn.density_head / color_heads).  Both must match the oracle pipeline."""
     from oracle import field
-    of, m, r, o, d, bits = _build(dev, half_tables=amp)
+    of, m, r, o, d, bits = _build(dev, half_tables=amp, fused_heads=fused_heads)
     g = torch.Generator().manual_seed(9)
     target = torch.rand(o.shape[0], 3, generator=g)
     tcls = torch.randint(0, 8, (o.shape[0],), generator=g)
@@ -61,6 +64,25 @@ def test_train_step_matches_oracle(cuda_lib, oracle, dev, amp):
         assert denom > 0, name
         tol = 2e-2
         assert np.abs(gp - eg).max() <= tol * denom, (name, np.abs(gp - eg).max() / denom)
+
+
+@pytest.mark.parametrize('amp', [False, True])
+def test_fused_heads_equal_reference_op_sequence(cuda_lib, dev, amp):
+    """The fused heads reproduce the unfused op sequence: same values (the f16 rounding points are kept), gradients
+    within the f16 rounding of dy (the fused path does not round the compositing gradient to f16 first)."""
+    outs = []
+    for fused in (True, False):
+        of, m, r, o, d, bits = _build(dev, half_tables=amp, n_rays=1024, fused_heads=fused)
+        with torch.autocast('cuda', dtype=torch.float16, enabled=amp):
+            image, depth, classes = r.render_train(o, d)
+            loss = torch.mean(image ** 2) + 0.01 * torch.mean(classes ** 2)
+        (loss * 65536.0).backward()
+        outs.append((image.detach(), classes.detach(), {n: p.grad.clone() for n, p in m.named_parameters()}))
+    torch.testing.assert_close(outs[0][0], outs[1][0], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-6)
+    for n in outs[0][2]:
+        a, b = outs[0][2][n].float(), outs[1][2][n].float()
+        assert float((a - b).abs().max()) <= 1e-2 * float(b.abs().max()), n
 
 
 def test_render_test_matches_render_train(cuda_lib, dev):
