@@ -211,7 +211,7 @@ int nrf_mlp_backward_ex(const void* x, int x_dtype, const void* params_f16, cons
 int nrf_nnfm_forward(const void* a_f16, const void* b_f16, uint32_t N1, uint32_t N2, uint32_t K,
                      const int32_t* a_label, const int32_t* b_label, const int32_t* match, uint32_t n_class,
                      float* min_dist, int32_t* argmin, void* scratch, void* stream);
-uint64_t nrf_nnfm_scratch_bytes(uint32_t N1, uint32_t N2);
+uint64_t nrf_nnfm_scratch_bytes(uint32_t N1, uint32_t N2, uint32_t K);   /* scratch: 256-byte aligned */
 
 /* ------------------------------------------------------------------ fused optimizer (SURVEY 8f NEXT-3) */
 

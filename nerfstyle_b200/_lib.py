@@ -53,7 +53,7 @@ SIGNATURES = {
     'nrf_mlp_backward_ex': (_i32, [_vp, _i32, _vp, _vp, _i32, _u32, _u32, _u32, _u32, _u32, _u32, _i32, _i32, _f32, _vp, _i32,
                                    _i32, _vp, _vp]),
     'nrf_nnfm_forward': (_i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
-    'nrf_nnfm_scratch_bytes': (_u64, [_u32, _u32]),
+    'nrf_nnfm_scratch_bytes': (_u64, [_u32, _u32, _u32]),
     'nrf_opt_state_bytes': (_u64, []),
     'nrf_grads_check': (_i32, [_vp, _u64, _vp, _vp]),
     'nrf_adam_step': (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _u64, _vp, _f32, _f32, _f32, _f32, _f32, _f32, _vp]),
@@ -64,6 +64,7 @@ EXTRA_SIGNATURES = {
     'nrf_grid_set_tuning': (None, [_i32, _i32, _i32]),
     'nrf_march_set_mode': (None, [_i32]),
     'nrf_mlp_set_mode': (None, [_i32]),
+    'nrf_nnfm_set_mode': (None, [_i32]),
     'nrf_mlp_set_tuning': (None, [_i32, _i32]),
     'nrf_mlp_set_profile': (None, [_vp]),
 }
@@ -79,7 +80,7 @@ KERNELS_PER_CALL = {
     'nrf_march_rays_train_count': 4, 'nrf_march_rays_train_write': 1, 'nrf_march_rays_train': 4,
     'nrf_composite_rays_train_forward': 1, 'nrf_composite_rays_train_backward': 1, 'nrf_march_rays': 1,
     'nrf_composite_rays': 1, 'nrf_compact_alive': 3, 'nrf_grid_encode_forward': 1, 'nrf_grid_encode_backward': 1,
-    'nrf_grid_initialize': 1, 'nrf_mlp_forward': 1, 'nrf_mlp_backward': 1, 'nrf_mlp_forward_ex': 1, 'nrf_mlp_backward_ex': 1, 'nrf_nnfm_forward': 3,
+    'nrf_grid_initialize': 1, 'nrf_mlp_forward': 1, 'nrf_mlp_backward': 1, 'nrf_mlp_forward_ex': 1, 'nrf_mlp_backward_ex': 1, 'nrf_nnfm_forward': 5,
     'nrf_adam_step': 1, 'nrf_grads_check': 1, 'nrf_scaler_update': 1,
 }
 

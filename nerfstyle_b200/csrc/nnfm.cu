@@ -171,9 +171,18 @@ __global__ void k_nnfm_finish(const unsigned long long* __restrict__ best, uint3
     if (argmin) argmin[i] = (int32_t)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
 }
 
-NRF_EXPORT uint64_t nrf_nnfm_scratch_bytes(uint32_t N1, uint32_t N2) {
-    (void)N2;
-    return (uint64_t)N1 * (sizeof(unsigned long long) + sizeof(int32_t)) + 64;
+// nnfm_tc.cu: the tcgen05 / TMEM implementation (default); the mma.sync kernel above is the selectable second one
+uint64_t nrf_nnfm_tc_pack_bytes(uint32_t N1, uint32_t N2, uint32_t K);
+int nrf_nnfm_tc_gemm(const __half* a, const __half* b, uint32_t N1, uint32_t N2, uint32_t K, const int32_t* row_req,
+                     const int32_t* b_label, unsigned long long* best, void* packed, cudaStream_t s);
+static int g_nnfm_mode = 0;     // 0 = tcgen05 (nnfm_tc.cu), 1 = mma.sync
+NRF_EXPORT void nrf_nnfm_set_mode(int mode) { g_nnfm_mode = mode; }
+
+static uint64_t nnfm_small_bytes(uint32_t N1) {
+    return (((uint64_t)N1 * (sizeof(unsigned long long) + sizeof(int32_t)) + 64) + 255) & ~255ull;
+}
+NRF_EXPORT uint64_t nrf_nnfm_scratch_bytes(uint32_t N1, uint32_t N2, uint32_t K) {
+    return nnfm_small_bytes(N1) + nrf_nnfm_tc_pack_bytes(N1, N2, K);
 }
 
 NRF_EXPORT int nrf_nnfm_forward(const void* a_f16, const void* b_f16, uint32_t N1, uint32_t N2, uint32_t K,
@@ -188,6 +197,14 @@ NRF_EXPORT int nrf_nnfm_forward(const void* a_f16, const void* b_f16, uint32_t N
     unsigned long long* best = (unsigned long long*)scratch;
     int32_t* row_req = (int32_t*)(best + N1);
     k_nnfm_prepare<<<ceil_div_u32(N1, 256), 256, 0, s>>>(a_label, match, n_class, N1, row_req, best);
+    if (g_nnfm_mode == 0) {
+        void* packed = (void*)((((uintptr_t)scratch + nnfm_small_bytes(N1)) + 127) & ~(uintptr_t)127);
+        const int rc = nrf_nnfm_tc_gemm((const __half*)a_f16, (const __half*)b_f16, N1, N2, K, row_req, match ? b_label : nullptr, best,
+                                        packed, s);
+        if (rc != NRF_OK) return rc;
+        k_nnfm_finish<<<ceil_div_u32(N1, 256), 256, 0, s>>>(best, N1, min_dist, argmin);
+        return nrf_check_launch();
+    }
     const uint32_t m_tiles = ceil_div_u32(N1, NN_BM), n_tiles = ceil_div_u32(N2, NN_BN);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

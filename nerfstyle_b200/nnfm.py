@@ -26,7 +26,7 @@ def nn_match(a_hat, b_hat, a_label=None, b_label=None, match=None):
     min_dist = torch.empty(N1, dtype=torch.float32, device=dev)
     argmin = torch.empty(N1, dtype=torch.int32, device=dev)
     lib = L.lib()
-    scratch = torch.empty(int(lib.nrf_nnfm_scratch_bytes(N1, N2)), dtype=torch.uint8, device=dev)
+    scratch = torch.empty(int(lib.nrf_nnfm_scratch_bytes(N1, N2, K)), dtype=torch.uint8, device=dev)
     n_class = 0
     if match is not None:
         a_label = a_label.to(device=dev, dtype=torch.int32).contiguous()

@@ -6,6 +6,16 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=['tcgen05', 'mma_sync'], autouse=True)
+def nnfm_impl(request, cuda_lib):
+    """Every test runs on both implementations behind nrf_nnfm_forward: tcgen05 + TMEM + bulk copies (nnfm_tc.cu, the
+    default) and mma.sync (nnfm.cu)."""
+    from nerfstyle_b200 import _lib
+    _lib.lib().nrf_nnfm_set_mode(0 if request.param == 'tcgen05' else 1)
+    yield request.param
+    _lib.lib().nrf_nnfm_set_mode(0)
+
+
 @pytest.mark.parametrize('N1,N2,K,masked', [(1000, 1300, 768, True), (257, 129, 64, False), (1, 5, 8, True), (640, 2048, 256, True)])
 def test_nn_match(cuda_lib, dev, N1, N2, K, masked):
     from nerfstyle_b200 import nnfm
@@ -60,3 +70,29 @@ def test_semantic_loss_value_and_grad(cuda_lib, dev):
     # gradients agree wherever the fp16 arg-min equals the fp32 arg-min (all but near-ties)
     diff = (img.grad - img2.grad).reshape(C, -1).abs().amax(dim=0)
     assert float((diff < 1e-6).float().mean()) > 0.97
+
+
+def test_full_size_implementations_agree(cuda_lib, dev):
+    """BASELINE config 4 size (N1 = 11 844, N2 = 15 876, K = 768): the two implementations pick the same minima."""
+    from nerfstyle_b200 import nnfm, _lib
+    g = torch.Generator().manual_seed(4)
+    N1, N2, K = 11844, 15876, 768
+    a = torch.randn(N1, K, generator=g).to(dev)
+    b = torch.randn(N2, K, generator=g).to(dev)
+    a_hat = a / a.norm(dim=1, keepdim=True)
+    b_hat = b / b.norm(dim=1, keepdim=True)
+    preds = torch.randint(0, 8, (N1,), generator=g).to(dev)
+    clusters = torch.randint(0, 8, (N2,), generator=g).to(dev)
+    match = list(range(8))
+    res = []
+    for mode in (0, 1):
+        _lib.lib().nrf_nnfm_set_mode(mode)
+        res.append(nnfm.nn_match(a_hat, b_hat, preds, clusters, match))
+    _lib.lib().nrf_nnfm_set_mode(0)
+    torch.testing.assert_close(res[0][0], res[1][0], rtol=0, atol=1e-4)
+    assert float((res[0][1] == res[1][1]).float().mean()) > 0.999
+    # and against a dense fp32 evaluation of a row sample
+    idx = torch.arange(0, N1, 97, device=dev)
+    d = 1.0 - a_hat[idx].half().float() @ b_hat.half().float().T
+    d[preds[idx][:, None] != clusters[None, :]] = float('inf')
+    torch.testing.assert_close(res[0][0][idx], d.min(dim=1).values, rtol=0, atol=2e-4)

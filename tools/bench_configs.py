@@ -89,14 +89,23 @@ def nnfm_bench(args):
     clusters = (torch.arange(N2) * 8 // N2).to(dev)
     match = list(range(8))
 
+    from nerfstyle_b200 import _lib
+
     def ours():
+        _lib.lib().nrf_nnfm_set_mode(0)
         return nnfm.nn_match(a_hat, b_hat, preds, clusters, match)
+
+    def ours_mma_sync():
+        _lib.lib().nrf_nnfm_set_mode(1)
+        out = nnfm.nn_match(a_hat, b_hat, preds, clusters, match)
+        _lib.lib().nrf_nnfm_set_mode(0)
+        return out
 
     def ref():
         with torch.autocast('cuda', dtype=torch.float16):
             return om.semantic_nn_loss(a, b, preds, clusters, match, 8)
     res = {}
-    for name, fn in (('ours', ours), ('torch_composition', ref)):
+    for name, fn in (('ours', ours), ('ours_mma_sync', ours_mma_sync), ('torch_composition', ref)):
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
