@@ -159,6 +159,9 @@ def build_trainer(device, amp, world):
 ALGO_BYTES = {   # SURVEY.md 8d, per point per encoder (fp32 tables / fp16 tables), per sample for compositing
     'nrf_grid_encode_forward': {False: 12 + 16 * 8 * 2 * 4 + 16 * 2 * 4, True: 12 + 16 * 8 * 2 * 2 + 16 * 2 * 2},
     'nrf_grid_encode_backward': {False: 12 + 128 + 2 * 1024, True: 12 + 64 + 2 * 512},
+    # one pass over the points for TWO encoders: the xyz read is shared
+    'nrf_grid_encode_forward_dual': {False: 12 + 2 * (16 * 8 * 2 * 4 + 16 * 2 * 4), True: 12 + 2 * (16 * 8 * 2 * 2 + 16 * 2 * 2)},
+    'nrf_grid_encode_backward_dual': {False: 12 + 2 * (128 + 2 * 1024), True: 12 + 2 * (64 + 2 * 512)},
 }
 
 
@@ -196,11 +199,13 @@ def run_ours(args):
         ts.step(*unpack(devb[s]))
     # live CUDA-event timing inside the timed region: only the roofline candidates (4 calls per step); the full per-op
     # breakdown (`kernels`) is taken in a separate instrumented pass afterwards so that it does not perturb `value`
-    all_ops = ['nrf_grid_encode_forward', 'nrf_grid_encode_backward', 'nrf_mlp_forward', 'nrf_mlp_backward',
+    all_ops = ['nrf_grid_encode_forward', 'nrf_grid_encode_backward', 'nrf_grid_encode_forward_dual',
+               'nrf_grid_encode_backward_dual', 'nrf_mlp_forward', 'nrf_mlp_backward',
                'nrf_mlp_forward_ex', 'nrf_mlp_backward_ex',
                'nrf_composite_rays_train_forward', 'nrf_composite_rays_train_backward', 'nrf_march_rays_train_count',
                'nrf_march_rays_train_write']
-    timed_ops = ['nrf_grid_encode_forward', 'nrf_grid_encode_backward']
+    timed_ops = ['nrf_grid_encode_forward', 'nrf_grid_encode_backward', 'nrf_grid_encode_forward_dual',
+                 'nrf_grid_encode_backward_dual']
     barrier()
     clocks = ClockSampler(local)
     clocks.start()

@@ -105,11 +105,14 @@ __device__ __forceinline__ void corner_weights_d3(float fx, float fy, float fz, 
 __device__ __forceinline__ uint32_t h2u(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 __device__ __forceinline__ uint32_t h2u(float2) { return 0u; }
 
-template <typename T, int LPT>
+// NE = 2: two encoders with IDENTICAL geometry (offsets, scale, resolution) evaluated in one pass -- positions, hash rows
+// and trilinear weights are computed once and reused for both tables (the model's x_density_embedder / x_color_embedder,
+// networks/style_nerf.py:29-30, are such a pair).
+template <typename T, int LPT, int NE>
 __global__ void __launch_bounds__(GRID_BLOCK)
-k_grid_fwd_d3c2(const float* __restrict__ inputs, const T* __restrict__ table, const int32_t* __restrict__ offsets,
-                T* __restrict__ outputs, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align_corners,
-                uint32_t style, bool point_major) {
+k_grid_fwd_d3c2(const float* __restrict__ inputs, const T* __restrict__ table0, const T* __restrict__ table1,
+                const int32_t* __restrict__ offsets, T* __restrict__ outputs0, T* __restrict__ outputs1, uint32_t B, uint32_t L,
+                float S, uint32_t H, uint32_t gridtype, bool align_corners, uint32_t style, bool point_major) {
     typedef typename Vec2<T>::type V2;
     __shared__ LevelP lp[LPT];
     const uint32_t l0 = blockIdx.y * LPT;
@@ -119,10 +122,13 @@ k_grid_fwd_d3c2(const float* __restrict__ inputs, const T* __restrict__ table, c
     if (b >= B) return;
     const float x = __ldg(inputs + 3 * (size_t)b), y = __ldg(inputs + 3 * (size_t)b + 1), z = __ldg(inputs + 3 * (size_t)b + 2);
     const bool oob = (x < 0 || x > 1) || (y < 0 || y > 1) || (z < 0 || z > 1);   // gridencoder.cu:107-114
-    V2 res[LPT];
+    V2 res[NE][LPT];
 #pragma unroll
     for (int j = 0; j < LPT; j++) {
-        if constexpr (sizeof(T) == 4) res[j] = make_float2(0.0f, 0.0f); else res[j] = __floats2half2_rn(0.0f, 0.0f);
+#pragma unroll
+        for (int e = 0; e < NE; e++) {
+            if constexpr (sizeof(T) == 4) res[e][j] = make_float2(0.0f, 0.0f); else res[e][j] = __floats2half2_rn(0.0f, 0.0f);
+        }
         if (l0 + j >= L || oob) continue;
         const LevelP& p = lp[j];
         uint32_t cx, cy, cz; float fx, fy, fz;
@@ -132,47 +138,54 @@ k_grid_fwd_d3c2(const float* __restrict__ inputs, const T* __restrict__ table, c
         uint32_t rows[8]; float w[8];
         corner_rows_d3(p, cx, cy, cz, rows);
         corner_weights_d3(fx, fy, fz, w);
-        const V2* tl = reinterpret_cast<const V2*>(table) + p.offset;
-        V2 v[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = __ldg(tl + rows[k]);
-        if constexpr (sizeof(T) == 4) {
-            float r0 = 0.0f, r1 = 0.0f;   // gridencoder.cu:177 compiles to fma.rn
+        for (int e = 0; e < NE; e++) {
+            const V2* tl = reinterpret_cast<const V2*>(e == 0 ? table0 : table1) + p.offset;
+            V2 v[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) { r0 = __fmaf_rn(w[k], v[k].x, r0); r1 = __fmaf_rn(w[k], v[k].y, r1); }
-            res[j] = make_float2(r0, r1);
-        } else {
-            // scalar_t = at::Half: the product is rounded to half, then the half sum is rounded to half
-            __half2 acc = __floats2half2_rn(0.0f, 0.0f);
+            for (int k = 0; k < 8; k++) v[k] = __ldg(tl + rows[k]);
+            if constexpr (sizeof(T) == 4) {
+                float r0 = 0.0f, r1 = 0.0f;   // gridencoder.cu:177 compiles to fma.rn
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const float2 g = __half22float2(v[k]);
-                acc = __hadd2(acc, __floats2half2_rn(__fmul_rn(w[k], g.x), __fmul_rn(w[k], g.y)));
+                for (int k = 0; k < 8; k++) { r0 = __fmaf_rn(w[k], v[k].x, r0); r1 = __fmaf_rn(w[k], v[k].y, r1); }
+                res[e][j] = make_float2(r0, r1);
+            } else {
+                // scalar_t = at::Half: the product is rounded to half, then the half sum is rounded to half
+                __half2 acc = __floats2half2_rn(0.0f, 0.0f);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const float2 g = __half22float2(v[k]);
+                    acc = __hadd2(acc, __floats2half2_rn(__fmul_rn(w[k], g.x), __fmul_rn(w[k], g.y)));
+                }
+                res[e][j] = acc;
             }
-            res[j] = acc;
         }
     }
-    if (point_major) {
-        V2* o = reinterpret_cast<V2*>(outputs) + (size_t)b * L + l0;
-        constexpr int PER16 = 16 / (int)sizeof(V2);
-        if (LPT % PER16 == 0 && (L % PER16) == 0 && l0 + LPT <= L && ((uintptr_t)outputs & 15) == 0) {
 #pragma unroll
-            for (int j = 0; j < LPT; j += PER16) {
-                uint4 u;
-                if constexpr (sizeof(T) == 4) {
-                    u = make_uint4(__float_as_uint(res[j].x), __float_as_uint(res[j].y), __float_as_uint(res[(j + 1) % LPT].x), __float_as_uint(res[(j + 1) % LPT].y));
-                } else {
-                    u = make_uint4(h2u(res[j]), h2u(res[(j + 1) % LPT]), h2u(res[(j + 2) % LPT]), h2u(res[(j + 3) % LPT]));
+    for (int e = 0; e < NE; e++) {
+        T* outputs = e == 0 ? outputs0 : outputs1;
+        if (point_major) {
+            V2* o = reinterpret_cast<V2*>(outputs) + (size_t)b * L + l0;
+            constexpr int PER16 = 16 / (int)sizeof(V2);
+            if (LPT % PER16 == 0 && (L % PER16) == 0 && l0 + LPT <= L && ((uintptr_t)outputs & 15) == 0) {
+#pragma unroll
+                for (int j = 0; j < LPT; j += PER16) {
+                    uint4 u;
+                    if constexpr (sizeof(T) == 4) {
+                        u = make_uint4(__float_as_uint(res[e][j].x), __float_as_uint(res[e][j].y), __float_as_uint(res[e][(j + 1) % LPT].x), __float_as_uint(res[e][(j + 1) % LPT].y));
+                    } else {
+                        u = make_uint4(h2u(res[e][j]), h2u(res[e][(j + 1) % LPT]), h2u(res[e][(j + 2) % LPT]), h2u(res[e][(j + 3) % LPT]));
+                    }
+                    *reinterpret_cast<uint4*>(o + j) = u;
                 }
-                *reinterpret_cast<uint4*>(o + j) = u;
+            } else {
+#pragma unroll
+                for (int j = 0; j < LPT; j++) if (l0 + j < L) o[j] = res[e][j];
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < LPT; j++) if (l0 + j < L) o[j] = res[j];
+            for (int j = 0; j < LPT; j++) if (l0 + j < L) reinterpret_cast<V2*>(outputs)[(size_t)(l0 + j) * B + b] = res[e][j];
         }
-    } else {
-#pragma unroll
-        for (int j = 0; j < LPT; j++) if (l0 + j < L) reinterpret_cast<V2*>(outputs)[(size_t)(l0 + j) * B + b] = res[j];
     }
 }
 
@@ -288,6 +301,7 @@ k_grid_fwd_generic(const float* __restrict__ inputs, const T* __restrict__ table
 static int g_fwd_lpt = 16;   // levels per thread of the fast path (tunable: nrf_grid_set_tuning)
 static int g_bwd_lpt = 16;
 static int g_bwd_agg = 1;    // warp aggregation of the scatter on (1) / off (0)
+
 NRF_EXPORT void nrf_grid_set_tuning(int fwd_lpt, int bwd_lpt, int bwd_agg) {
     if (fwd_lpt > 0) g_fwd_lpt = fwd_lpt;
     if (bwd_lpt > 0) g_bwd_lpt = bwd_lpt;
@@ -302,7 +316,7 @@ static int launch_fwd(const float* inputs, const void* embeddings, const int32_t
     const uint32_t nbx = ceil_div_u32(B, GRID_BLOCK);
     if (D == 3 && C == 2 && !calc && (((uintptr_t)embeddings) & 7) == 0) {
         const int lpt = g_fwd_lpt;
-#define FWD_FAST(LPT) k_grid_fwd_d3c2<T, LPT><<<dim3(nbx, ceil_div_u32(L, LPT)), GRID_BLOCK, 0, s>>>(inputs, tab, offsets, out, B, L, S, H, gridtype, ac, style, pm)
+#define FWD_FAST(LPT) k_grid_fwd_d3c2<T, LPT, 1><<<dim3(nbx, ceil_div_u32(L, LPT)), GRID_BLOCK, 0, s>>>(inputs, tab, nullptr, offsets, out, nullptr, B, L, S, H, gridtype, ac, style, pm)
         if (lpt >= 16) FWD_FAST(16); else if (lpt >= 8) FWD_FAST(8); else if (lpt >= 4) FWD_FAST(4); else if (lpt >= 2) FWD_FAST(2); else FWD_FAST(1);
 #undef FWD_FAST
         return nrf_check_launch();
@@ -342,16 +356,27 @@ __device__ __forceinline__ void atomic_add2(__half* base, uint32_t row, float a,
     atomicAdd(reinterpret_cast<__half2*>(base) + row, __floats2half2_rn(a, b));
 }
 
-template <typename T, typename TO, int LPT>
-__global__ void __launch_bounds__(GRID_BLOCK)
-k_grid_bwd_d3c2(const T* __restrict__ grad, const float* __restrict__ inputs, const int32_t* __restrict__ offsets,
-                TO* __restrict__ grad_table, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align_corners,
-                uint32_t style, bool point_major, int agg_max_groups) {
+// scatter the 8 corner contributions (v0[k], v1[k]) of one cell: one 8-byte vector reduction per corner.
+// (Measured and rejected: pairing the x / x+1 corners of an even cell on power-of-two hashed levels into one 16-byte
+//  REDG.ADD.F32x4 -- the rows differ only in bit 0 -- is 10 % SLOWER on B200: a 16-byte reduction costs two 8-byte ones.)
+template <typename TO>
+__device__ __forceinline__ void scatter_cell(TO* gl, const uint32_t (&rows)[8], const float (&v0)[8], const float (&v1)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) atomic_add2(gl, rows[k], v0[k], v1[k]);
+}
+
+// NE = 2: the gradients of two encoders with identical geometry are scattered in one pass (cells, hash rows, weights
+// and the warp-aggregation bookkeeping are computed once).
+template <typename T, typename TO, int LPT, int NE>
+__global__ void __launch_bounds__(GRID_BLOCK, NE == 1 ? 1 : 4)
+k_grid_bwd_d3c2(const T* __restrict__ grad0, const T* __restrict__ grad1, const float* __restrict__ inputs,
+                const int32_t* __restrict__ offsets, TO* __restrict__ grad_table0, TO* __restrict__ grad_table1, uint32_t B, uint32_t L,
+                float S, uint32_t H, uint32_t gridtype, bool align_corners, uint32_t style, bool point_major, int agg_max_groups) {
     typedef typename Vec2<T>::type V2;
     constexpr int WPL = (int)sizeof(V2) / 4;           // 32-bit words per level of one point's gradient
     constexpr int ROW = LPT * WPL + 1;                 // padded smem row (conflict-free column reads)
     __shared__ LevelP lp[LPT];
-    __shared__ uint32_t sg[GRID_BLOCK * ROW];          // this block's gradients, [point][level] (16.3 / 32.3 KB at LPT=16)
+    __shared__ uint32_t sg[NE][GRID_BLOCK * ROW];      // this block's gradients, [point][level] (16.3 / 32.3 KB per encoder at LPT=16)
     const uint32_t l0 = blockIdx.y * LPT;
     if (threadIdx.x < LPT && l0 + threadIdx.x < L) level_setup(lp[threadIdx.x], offsets, l0 + threadIdx.x, 3, S, H, gridtype, align_corners, style);
     const uint32_t b0 = blockIdx.x * GRID_BLOCK;
@@ -359,33 +384,38 @@ k_grid_bwd_d3c2(const T* __restrict__ grad, const float* __restrict__ inputs, co
     const int lane = threadIdx.x & 31;
     // ---- stage the block's gradient rows through shared memory with fully coalesced 16-byte loads
     const uint32_t nlev = min((uint32_t)LPT, L - l0);
-    if (point_major) {
-        constexpr int WORDS = LPT * WPL;               // words per point in this level group
-        const bool vec = (WORDS % 4 == 0) && ((L * WPL) % 4 == 0) && ((l0 * WPL) % 4 == 0) && (nlev == (uint32_t)LPT) &&
-                         (((uintptr_t)grad & 15) == 0);
-        if (vec) {
-            constexpr int CPP = WORDS / 4;             // 16-byte chunks per point
-            for (int c = threadIdx.x; c < GRID_BLOCK * CPP; c += GRID_BLOCK) {
-                const int pt = c / CPP, ch = c - pt * CPP;
-                if (b0 + pt < B) {
-                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(grad) + ((size_t)(b0 + pt) * L + l0) * WPL) + ch);
-                    uint32_t* d = sg + pt * ROW + ch * 4;
-                    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+#pragma unroll
+    for (int e = 0; e < NE; e++) {
+        const T* grad = e == 0 ? grad0 : grad1;
+        uint32_t* sge = sg[e];
+        if (point_major) {
+            constexpr int WORDS = LPT * WPL;               // words per point in this level group
+            const bool vec = (WORDS % 4 == 0) && ((L * WPL) % 4 == 0) && ((l0 * WPL) % 4 == 0) && (nlev == (uint32_t)LPT) &&
+                             (((uintptr_t)grad & 15) == 0);
+            if (vec) {
+                constexpr int CPP = WORDS / 4;             // 16-byte chunks per point
+                for (int c = threadIdx.x; c < GRID_BLOCK * CPP; c += GRID_BLOCK) {
+                    const int pt = c / CPP, ch = c - pt * CPP;
+                    if (b0 + pt < B) {
+                        const uint4 v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(grad) + ((size_t)(b0 + pt) * L + l0) * WPL) + ch);
+                        uint32_t* d = sge + pt * ROW + ch * 4;
+                        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+                    }
+                }
+            } else {
+                for (int c = threadIdx.x; c < GRID_BLOCK * WORDS; c += GRID_BLOCK) {
+                    const int pt = c / WORDS, wd = c - pt * WORDS;
+                    if (b0 + pt < B && (uint32_t)(wd / WPL) < nlev)
+                        sge[pt * ROW + wd] = __ldg(reinterpret_cast<const uint32_t*>(grad) + ((size_t)(b0 + pt) * L + l0) * WPL + wd);
                 }
             }
         } else {
-            for (int c = threadIdx.x; c < GRID_BLOCK * WORDS; c += GRID_BLOCK) {
-                const int pt = c / WORDS, wd = c - pt * WORDS;
-                if (b0 + pt < B && (uint32_t)(wd / WPL) < nlev)
-                    sg[pt * ROW + wd] = __ldg(reinterpret_cast<const uint32_t*>(grad) + ((size_t)(b0 + pt) * L + l0) * WPL + wd);
-            }
-        }
-    } else {
-        for (uint32_t j = 0; j < nlev; j++) {
-            if (b < B) {
+            for (uint32_t j = 0; j < nlev; j++) {
+                if (b < B) {
 #pragma unroll
-                for (int w = 0; w < WPL; w++)
-                    sg[threadIdx.x * ROW + j * WPL + w] = __ldg(reinterpret_cast<const uint32_t*>(grad) + ((size_t)(l0 + j) * B + b) * WPL + w);
+                    for (int w = 0; w < WPL; w++)
+                        sge[threadIdx.x * ROW + j * WPL + w] = __ldg(reinterpret_cast<const uint32_t*>(grad) + ((size_t)(l0 + j) * B + b) * WPL + w);
+                }
             }
         }
     }
@@ -398,38 +428,45 @@ k_grid_bwd_d3c2(const T* __restrict__ grad, const float* __restrict__ inputs, co
         const LevelP& p = lp[j];
         uint32_t cx = 0, cy = 0, cz = 0; float fx = 0, fy = 0, fz = 0;
         uint32_t rows[8]; float w[8];
-        float g0 = 0.0f, g1 = 0.0f;
         if (active) {
             locate1(x, p, align_corners, cx, fx);
             locate1(y, p, align_corners, cy, fy);
             locate1(z, p, align_corners, cz, fz);
             corner_rows_d3(p, cx, cy, cz, rows);
             corner_weights_d3(fx, fy, fz, w);
-            if constexpr (sizeof(T) == 4) {
-                g0 = __uint_as_float(sg[threadIdx.x * ROW + j * 2]);
-                g1 = __uint_as_float(sg[threadIdx.x * ROW + j * 2 + 1]);
-            } else {
-                uint32_t u = sg[threadIdx.x * ROW + j];
-                const float2 gg = __half22float2(*reinterpret_cast<__half2*>(&u));
-                g0 = gg.x; g1 = gg.y;
-            }
         }
-        TO* gl = grad_table + (size_t)p.offset * 2;
-        bool done = false;
+        // lanes in the same cell share all 8 corner rows: reduce each run of equal cells with shuffles and issue ONE vector
+        // atomic per corner per run.  The butterfly depth adapts to the longest run in the warp (coarse levels: 5
+        // steps for 1-2 runs; fine levels: 0-2 steps).
+        bool agg = false;
+        int lo = lane, hi = lane, maxlen = 1;
         if (agg_max_groups > 0) {
-            // lanes in the same cell share all 8 corner rows: reduce each run of equal cells with shuffles and issue ONE
-            // vector atomic per corner per run.  The butterfly depth adapts to the longest run in the warp (coarse levels:
-            // 5 steps for 1-2 runs; fine levels: 0-2 steps).
             const unsigned long long key = active ? (((unsigned long long)cz << 42) | ((unsigned long long)cy << 21) | (unsigned long long)cx)
                                                   : (0xFFFFFFFF00000000ull | (unsigned)lane);
             const uint32_t mask = __match_any_sync(NRF_FULL_MASK, key);
-            const int lo = __ffs(mask) - 1, hi = 31 - __clz(mask);
+            lo = __ffs(mask) - 1; hi = 31 - __clz(mask);
             const uint32_t span = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
-            if (__all_sync(NRF_FULL_MASK, mask == span)) {
-                const int maxlen = (int)__reduce_max_sync(NRF_FULL_MASK, (unsigned)(hi - lo + 1));
-                float v0[8], v1[8];
+            agg = __all_sync(NRF_FULL_MASK, mask == span);
+            if (agg) maxlen = (int)__reduce_max_sync(NRF_FULL_MASK, (unsigned)(hi - lo + 1));
+        }
 #pragma unroll
-                for (int k = 0; k < 8; k++) { v0[k] = active ? __fmul_rn(w[k], g0) : 0.0f; v1[k] = active ? __fmul_rn(w[k], g1) : 0.0f; }
+        for (int e = 0; e < NE; e++) {
+            float g0 = 0.0f, g1 = 0.0f;
+            if (active) {
+                if constexpr (sizeof(T) == 4) {
+                    g0 = __uint_as_float(sg[e][threadIdx.x * ROW + j * 2]);
+                    g1 = __uint_as_float(sg[e][threadIdx.x * ROW + j * 2 + 1]);
+                } else {
+                    uint32_t u = sg[e][threadIdx.x * ROW + j];
+                    const float2 gg = __half22float2(*reinterpret_cast<__half2*>(&u));
+                    g0 = gg.x; g1 = gg.y;
+                }
+            }
+            TO* gl = (e == 0 ? grad_table0 : grad_table1) + (size_t)p.offset * 2;
+            float v0[8], v1[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) { v0[k] = active ? __fmul_rn(w[k], g0) : 0.0f; v1[k] = active ? __fmul_rn(w[k], g1) : 0.0f; }
+            if (agg) {
                 for (int d = 1; d < maxlen; d <<= 1) {
                     const bool take = (lane + d <= hi);
 #pragma unroll
@@ -439,16 +476,10 @@ k_grid_bwd_d3c2(const T* __restrict__ grad, const float* __restrict__ inputs, co
                         if (take) { v0[k] += o0; v1[k] += o1; }
                     }
                 }
-                if (active && lane == lo) {
-#pragma unroll
-                    for (int k = 0; k < 8; k++) atomic_add2(gl, rows[k], v0[k], v1[k]);
-                }
-                done = true;
+                if (active && lane == lo) scatter_cell<TO>(gl, rows, v0, v1);
+            } else if (active) {
+                scatter_cell<TO>(gl, rows, v0, v1);
             }
-        }
-        if (!done && active) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) atomic_add2(gl, rows[k], __fmul_rn(w[k], g0), __fmul_rn(w[k], g1));
         }
     }
 }
@@ -521,7 +552,7 @@ static int launch_bwd(const void* grad, const float* inputs, const int32_t* offs
     const uint32_t nbx = ceil_div_u32(B, GRID_BLOCK);
     if (D == 3 && C == 2 && (((uintptr_t)grad_embeddings) & 7) == 0) {
         const int lpt = g_bwd_lpt;
-#define BWD_FAST(LPT) k_grid_bwd_d3c2<T, TO, LPT><<<dim3(nbx, ceil_div_u32(L, LPT)), GRID_BLOCK, 0, s>>>(g, inputs, offsets, ge, B, L, S, H, gridtype, ac, style, pm, g_bwd_agg)
+#define BWD_FAST(LPT) k_grid_bwd_d3c2<T, TO, LPT, 1><<<dim3(nbx, ceil_div_u32(L, LPT)), GRID_BLOCK, 0, s>>>(g, nullptr, inputs, offsets, ge, nullptr, B, L, S, H, gridtype, ac, style, pm, g_bwd_agg)
         if (lpt >= 16) BWD_FAST(16); else if (lpt >= 8) BWD_FAST(8); else if (lpt >= 4) BWD_FAST(4); else if (lpt >= 2) BWD_FAST(2); else BWD_FAST(1);
 #undef BWD_FAST
     } else {
@@ -555,6 +586,59 @@ NRF_EXPORT int nrf_grid_encode_backward(const void* grad, const float* inputs, c
     if (dtype == NRF_DTYPE_F16 && grad_table_dtype == NRF_DTYPE_F32)
         return launch_bwd<__half, float>(grad, inputs, offsets, grad_embeddings, B, D, C, L, S, H, calc, dy_dx, grad_inputs, gridtype, ac, style, pm, s);
     return NRF_E_UNSUPPORTED;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dual encoders: two tables with identical geometry in one pass (D=3, C=2, point-major, no input gradients)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static int launch_fwd_dual(const float* inputs, const void* e0, const void* e1, const int32_t* offsets, void* o0, void* o1, uint32_t B,
+                           uint32_t L, float S, uint32_t H, uint32_t gridtype, bool ac, uint32_t style, cudaStream_t s) {
+    const uint32_t nbx = ceil_div_u32(B, GRID_BLOCK);
+    // 8 levels per thread keeps the register footprint of the two result sets at the single-encoder kernel's (48 regs)
+    k_grid_fwd_d3c2<T, 8, 2><<<dim3(nbx, ceil_div_u32(L, 8)), GRID_BLOCK, 0, s>>>(inputs, (const T*)e0, (const T*)e1, offsets, (T*)o0, (T*)o1,
+                                                                                B, L, S, H, gridtype, ac, style, true);
+    return nrf_check_launch();
+}
+
+NRF_EXPORT int nrf_grid_encode_forward_dual(const float* inputs, const void* embeddings0, const void* embeddings1,
+                                            const int32_t* offsets, void* outputs0, void* outputs1, uint32_t B, uint32_t L, float S,
+                                            uint32_t H, uint32_t gridtype, int align_corners, uint32_t style, int dtype, void* stream) {
+    if (B == 0) return NRF_OK;
+    if (!inputs || !embeddings0 || !embeddings1 || !offsets || !outputs0 || !outputs1) return NRF_E_INVALID;
+    if (L == 0 || L > GRID_MAX_LEVELS) return NRF_E_UNSUPPORTED;
+    if ((((uintptr_t)embeddings0) & 7) || (((uintptr_t)embeddings1) & 7)) return NRF_E_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == NRF_DTYPE_F32) return launch_fwd_dual<float>(inputs, embeddings0, embeddings1, offsets, outputs0, outputs1, B, L, S, H, gridtype, align_corners != 0, style, s);
+    if (dtype == NRF_DTYPE_F16) return launch_fwd_dual<__half>(inputs, embeddings0, embeddings1, offsets, outputs0, outputs1, B, L, S, H, gridtype, align_corners != 0, style, s);
+    return NRF_E_UNSUPPORTED;
+}
+
+NRF_EXPORT int nrf_grid_encode_backward_dual(const void* grad0, const void* grad1, const float* inputs, const int32_t* offsets,
+                                             void* grad_embeddings0, void* grad_embeddings1, uint32_t B, uint32_t L, float S, uint32_t H,
+                                             uint32_t gridtype, int align_corners, uint32_t style, int dtype, int grad_table_dtype,
+                                             void* stream) {
+    if (B == 0) return NRF_OK;
+    if (!grad0 || !grad1 || !inputs || !offsets || !grad_embeddings0 || !grad_embeddings1) return NRF_E_INVALID;
+    if (L == 0 || L > GRID_MAX_LEVELS) return NRF_E_UNSUPPORTED;
+    if ((((uintptr_t)grad_embeddings0) & 7) || (((uintptr_t)grad_embeddings1) & 7)) return NRF_E_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool ac = align_corners != 0;
+    const uint32_t nbx = ceil_div_u32(B, GRID_BLOCK);
+    if (dtype == NRF_DTYPE_F16 && grad_table_dtype == NRF_DTYPE_F32)
+        k_grid_bwd_d3c2<__half, float, 16, 2><<<dim3(nbx, ceil_div_u32(L, 16)), GRID_BLOCK, 0, s>>>(
+            (const __half*)grad0, (const __half*)grad1, inputs, offsets, (float*)grad_embeddings0, (float*)grad_embeddings1, B, L, S, H,
+            gridtype, ac, style, true, g_bwd_agg);
+    else if (dtype == NRF_DTYPE_F16 && grad_table_dtype == NRF_DTYPE_F16)
+        k_grid_bwd_d3c2<__half, __half, 16, 2><<<dim3(nbx, ceil_div_u32(L, 16)), GRID_BLOCK, 0, s>>>(
+            (const __half*)grad0, (const __half*)grad1, inputs, offsets, (__half*)grad_embeddings0, (__half*)grad_embeddings1, B, L, S, H,
+            gridtype, ac, style, true, g_bwd_agg);
+    else if (dtype == NRF_DTYPE_F32 && grad_table_dtype == NRF_DTYPE_F32)      // 8 levels per block: the staged f32 gradients of two encoders fit 48 KB
+        k_grid_bwd_d3c2<float, float, 8, 2><<<dim3(nbx, ceil_div_u32(L, 8)), GRID_BLOCK, 0, s>>>(
+            (const float*)grad0, (const float*)grad1, inputs, offsets, (float*)grad_embeddings0, (float*)grad_embeddings1, B, L, S, H,
+            gridtype, ac, style, true, g_bwd_agg);
+    else return NRF_E_UNSUPPORTED;
+    return nrf_check_launch();
 }
 
 // ------------------------------------------------------------------------------------------------

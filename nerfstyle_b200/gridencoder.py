@@ -91,6 +91,87 @@ class _grid_encode(Function):
 grid_encode = _grid_encode.apply
 
 
+class _grid_encode_dual(Function):
+    """Two encoders with identical geometry on the same points in one pass per direction (nrf_grid_encode_*_dual):
+    cells, hash rows and trilinear weights are computed once.  Same values as two `_grid_encode` calls."""
+
+    @staticmethod
+    @custom_fwd(device_type='cuda')
+    def forward(ctx, inputs, emb0, emb1, offsets, per_level_scale, base_resolution, gridtype, align_corners, style):
+        L.require_cuda(inputs, emb0, emb1, offsets)
+        inputs = inputs.contiguous()
+        if inputs.dtype != torch.float32:
+            inputs = inputs.float()
+        B, D = inputs.shape
+        Lv = offsets.shape[0] - 1
+        C = emb0.shape[1]
+        if D != 3 or C != 2 or emb1.shape != emb0.shape:
+            raise RuntimeError('grid_encode_dual: D=3, C=2 and equal table shapes are required')
+        S = float(np.float32(np.log2(per_level_scale)))
+        H = int(base_resolution)
+        embs = []
+        for e in (emb0, emb1):
+            if torch.is_autocast_enabled('cuda'):
+                shadow = getattr(e, '_nrf_half_copy', None)
+                e = shadow if shadow is not None else e.to(torch.half)
+            embs.append(e.contiguous())
+        if embs[0].dtype != embs[1].dtype:
+            raise RuntimeError('grid_encode_dual: tables must share a dtype')
+        offsets = offsets.contiguous()
+        dt = L.dtype_code(embs[0].dtype)
+        out0 = torch.empty(B, Lv * C, device=inputs.device, dtype=embs[0].dtype)
+        out1 = torch.empty_like(out0)
+        L.Stats.units = B
+        with torch.cuda.device(inputs.device):
+            L.check(L.lib().nrf_grid_encode_forward_dual(L.ptr(inputs), L.ptr(embs[0]), L.ptr(embs[1]), L.ptr(offsets),
+                                                         L.ptr(out0), L.ptr(out1), B, Lv, S, H, int(gridtype),
+                                                         int(bool(align_corners)), int(style), dt, L.stream_of(inputs)),
+                    'grid_encode_forward_dual')
+        ctx.save_for_backward(inputs, offsets)
+        ctx.meta = (B, Lv, S, H, gridtype, align_corners, style, embs[0].dtype, emb0.shape)
+        return out0, out1
+
+    @staticmethod
+    @custom_bwd(device_type='cuda')
+    def backward(ctx, g0, g1):
+        inputs, offsets = ctx.saved_tensors
+        B, Lv, S, H, gridtype, align_corners, style, dtype, shape = ctx.meta
+        dev = inputs.device
+        gs = []
+        for g in (g0, g1):
+            if g is None:
+                g = torch.zeros(B, Lv * 2, dtype=dtype, device=dev)
+            g = g.contiguous()
+            gs.append(g if g.dtype == dtype else g.to(dtype))
+        ge0 = torch.zeros(shape, dtype=torch.float32, device=dev)
+        ge1 = torch.zeros(shape, dtype=torch.float32, device=dev)
+        L.Stats.units = B
+        with torch.cuda.device(dev):
+            L.check(L.lib().nrf_grid_encode_backward_dual(L.ptr(gs[0]), L.ptr(gs[1]), L.ptr(inputs), L.ptr(offsets), L.ptr(ge0),
+                                                          L.ptr(ge1), B, Lv, S, H, int(gridtype), int(bool(align_corners)),
+                                                          int(style), L.dtype_code(dtype), L.DTYPE_F32, L.stream_of(inputs)),
+                    'grid_encode_backward_dual')
+        return None, ge0, ge1, None, None, None, None, None, None
+
+
+def same_geometry(a, b):
+    """True when two GridEncoders address their tables identically (so one index computation serves both)."""
+    return (a.input_dim == b.input_dim == 3 and a.level_dim == b.level_dim == 2 and a.num_levels == b.num_levels
+            and a.per_level_scale == b.per_level_scale and a.base_resolution == b.base_resolution
+            and a.gridtype_id == b.gridtype_id and a.align_corners == b.align_corners
+            and a.embeddings.shape == b.embeddings.shape and torch.equal(a.offsets, b.offsets))
+
+
+def grid_encode_dual(inputs, enc_a, enc_b, bound=1, style=0):
+    """(enc_a(inputs, bound, style), enc_b(inputs, bound, style)) in one pass; the encoders must satisfy same_geometry()."""
+    inputs = (inputs + bound) / (2 * bound)          # GridEncoder.forward, grid.py:174
+    prefix_shape = list(inputs.shape[:-1])
+    inputs = inputs.view(-1, enc_a.input_dim)
+    o0, o1 = _grid_encode_dual.apply(inputs, enc_a.embeddings, enc_b.embeddings, enc_a.offsets, enc_a.per_level_scale,
+                                     enc_a.base_resolution, enc_a.gridtype_id, enc_a.align_corners, style)
+    return o0.view(prefix_shape + [enc_a.output_dim]), o1.view(prefix_shape + [enc_b.output_dim])
+
+
 class GridEncoder(nn.Module):
     """grid.py:103-191 (same arguments, attributes and state-dict keys)."""
 

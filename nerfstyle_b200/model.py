@@ -22,7 +22,7 @@ from torch.amp import custom_bwd, custom_fwd
 
 from . import raymarching
 from . import tcnn
-from .gridencoder import GridEncoder
+from .gridencoder import GridEncoder, grid_encode_dual, same_geometry
 
 STEP_CTR_SIZE = 16
 
@@ -70,6 +70,7 @@ class StyleTCNerf(nn.Module):
         # fused_heads: same math as the reference's op-by-op glue below, with trunc_exp / cat / casts folded into the
         # MLP kernels (tcnn.density_head / tcnn.color_heads); False runs the reference's exact op sequence
         self.fused_heads = fused_heads
+        self._dual = None
         self.register_buffer('bbox_min', torch.as_tensor(bbox_min, dtype=torch.float32))
         self.register_buffer('bbox_size', torch.as_tensor(bbox_max, dtype=torch.float32) - self.bbox_min)
         self.class_dim = class_dim
@@ -89,13 +90,19 @@ class StyleTCNerf(nn.Module):
 
     def _forward(self, pts, dirs=None):
         pts = (pts - self.bbox_min) / self.bbox_size            # BBox.normalize, common.py:288
-        x_embedded = self.x_density_embedder(pts)
-        if self.fused_heads and x_embedded.is_cuda:
-            sigmas = tcnn.density_head(x_embedded, self.density_net)
+        if self.fused_heads and pts.is_cuda:
             if dirs is None:
-                return sigmas
-            rgbs = tcnn.color_heads(self.x_color_embedder(pts), self.class_net, self.color1_net, self.color2_net)
+                return tcnn.density_head(self.x_density_embedder(pts), self.density_net)
+            if self._dual is None:
+                self._dual = bool(same_geometry(self.x_density_embedder, self.x_color_embedder))
+            if self._dual:       # one index computation for both hash tables
+                x_embedded, x_color_embedded = grid_encode_dual(pts, self.x_density_embedder, self.x_color_embedder)
+            else:
+                x_embedded, x_color_embedded = self.x_density_embedder(pts), self.x_color_embedder(pts)
+            sigmas = tcnn.density_head(x_embedded, self.density_net)
+            rgbs = tcnn.color_heads(x_color_embedded, self.class_net, self.color1_net, self.color2_net)
             return rgbs, sigmas
+        x_embedded = self.x_density_embedder(pts)
         density_output = self.density_net(x_embedded)
         sigmas = trunc_exp(density_output)
         if dirs is None:

@@ -167,3 +167,37 @@ def test_empty_and_errors(cuda_lib, dev):
     with pytest.raises(RuntimeError):
         enc(torch.zeros(4, 3))                                   # CPU tensor: no fallback
     assert cuda_lib.nrf_grid_encode_forward(1, 1, 1, 1, 4, 7, 2, 16, 0.5, 16, 0, None, 0, 1, 0, 0, 1, None) == -2
+
+
+@pytest.mark.parametrize('amp', [False, True])
+def test_dual_equals_two_single_passes(cuda_lib, dev, amp):
+    """nrf_grid_encode_*_dual (one index computation for two tables) == two independent encoder calls: forward bit for
+    bit, backward up to the float-atomics summation order.  Points mimic
+    ray samples (runs in the same cell) plus out-of-range rows."""
+    from nerfstyle_b200.gridencoder import grid_encode_dual, same_geometry
+    ea, eb = _default_encoder(dev, 1), _default_encoder(dev, 2)
+    assert same_geometry(ea, eb)
+    B = 20011
+    g = torch.Generator().manual_seed(5)
+    base = torch.rand(B // 32 + 1, 3, generator=g).repeat_interleave(32, dim=0)[:B]
+    x = (base + torch.arange(B)[:, None] % 32 * 4e-4).to(dev) * 2 - 1           # short rays of 32 samples
+    x[7] = 3.0                                                                   # out of range -> zero row, no gradient
+    if True:
+        res = []
+        for dual in (True, False):
+            for e in (ea, eb):
+                e.embeddings.grad = None
+            with torch.autocast('cuda', dtype=torch.float16, enabled=amp):
+                if dual:
+                    oa, ob = grid_encode_dual(x, ea, eb)
+                else:
+                    oa, ob = ea(x), eb(x)
+            ga = torch.randn(oa.shape, generator=torch.Generator().manual_seed(6)).to(dev).to(oa.dtype)
+            gb = torch.randn(ob.shape, generator=torch.Generator().manual_seed(7)).to(dev).to(ob.dtype)
+            torch.autograd.backward([oa, ob], [ga, gb])
+            res.append((oa.detach(), ob.detach(), ea.embeddings.grad.clone(), eb.embeddings.grad.clone()))
+        assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+        for k in (2, 3):
+            a, b = res[0][k], res[1][k]
+            assert a.dtype == torch.float32
+            assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
