@@ -165,14 +165,17 @@ int nrf_grid_encode_backward(const void* grad, const float* inputs, const void* 
 /* Two encoders with IDENTICAL geometry (same offsets / S / H / gridtype / align_corners) on the same points in one
  * pass: cell positions, hash rows and trilinear weights are computed once (the model's x_density_embedder and
  * x_color_embedder, networks/style_nerf.py:29-30,121-134, are such a pair).  D=3, C=2, point-major [B, L*2] outputs /
- * gradients, no input gradients.  Results are those of two nrf_grid_encode_forward / _backward calls. */
+ * gradients, no input gradients.  Results are those of two nrf_grid_encode_forward / _backward calls.
+ * xform (device float[7] = {min[3], size[3], bound}, or NULL): the points are first mapped by ((x - min) / size + bound) /
+ * (2 bound) in f32, operation for operation what common.py:288 and grid.py:174 do in four elementwise kernels. */
 int nrf_grid_encode_forward_dual(const float* inputs, const void* embeddings0, const void* embeddings1,
                                  const int32_t* offsets, void* outputs0, void* outputs1, uint32_t B, uint32_t L, float S,
-                                 uint32_t H, uint32_t gridtype, int align_corners, uint32_t style, int dtype, void* stream);
+                                 uint32_t H, uint32_t gridtype, int align_corners, uint32_t style, int dtype,
+                                 const float* xform, void* stream);
 int nrf_grid_encode_backward_dual(const void* grad0, const void* grad1, const float* inputs, const int32_t* offsets,
                                   void* grad_embeddings0, void* grad_embeddings1, uint32_t B, uint32_t L, float S, uint32_t H,
                                   uint32_t gridtype, int align_corners, uint32_t style, int dtype, int grad_table_dtype,
-                                  void* stream);
+                                  const float* xform, void* stream);
 
 /* gridencoder.cu:551-571 (D=3, C=2, f32 like the reference's only use). */
 int nrf_grid_initialize(const float* ref_embeddings, float* embeddings, const int32_t* ref_offsets,

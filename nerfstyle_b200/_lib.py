@@ -45,9 +45,10 @@ SIGNATURES = {
                                        _u32, _i32, _i32, _vp]),
     'nrf_grid_encode_backward': (_i32, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _u32, _i32, _vp, _vp,
                                         _u32, _i32, _u32, _i32, _i32, _i32, _vp]),
-    'nrf_grid_encode_forward_dual': (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _f32, _u32, _u32, _i32, _u32, _i32, _vp]),
+    'nrf_grid_encode_forward_dual': (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _f32, _u32, _u32, _i32, _u32, _i32, _vp,
+                                            _vp]),
     'nrf_grid_encode_backward_dual': (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _f32, _u32, _u32, _i32, _u32, _i32, _i32,
-                                             _vp]),
+                                             _vp, _vp]),
     'nrf_grid_initialize': (_i32, [_vp, _vp, _vp, _vp, _u32, _f32, _u32, _u32, _vp]),
     'nrf_mlp_forward': (_i32, [_vp, _i32, _vp, _u32, _u32, _u32, _u32, _u32, _i32, _i32, _vp, _i32, _vp]),
     'nrf_mlp_backward': (_i32, [_vp, _i32, _vp, _vp, _i32, _u32, _u32, _u32, _u32, _u32, _i32, _i32, _f32, _vp, _i32,

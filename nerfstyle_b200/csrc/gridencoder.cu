@@ -74,6 +74,14 @@ __device__ __forceinline__ void locate1(float in, const LevelP& p, bool align_co
 // ------------------------------------------------------------------------------------------------
 // forward, fast path D=3 C=2 (the only instance the model uses)
 // ------------------------------------------------------------------------------------------------
+// optional input transform of the dual entry points: xform = {min[3], size[3], bound}; reproduces, operation for operation,
+// BBox.normalize (common.py:288: (x - min) / size) followed by GridEncoder.forward's (x + bound) / (2 bound) (grid.py:174)
+__device__ __forceinline__ float xform1(float v, const float* __restrict__ xf, int d) {
+    const float t = __fdiv_rn(__fsub_rn(v, __ldg(xf + d)), __ldg(xf + 3 + d));
+    const float b = __ldg(xf + 6);
+    return __fmul_rn(__fadd_rn(t, b), __fdiv_rn(1.0f, __fmul_rn(2.0f, b)));     // torch divides by a scalar as a * (1 / s)
+}
+
 template <typename T> struct Vec2;
 template <> struct Vec2<float> { typedef float2 type; };
 template <> struct Vec2<__half> { typedef __half2 type; };
@@ -112,7 +120,8 @@ template <typename T, int LPT, int NE>
 __global__ void __launch_bounds__(GRID_BLOCK)
 k_grid_fwd_d3c2(const float* __restrict__ inputs, const T* __restrict__ table0, const T* __restrict__ table1,
                 const int32_t* __restrict__ offsets, T* __restrict__ outputs0, T* __restrict__ outputs1, uint32_t B, uint32_t L,
-                float S, uint32_t H, uint32_t gridtype, bool align_corners, uint32_t style, bool point_major) {
+                float S, uint32_t H, uint32_t gridtype, bool align_corners, uint32_t style, bool point_major,
+                const float* __restrict__ xform) {
     typedef typename Vec2<T>::type V2;
     __shared__ LevelP lp[LPT];
     const uint32_t l0 = blockIdx.y * LPT;
@@ -120,7 +129,8 @@ k_grid_fwd_d3c2(const float* __restrict__ inputs, const T* __restrict__ table0, 
     __syncthreads();
     const uint32_t b = blockIdx.x * GRID_BLOCK + threadIdx.x;
     if (b >= B) return;
-    const float x = __ldg(inputs + 3 * (size_t)b), y = __ldg(inputs + 3 * (size_t)b + 1), z = __ldg(inputs + 3 * (size_t)b + 2);
+    float x = __ldg(inputs + 3 * (size_t)b), y = __ldg(inputs + 3 * (size_t)b + 1), z = __ldg(inputs + 3 * (size_t)b + 2);
+    if (xform) { x = xform1(x, xform, 0); y = xform1(y, xform, 1); z = xform1(z, xform, 2); }
     const bool oob = (x < 0 || x > 1) || (y < 0 || y > 1) || (z < 0 || z > 1);   // gridencoder.cu:107-114
     V2 res[NE][LPT];
 #pragma unroll
@@ -316,7 +326,7 @@ static int launch_fwd(const float* inputs, const void* embeddings, const int32_t
     const uint32_t nbx = ceil_div_u32(B, GRID_BLOCK);
     if (D == 3 && C == 2 && !calc && (((uintptr_t)embeddings) & 7) == 0) {
         const int lpt = g_fwd_lpt;
-#define FWD_FAST(LPT) k_grid_fwd_d3c2<T, LPT, 1><<<dim3(nbx, ceil_div_u32(L, LPT)), GRID_BLOCK, 0, s>>>(inputs, tab, nullptr, offsets, out, nullptr, B, L, S, H, gridtype, ac, style, pm)
+#define FWD_FAST(LPT) k_grid_fwd_d3c2<T, LPT, 1><<<dim3(nbx, ceil_div_u32(L, LPT)), GRID_BLOCK, 0, s>>>(inputs, tab, nullptr, offsets, out, nullptr, B, L, S, H, gridtype, ac, style, pm, nullptr)
         if (lpt >= 16) FWD_FAST(16); else if (lpt >= 8) FWD_FAST(8); else if (lpt >= 4) FWD_FAST(4); else if (lpt >= 2) FWD_FAST(2); else FWD_FAST(1);
 #undef FWD_FAST
         return nrf_check_launch();
@@ -371,7 +381,8 @@ template <typename T, typename TO, int LPT, int NE>
 __global__ void __launch_bounds__(GRID_BLOCK, NE == 1 ? 1 : 4)
 k_grid_bwd_d3c2(const T* __restrict__ grad0, const T* __restrict__ grad1, const float* __restrict__ inputs,
                 const int32_t* __restrict__ offsets, TO* __restrict__ grad_table0, TO* __restrict__ grad_table1, uint32_t B, uint32_t L,
-                float S, uint32_t H, uint32_t gridtype, bool align_corners, uint32_t style, bool point_major, int agg_max_groups) {
+                float S, uint32_t H, uint32_t gridtype, bool align_corners, uint32_t style, bool point_major, int agg_max_groups,
+                const float* __restrict__ xform) {
     typedef typename Vec2<T>::type V2;
     constexpr int WPL = (int)sizeof(V2) / 4;           // 32-bit words per level of one point's gradient
     constexpr int ROW = LPT * WPL + 1;                 // padded smem row (conflict-free column reads)
@@ -420,7 +431,10 @@ k_grid_bwd_d3c2(const T* __restrict__ grad0, const T* __restrict__ grad1, const 
         }
     }
     float x = -1.0f, y = -1.0f, z = -1.0f;
-    if (b < B) { x = __ldg(inputs + 3 * (size_t)b); y = __ldg(inputs + 3 * (size_t)b + 1); z = __ldg(inputs + 3 * (size_t)b + 2); }
+    if (b < B) {
+        x = __ldg(inputs + 3 * (size_t)b); y = __ldg(inputs + 3 * (size_t)b + 1); z = __ldg(inputs + 3 * (size_t)b + 2);
+        if (xform) { x = xform1(x, xform, 0); y = xform1(y, xform, 1); z = xform1(z, xform, 2); }
+    }
     const bool active = !((x < 0 || x > 1) || (y < 0 || y > 1) || (z < 0 || z > 1));   // oob points contribute nothing (:268-273)
     __syncthreads();
 #pragma unroll 1
@@ -552,7 +566,7 @@ static int launch_bwd(const void* grad, const float* inputs, const int32_t* offs
     const uint32_t nbx = ceil_div_u32(B, GRID_BLOCK);
     if (D == 3 && C == 2 && (((uintptr_t)grad_embeddings) & 7) == 0) {
         const int lpt = g_bwd_lpt;
-#define BWD_FAST(LPT) k_grid_bwd_d3c2<T, TO, LPT, 1><<<dim3(nbx, ceil_div_u32(L, LPT)), GRID_BLOCK, 0, s>>>(g, nullptr, inputs, offsets, ge, nullptr, B, L, S, H, gridtype, ac, style, pm, g_bwd_agg)
+#define BWD_FAST(LPT) k_grid_bwd_d3c2<T, TO, LPT, 1><<<dim3(nbx, ceil_div_u32(L, LPT)), GRID_BLOCK, 0, s>>>(g, nullptr, inputs, offsets, ge, nullptr, B, L, S, H, gridtype, ac, style, pm, g_bwd_agg, nullptr)
         if (lpt >= 16) BWD_FAST(16); else if (lpt >= 8) BWD_FAST(8); else if (lpt >= 4) BWD_FAST(4); else if (lpt >= 2) BWD_FAST(2); else BWD_FAST(1);
 #undef BWD_FAST
     } else {
@@ -593,31 +607,32 @@ NRF_EXPORT int nrf_grid_encode_backward(const void* grad, const float* inputs, c
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 static int launch_fwd_dual(const float* inputs, const void* e0, const void* e1, const int32_t* offsets, void* o0, void* o1, uint32_t B,
-                           uint32_t L, float S, uint32_t H, uint32_t gridtype, bool ac, uint32_t style, cudaStream_t s) {
+                           uint32_t L, float S, uint32_t H, uint32_t gridtype, bool ac, uint32_t style, const float* xform, cudaStream_t s) {
     const uint32_t nbx = ceil_div_u32(B, GRID_BLOCK);
     // 8 levels per thread keeps the register footprint of the two result sets at the single-encoder kernel's (48 regs)
     k_grid_fwd_d3c2<T, 8, 2><<<dim3(nbx, ceil_div_u32(L, 8)), GRID_BLOCK, 0, s>>>(inputs, (const T*)e0, (const T*)e1, offsets, (T*)o0, (T*)o1,
-                                                                                B, L, S, H, gridtype, ac, style, true);
+                                                                                B, L, S, H, gridtype, ac, style, true, xform);
     return nrf_check_launch();
 }
 
 NRF_EXPORT int nrf_grid_encode_forward_dual(const float* inputs, const void* embeddings0, const void* embeddings1,
                                             const int32_t* offsets, void* outputs0, void* outputs1, uint32_t B, uint32_t L, float S,
-                                            uint32_t H, uint32_t gridtype, int align_corners, uint32_t style, int dtype, void* stream) {
+                                            uint32_t H, uint32_t gridtype, int align_corners, uint32_t style, int dtype,
+                                            const float* xform, void* stream) {
     if (B == 0) return NRF_OK;
     if (!inputs || !embeddings0 || !embeddings1 || !offsets || !outputs0 || !outputs1) return NRF_E_INVALID;
     if (L == 0 || L > GRID_MAX_LEVELS) return NRF_E_UNSUPPORTED;
     if ((((uintptr_t)embeddings0) & 7) || (((uintptr_t)embeddings1) & 7)) return NRF_E_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
-    if (dtype == NRF_DTYPE_F32) return launch_fwd_dual<float>(inputs, embeddings0, embeddings1, offsets, outputs0, outputs1, B, L, S, H, gridtype, align_corners != 0, style, s);
-    if (dtype == NRF_DTYPE_F16) return launch_fwd_dual<__half>(inputs, embeddings0, embeddings1, offsets, outputs0, outputs1, B, L, S, H, gridtype, align_corners != 0, style, s);
+    if (dtype == NRF_DTYPE_F32) return launch_fwd_dual<float>(inputs, embeddings0, embeddings1, offsets, outputs0, outputs1, B, L, S, H, gridtype, align_corners != 0, style, xform, s);
+    if (dtype == NRF_DTYPE_F16) return launch_fwd_dual<__half>(inputs, embeddings0, embeddings1, offsets, outputs0, outputs1, B, L, S, H, gridtype, align_corners != 0, style, xform, s);
     return NRF_E_UNSUPPORTED;
 }
 
 NRF_EXPORT int nrf_grid_encode_backward_dual(const void* grad0, const void* grad1, const float* inputs, const int32_t* offsets,
                                              void* grad_embeddings0, void* grad_embeddings1, uint32_t B, uint32_t L, float S, uint32_t H,
                                              uint32_t gridtype, int align_corners, uint32_t style, int dtype, int grad_table_dtype,
-                                             void* stream) {
+                                             const float* xform, void* stream) {
     if (B == 0) return NRF_OK;
     if (!grad0 || !grad1 || !inputs || !offsets || !grad_embeddings0 || !grad_embeddings1) return NRF_E_INVALID;
     if (L == 0 || L > GRID_MAX_LEVELS) return NRF_E_UNSUPPORTED;
@@ -628,15 +643,15 @@ NRF_EXPORT int nrf_grid_encode_backward_dual(const void* grad0, const void* grad
     if (dtype == NRF_DTYPE_F16 && grad_table_dtype == NRF_DTYPE_F32)
         k_grid_bwd_d3c2<__half, float, 16, 2><<<dim3(nbx, ceil_div_u32(L, 16)), GRID_BLOCK, 0, s>>>(
             (const __half*)grad0, (const __half*)grad1, inputs, offsets, (float*)grad_embeddings0, (float*)grad_embeddings1, B, L, S, H,
-            gridtype, ac, style, true, g_bwd_agg);
+            gridtype, ac, style, true, g_bwd_agg, xform);
     else if (dtype == NRF_DTYPE_F16 && grad_table_dtype == NRF_DTYPE_F16)
         k_grid_bwd_d3c2<__half, __half, 16, 2><<<dim3(nbx, ceil_div_u32(L, 16)), GRID_BLOCK, 0, s>>>(
             (const __half*)grad0, (const __half*)grad1, inputs, offsets, (__half*)grad_embeddings0, (__half*)grad_embeddings1, B, L, S, H,
-            gridtype, ac, style, true, g_bwd_agg);
+            gridtype, ac, style, true, g_bwd_agg, xform);
     else if (dtype == NRF_DTYPE_F32 && grad_table_dtype == NRF_DTYPE_F32)      // 8 levels per block: the staged f32 gradients of two encoders fit 48 KB
         k_grid_bwd_d3c2<float, float, 8, 2><<<dim3(nbx, ceil_div_u32(L, 8)), GRID_BLOCK, 0, s>>>(
             (const float*)grad0, (const float*)grad1, inputs, offsets, (float*)grad_embeddings0, (float*)grad_embeddings1, B, L, S, H,
-            gridtype, ac, style, true, g_bwd_agg);
+            gridtype, ac, style, true, g_bwd_agg, xform);
     else return NRF_E_UNSUPPORTED;
     return nrf_check_launch();
 }

@@ -868,14 +868,24 @@ k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays
         return;
     }
     const int32_t index = rays_alive[n];
-    MarchCtx c;
-    march_init(c, rays_o + 3 * (size_t)index, rays_d + 3 * (size_t)index, bound, dt_gamma, max_steps, C, H);
-    float t = rays_t[(size_t)index * (is_ndc ? 2 : 1)];
-    const float far = fars[index];
     float* px = xyzs + 3 * (size_t)n * n_step;
     float* pd = dirs + 3 * (size_t)n * n_step;
     float4* pl = reinterpret_cast<float4*>(deltas) + (size_t)n * n_step;
     uint32_t step = 0;
+    if (index < 0) {
+        // extension: a dead slot (-1) left in the list by a caller that compacts without reading the count back every
+        // iteration (Renderer.render_test of the host mirror); its rows are zero so that composite_rays skips them
+        for (; step < n_step; step++) {
+            px[0] = 0; px[1] = 0; px[2] = 0; pd[0] = 0; pd[1] = 0; pd[2] = 0;
+            *pl = make_float4(0, 0, 0, 0);
+            px += 3; pd += 3; pl += 1;
+        }
+        return;
+    }
+    MarchCtx c;
+    march_init(c, rays_o + 3 * (size_t)index, rays_d + 3 * (size_t)index, bound, dt_gamma, max_steps, C, H);
+    float t = rays_t[(size_t)index * (is_ndc ? 2 : 1)];
+    const float far = fars[index];
     t = march_t0(c, t, noises ? noises[n] : 0.0f);
     float last_t = t;
     float last_z = nrf_clamp(__fmaf_rn(c.dz, t, c.oz), c.nbound, c.bound);
@@ -935,6 +945,7 @@ k_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* __r
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= n_alive) return;
     const int32_t index = rays_alive[n];
+    if (index < 0) return;          // dead slot (see k_march_rays)
     const float* s = sigmas + (size_t)n * n_step;
     const float* r = rgbs + (size_t)n * n_step * C;
     const float4* dl4 = reinterpret_cast<const float4*>(deltas) + (size_t)n * n_step;
@@ -1012,6 +1023,7 @@ NRF_EXPORT int nrf_compact_alive(const int32_t* in, uint32_t n, int32_t* out, in
     // scratch sized by nrf_march_scratch_bytes(n): ceil(n/64)+1024 words >= nb + 2
     int32_t* total = (int32_t*)(block_sums + nb);
     cudaMemsetAsync(total, 0, 2 * sizeof(int32_t), s);
+    cudaMemsetAsync(out, 0xFF, (size_t)n * sizeof(int32_t), s);      // entries past the new count read -1 (dead slots)
     k_compact_count<<<nb, COMPACT_BLOCK, 0, s>>>(in, n, block_sums);
     k_scan_block_sums<<<1, 1024, 0, s>>>(block_sums, nb, total, 0);
     k_compact_write<<<nb, COMPACT_BLOCK, 0, s>>>(in, n, block_sums, out);

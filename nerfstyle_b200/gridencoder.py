@@ -97,8 +97,9 @@ class _grid_encode_dual(Function):
 
     @staticmethod
     @custom_fwd(device_type='cuda')
-    def forward(ctx, inputs, emb0, emb1, offsets, per_level_scale, base_resolution, gridtype, align_corners, style):
-        L.require_cuda(inputs, emb0, emb1, offsets)
+    def forward(ctx, inputs, emb0, emb1, offsets, per_level_scale, base_resolution, gridtype, align_corners, style,
+                xform=None):
+        L.require_cuda(inputs, emb0, emb1, offsets, xform)
         inputs = inputs.contiguous()
         if inputs.dtype != torch.float32:
             inputs = inputs.float()
@@ -125,16 +126,17 @@ class _grid_encode_dual(Function):
         with torch.cuda.device(inputs.device):
             L.check(L.lib().nrf_grid_encode_forward_dual(L.ptr(inputs), L.ptr(embs[0]), L.ptr(embs[1]), L.ptr(offsets),
                                                          L.ptr(out0), L.ptr(out1), B, Lv, S, H, int(gridtype),
-                                                         int(bool(align_corners)), int(style), dt, L.stream_of(inputs)),
+                                                         int(bool(align_corners)), int(style), dt, L.ptr(xform),
+                                                         L.stream_of(inputs)),
                     'grid_encode_forward_dual')
-        ctx.save_for_backward(inputs, offsets)
+        ctx.save_for_backward(inputs, offsets, xform)
         ctx.meta = (B, Lv, S, H, gridtype, align_corners, style, embs[0].dtype, emb0.shape)
         return out0, out1
 
     @staticmethod
     @custom_bwd(device_type='cuda')
     def backward(ctx, g0, g1):
-        inputs, offsets = ctx.saved_tensors
+        inputs, offsets, xform = ctx.saved_tensors
         B, Lv, S, H, gridtype, align_corners, style, dtype, shape = ctx.meta
         dev = inputs.device
         gs = []
@@ -149,9 +151,10 @@ class _grid_encode_dual(Function):
         with torch.cuda.device(dev):
             L.check(L.lib().nrf_grid_encode_backward_dual(L.ptr(gs[0]), L.ptr(gs[1]), L.ptr(inputs), L.ptr(offsets), L.ptr(ge0),
                                                           L.ptr(ge1), B, Lv, S, H, int(gridtype), int(bool(align_corners)),
-                                                          int(style), L.dtype_code(dtype), L.DTYPE_F32, L.stream_of(inputs)),
+                                                          int(style), L.dtype_code(dtype), L.DTYPE_F32, L.ptr(xform),
+                                                          L.stream_of(inputs)),
                     'grid_encode_backward_dual')
-        return None, ge0, ge1, None, None, None, None, None, None
+        return None, ge0, ge1, None, None, None, None, None, None, None
 
 
 def same_geometry(a, b):
@@ -162,13 +165,16 @@ def same_geometry(a, b):
             and a.embeddings.shape == b.embeddings.shape and torch.equal(a.offsets, b.offsets))
 
 
-def grid_encode_dual(inputs, enc_a, enc_b, bound=1, style=0):
-    """(enc_a(inputs, bound, style), enc_b(inputs, bound, style)) in one pass; the encoders must satisfy same_geometry()."""
-    inputs = (inputs + bound) / (2 * bound)          # GridEncoder.forward, grid.py:174
+def grid_encode_dual(inputs, enc_a, enc_b, bound=1, style=0, xform=None):
+    """(enc_a(inputs, bound, style), enc_b(inputs, bound, style)) in one pass; the encoders must satisfy same_geometry().
+    xform (device f32[7] = bbox_min, bbox_size, bound): `inputs` are RAW points and the kernel applies
+    ((x - min) / size + bound) / (2 bound) itself (same f32 operations as the two Python lines it replaces)."""
+    if xform is None:
+        inputs = (inputs + bound) / (2 * bound)          # GridEncoder.forward, grid.py:174
     prefix_shape = list(inputs.shape[:-1])
-    inputs = inputs.view(-1, enc_a.input_dim)
+    inputs = inputs.reshape(-1, enc_a.input_dim)
     o0, o1 = _grid_encode_dual.apply(inputs, enc_a.embeddings, enc_b.embeddings, enc_a.offsets, enc_a.per_level_scale,
-                                     enc_a.base_resolution, enc_a.gridtype_id, enc_a.align_corners, style)
+                                     enc_a.base_resolution, enc_a.gridtype_id, enc_a.align_corners, style, xform)
     return o0.view(prefix_shape + [enc_a.output_dim]), o1.view(prefix_shape + [enc_b.output_dim])
 
 

@@ -89,13 +89,22 @@ class StyleTCNerf(nn.Module):
         return self.bbox_min.device
 
     def _forward(self, pts, dirs=None):
+        if self.fused_heads and pts.is_cuda and dirs is not None:
+            if self._dual is None:
+                self._dual = bool(same_geometry(self.x_density_embedder, self.x_color_embedder))
+                self._xform = torch.cat([self.bbox_min, self.bbox_size, self.bbox_min.new_ones(1)]).contiguous()
+            if self._dual and pts.dtype == torch.float32:
+                # one index computation for both hash tables; BBox.normalize + the encoder's input map run in the kernel
+                x_embedded, x_color_embedded = grid_encode_dual(pts, self.x_density_embedder, self.x_color_embedder,
+                                                                xform=self._xform)
+                sigmas = tcnn.density_head(x_embedded, self.density_net)
+                rgbs = tcnn.color_heads(x_color_embedded, self.class_net, self.color1_net, self.color2_net)
+                return rgbs, sigmas
         pts = (pts - self.bbox_min) / self.bbox_size            # BBox.normalize, common.py:288
         if self.fused_heads and pts.is_cuda:
             if dirs is None:
                 return tcnn.density_head(self.x_density_embedder(pts), self.density_net)
-            if self._dual is None:
-                self._dual = bool(same_geometry(self.x_density_embedder, self.x_color_embedder))
-            if self._dual:       # one index computation for both hash tables
+            if self._dual:
                 x_embedded, x_color_embedded = grid_encode_dual(pts, self.x_density_embedder, self.x_color_embedder)
             else:
                 x_embedded, x_color_embedded = self.x_density_embedder(pts), self.x_color_embedder(pts)
@@ -251,8 +260,12 @@ class Renderer(nn.Module):
         depth = torch.clamp(depth - nears, min=0) / (fars - nears)
         return image, depth, classes
 
-    def render_test(self, rays_o, rays_d, **kwargs):
-        """renderer.py:237-293"""
+    def render_test(self, rays_o, rays_d, sync_every=4, **kwargs):
+        """renderer.py:237-293.  sync_every = 1 is the reference's loop (the alive-ray count is read back every iteration,
+        `rays_alive[rays_alive >= 0]`, renderer.py:284).  sync_every = k > 1 compacts on the device and refreshes the
+        host-side count only every k-th iteration: in between, the list keeps its previous length with -1 in the dead
+        slots (march_rays / composite_rays skip them) and n_step is derived from the stale (larger) count.  n_step only
+        partitions a ray's samples over launches, so the image is the same; the loop sheds 1 - 1/k of its host syncs."""
         nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, self.aabb, self.min_near)
         N = rays_o.shape[0]
         weights_sum = torch.zeros(N, dtype=torch.float32, device=self.device)
@@ -262,8 +275,14 @@ class Renderer(nn.Module):
         rays_alive = torch.arange(n_alive, dtype=torch.int32, device=self.device)
         rays_t = nears.clone()[:, None]
         step = 0
+        it = 0
+        cnt = None
         while step < self.max_steps:
-            n_alive = len(rays_alive)
+            if sync_every <= 1:
+                n_alive = len(rays_alive)
+            elif cnt is not None and it % sync_every == 0:
+                n_alive = int(cnt.item())                 # the only host sync of the fast loop
+                rays_alive = rays_alive[:n_alive]
             if n_alive <= 0:
                 break
             n_step = max(min(N // n_alive, 8), 1)
@@ -274,8 +293,12 @@ class Renderer(nn.Module):
             sigmas = sigmas * self.density_scale
             raymarching.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, False, weights_sum,
                                        depth, image, self.t_thresh)
-            rays_alive = rays_alive[rays_alive >= 0]
+            if sync_every <= 1:
+                rays_alive = rays_alive[rays_alive >= 0]
+            else:
+                rays_alive, cnt = raymarching.compact_rays_alive_nosync(rays_alive)
             step += n_step
+            it += 1
         classes = image[:, 3:]
         image = image[:, :3]
         image = image + (1 - weights_sum).unsqueeze(-1)

@@ -12,7 +12,7 @@ from torch.amp import custom_bwd, custom_fwd
 from . import _lib as L
 
 __all__ = ['near_far_from_aabb', 'sph_from_ray', 'morton3D', 'morton3D_invert', 'packbits', 'march_rays_train',
-           'composite_rays_train', 'march_rays', 'composite_rays', 'march_rays_unbounded_train', 'compact_rays_alive']
+           'composite_rays_train', 'march_rays', 'composite_rays', 'march_rays_unbounded_train', 'compact_rays_alive', 'compact_rays_alive_nosync']
 
 
 def _cuda(t):
@@ -344,3 +344,23 @@ def compact_rays_alive(rays_alive):
                                       L.stream_of(rays_alive)), 'compact_alive')
     k = int(cnt.item())
     return out[:k], k
+
+
+def compact_rays_alive_nosync(rays_alive, out=None, cnt=None):
+    """Same compaction WITHOUT the read-back: returns (out, cnt) where out has the input's length, its first cnt[0]
+    entries are the surviving ray ids in order and the rest are -1 (dead slots, skipped by march_rays /
+    composite_rays); cnt is a device int32[1].  Lets an inference loop refresh its host-side ray count only every few
+    iterations."""
+    rays_alive = rays_alive.contiguous()
+    L.require_cuda(rays_alive)
+    n = rays_alive.shape[0]
+    if out is None:
+        out = torch.empty_like(rays_alive)
+    if cnt is None:
+        cnt = torch.empty(1, dtype=torch.int32, device=rays_alive.device)
+    lib = L.lib()
+    scratch = L.scratch(rays_alive.device, lib.nrf_march_scratch_bytes(n))
+    with torch.cuda.device(rays_alive.device):
+        L.check(lib.nrf_compact_alive(L.ptr(rays_alive), n, L.ptr(out), L.ptr(cnt), L.ptr(scratch),
+                                      L.stream_of(rays_alive)), 'compact_alive')
+    return out, cnt

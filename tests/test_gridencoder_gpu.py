@@ -201,3 +201,21 @@ def test_dual_equals_two_single_passes(cuda_lib, dev, amp):
             a, b = res[0][k], res[1][k]
             assert a.dtype == torch.float32
             assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
+
+
+def test_dual_input_transform_is_bit_exact(cuda_lib, dev):
+    """xform folds BBox.normalize and the encoder's input map into the kernel: same f32 operations -> same bits."""
+    from nerfstyle_b200.gridencoder import grid_encode_dual
+    ea, eb = _default_encoder(dev, 1), _default_encoder(dev, 2)
+    x = _points(9001, 3, dev, -2.2, 2.2)                       # some points outside the box
+    bmin = torch.tensor([-2., -2., -2.], device=dev)
+    bsize = torch.tensor([4., 4., 4.], device=dev)
+    xf = torch.cat([bmin, bsize, torch.ones(1, device=dev)])
+    a0, a1 = grid_encode_dual(x, ea, eb, xform=xf)
+    b0, b1 = grid_encode_dual((x - bmin) / bsize, ea, eb)
+    assert torch.equal(a0, b0) and torch.equal(a1, b1)
+    bsize2 = torch.tensor([3.7, 4.1, 4.9], device=dev)          # non-power-of-two sizes: true division per axis
+    xf2 = torch.cat([bmin, bsize2, torch.ones(1, device=dev)])
+    c0, _ = grid_encode_dual(x, ea, eb, xform=xf2)
+    d0, _ = grid_encode_dual((x - bmin) / bsize2, ea, eb)
+    assert torch.equal(c0, d0)

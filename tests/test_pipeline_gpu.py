@@ -97,6 +97,24 @@ def test_render_test_matches_render_train(cuda_lib, dev):
     torch.testing.assert_close(a_cls, b_cls, rtol=1e-3, atol=1e-4)
 
 
+def test_render_test_sync_light_loop_equals_reference_loop(cuda_lib, dev):
+    """sync_every > 1 (device-side compaction with dead slots, host count refreshed every k iterations) renders the same
+    image as the reference's loop (count read back every iteration), with early termination active."""
+    of, m, r, o, d, bits = _build(dev, half_tables=False, n_rays=3000, table_std=0.5)
+    r.density_scale = 20.0
+    with torch.no_grad():
+        a = r.render_test(o, d, sync_every=1)
+        for k in (2, 4, 7):
+            b = r.render_test(o, d, sync_every=k)
+            for x, y in zip(a, b):
+                torch.testing.assert_close(x, y, rtol=1e-6, atol=1e-7)
+    # the compaction primitive itself: survivors in order, -1 tail, device-side count
+    from nerfstyle_b200 import raymarching
+    v = torch.tensor([5, -1, 7, -1, -1, 9, 11], dtype=torch.int32, device=dev)
+    out, cnt = raymarching.compact_rays_alive_nosync(v)
+    assert out.tolist() == [5, 7, 9, 11, -1, -1, -1] and int(cnt) == 4
+
+
 def test_update_state_and_steps(cuda_lib, dev):
     """Occupancy update + a few optimiser steps run end to end and reduce the loss."""
     from nerfstyle_b200 import model as M, scenes
