@@ -34,12 +34,21 @@ class FusedAdamEMA:
         # fp16 shadow copies of the big tables, registered on the parameter for GridEncoder to find
         self.half = []
         for p in self.params:
-            if enable_amp and p.numel() >= half_copy_min_numel:
+            # big tensors (hash tables): fp16 copy only under AMP; small ones (the MLPs' flat params): always -- the
+            # tensor-core kernels consume fp16 weights in every mode (nerfstyle_b200.tcnn.half_params)
+            if (enable_amp and p.numel() >= half_copy_min_numel) or p.numel() < half_copy_min_numel:
                 h = p.detach().to(torch.float16)
                 p._nrf_half_copy = h
                 self.half.append(h)
             else:
                 self.half.append(None)
+
+    @torch.no_grad()
+    def refresh_half_copies(self):
+        """Call after writing the parameters by any other means (loading a checkpoint, swapping in the EMA weights)."""
+        for p, h in zip(self.params, self.half):
+            if h is not None:
+                h.copy_(p.detach())
 
     def scale_loss(self, loss):
         return loss * self.scale if self.enable_amp else loss

@@ -33,13 +33,13 @@ def _pad16(n):
 
 class _mlp_function(Function):
     @staticmethod
-    def forward(ctx, x, params, cfg):
+    def forward(ctx, x, params, cfg, owner=None):
         n_in, n_out, n_hidden, width, hidden_act, out_act, loss_scale = cfg
         L.require_cuda(x, params)
         if x.dtype not in (torch.float16, torch.float32):
             x = x.float()
         x = x.contiguous()
-        params_h = params.detach().to(torch.float16).contiguous()
+        params_h = half_params(params, owner)
         B = x.shape[0]
         y = torch.empty(B, n_out, dtype=torch.float16, device=x.device)
         with torch.cuda.device(x.device):
@@ -68,7 +68,23 @@ class _mlp_function(Function):
                                                  L.dtype_code(dy.dtype), B, n_in, n_out, n_hidden, width, hidden_act,
                                                  out_act, float(loss_scale), L.ptr(dx), L.dtype_code(x.dtype),
                                                  L.ptr(dparams), L.stream_of(x)), 'mlp_backward')
-        return dx, dparams, None
+        return dx, dparams, None, None
+
+
+def half_params(params, owner=None):
+    """fp16 copy of a flat parameter vector for the kernels.  FusedAdamEMA keeps one current on the parameter
+    (`_nrf_half_copy`, written by the optimizer kernel); otherwise the cast is cached on `owner` until the parameter's
+    version counter or storage changes (inference loops call the networks hundreds of times per frame)."""
+    h = getattr(params, '_nrf_half_copy', None)
+    if h is not None:
+        return h
+    if owner is None:
+        return params.detach().to(torch.float16).contiguous()
+    key = (params._version, params.data_ptr())
+    if getattr(owner, '_half_key', None) != key:
+        owner._half = params.detach().to(torch.float16).contiguous()
+        owner._half_key = key
+    return owner._half
 
 
 def _fwd_ex(net, x, params_h, y, col, n_out, out_act):
@@ -95,7 +111,7 @@ class _density_head(Function):
     def forward(ctx, enc, params, net):
         L.require_cuda(enc, params)
         enc = enc.contiguous()
-        params_h = params.detach().to(torch.float16).contiguous()
+        params_h = half_params(params, net)
         y = torch.empty(enc.shape[0], 1, dtype=torch.float32, device=enc.device)
         with torch.cuda.device(enc.device):
             _fwd_ex(net, enc, params_h, y, 0, 1, L.ACT['trunc_exp'])
@@ -130,7 +146,7 @@ class _color_heads(Function):
         enc = enc.contiguous()
         B = enc.shape[0]
         K = class_net.n_output_dims
-        hp = [p.detach().to(torch.float16).contiguous() for p in (p_class, p_c1, p_c2)]
+        hp = [half_params(p, n) for p, n in ((p_class, class_net), (p_c1, color1_net), (p_c2, color2_net))]
         c1 = torch.empty(B, color1_net.n_output_dims, dtype=torch.float16, device=enc.device)
         rgbs = torch.empty(B, 3 + K, dtype=torch.float32, device=enc.device)
         with torch.cuda.device(enc.device):
@@ -230,7 +246,7 @@ class Network(nn.Module):
         cfg = (self.n_input_dims, self.n_output_dims, self.n_hidden_layers, self.n_neurons, self.hidden_act,
                self.out_act, self.loss_scale)
         lead = x.shape[:-1]
-        y = _mlp_function.apply(x.reshape(-1, self.n_input_dims), self.params, cfg)
+        y = _mlp_function.apply(x.reshape(-1, self.n_input_dims), self.params, cfg, self)
         return y.view(*lead, self.n_output_dims)
 
     def extra_repr(self):

@@ -184,4 +184,5 @@ def test_fused_optimizer_matches_torch(cuda_lib, dev):
         torch.testing.assert_close(f, e, rtol=2e-5, atol=2e-6)
     assert int(fused.good_steps.item()) == 8
     torch.testing.assert_close(pa[0]._nrf_half_copy.float(), pa[0].detach().half().float())
-    assert not hasattr(pa[1], '_nrf_half_copy')
+    for p in pa[1:]:       # the small (MLP-sized) tensors keep a current fp16 copy in every mode
+        torch.testing.assert_close(p._nrf_half_copy.float(), p.detach().half().float())
