@@ -454,13 +454,14 @@ k_grid_bwd_d3c2(const T* __restrict__ grad0, const T* __restrict__ grad1, const 
         // steps for 1-2 runs; fine levels: 0-2 steps).
         bool agg = false;
         int lo = lane, hi = lane, maxlen = 1;
+        uint32_t cellmask = 1u << lane;
         if (agg_max_groups > 0) {
             const unsigned long long key = active ? (((unsigned long long)cz << 42) | ((unsigned long long)cy << 21) | (unsigned long long)cx)
                                                   : (0xFFFFFFFF00000000ull | (unsigned)lane);
-            const uint32_t mask = __match_any_sync(NRF_FULL_MASK, key);
-            lo = __ffs(mask) - 1; hi = 31 - __clz(mask);
+            cellmask = __match_any_sync(NRF_FULL_MASK, key);
+            lo = __ffs(cellmask) - 1; hi = 31 - __clz(cellmask);
             const uint32_t span = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
-            agg = __all_sync(NRF_FULL_MASK, mask == span);
+            agg = __all_sync(NRF_FULL_MASK, cellmask == span);
             if (agg) maxlen = (int)__reduce_max_sync(NRF_FULL_MASK, (unsigned)(hi - lo + 1));
         }
 #pragma unroll
@@ -476,6 +477,10 @@ k_grid_bwd_d3c2(const T* __restrict__ grad0, const T* __restrict__ grad1, const 
                     g0 = gg.x; g1 = gg.y;
                 }
             }
+            // exact zeros add nothing: samples behind an early-terminated ray arrive here with all-zero gradients
+            // (composite_rays_train backward never writes them) and are skipped instead of costing 8 reductions each
+            const uint32_t nzmask = __ballot_sync(NRF_FULL_MASK, g0 != 0.0f || g1 != 0.0f);
+            if (nzmask == 0u) continue;
             TO* gl = (e == 0 ? grad_table0 : grad_table1) + (size_t)p.offset * 2;
             float v0[8], v1[8];
 #pragma unroll
@@ -490,8 +495,8 @@ k_grid_bwd_d3c2(const T* __restrict__ grad0, const T* __restrict__ grad1, const 
                         if (take) { v0[k] += o0; v1[k] += o1; }
                     }
                 }
-                if (active && lane == lo) scatter_cell<TO>(gl, rows, v0, v1);
-            } else if (active) {
+                if (active && lane == lo && (nzmask & cellmask)) scatter_cell<TO>(gl, rows, v0, v1);
+            } else if (active && ((nzmask >> lane) & 1u)) {
                 scatter_cell<TO>(gl, rows, v0, v1);
             }
         }

@@ -219,3 +219,22 @@ def test_dual_input_transform_is_bit_exact(cuda_lib, dev):
     c0, _ = grid_encode_dual(x, ea, eb, xform=xf2)
     d0, _ = grid_encode_dual((x - bmin) / bsize2, ea, eb)
     assert torch.equal(c0, d0)
+
+
+def test_backward_skips_exact_zero_gradients(cuda_lib, oracle, dev):
+    """Rows whose gradient is exactly zero (samples behind an early-terminated ray) are skipped by the scatter; the
+    table gradient is unchanged: whole warps of zeros, zeros inside aggregated runs, and zeros in one channel only."""
+    enc = _default_encoder(dev)
+    B = 6016
+    t = torch.linspace(0, 1, B, device=dev)[:, None]
+    x = torch.tensor([[-0.9, -0.7, 0.3]], device=dev) + t * torch.tensor([[1.7, 1.1, 0.4]], device=dev)
+    out = enc(x)
+    grad = torch.randn(out.shape, generator=torch.Generator().manual_seed(1)).to(dev)
+    grad[1000:3000] = 0            # whole warps
+    grad[3001:3500:3] = 0          # scattered rows inside runs
+    grad[4000:4500, 0::2] = 0      # one channel of every level
+    out.backward(grad)
+    ege = oracle.grid_encode_backward(grad.cpu().numpy(), ((x + 1) / 2).cpu().numpy(), enc.offsets.cpu().numpy(),
+                                      enc.embeddings.shape[0], 2, enc.per_level_scale, 16, 0, True, 0)
+    ge = enc.embeddings.grad.cpu().numpy()
+    assert np.abs(ge - ege).max() <= 1e-5 * np.abs(ege).max()

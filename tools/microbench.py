@@ -100,13 +100,13 @@ def bench_grid(xyzs):
         # dual (two tables, one index computation) and the paired 16-byte reductions
         emb2, out2, ge2, grad2 = emb.clone(), torch.empty_like(out), torch.zeros_like(ge), grad.clone()
         t = timeit(lambda: lib.nrf_grid_encode_forward_dual(pts.data_ptr(), emb.data_ptr(), emb2.data_ptr(), enc.offsets.data_ptr(),
-                                                            out.data_ptr(), out2.data_ptr(), B, 16, S, 16, 0, 1, 0, dt, st))
+                                                            out.data_ptr(), out2.data_ptr(), B, 16, S, 16, 0, 1, 0, dt, None, st))
         print('grid fwd DUAL half=%d: %.3f ms for two encoders  (%.0f GB/s algorithmic)' % (half, t, 2 * B * fb / t / 1e6))
         for pr in (0,):
             t1 = timeit(lambda: lib.nrf_grid_encode_backward(grad.data_ptr(), pts.data_ptr(), None, enc.offsets.data_ptr(),
                                                              ge.data_ptr(), B, 3, 2, 16, S, 16, 0, None, None, 0, 1, 0, dt, 0, 1, st))
             t2 = timeit(lambda: lib.nrf_grid_encode_backward_dual(grad.data_ptr(), grad2.data_ptr(), pts.data_ptr(), enc.offsets.data_ptr(),
-                                                                  ge.data_ptr(), ge2.data_ptr(), B, 16, S, 16, 0, 1, 0, dt, 0, st))
+                                                                  ge.data_ptr(), ge2.data_ptr(), B, 16, S, 16, 0, 1, 0, dt, 0, None, st))
             print('grid bwd  half=%d (%d): single %.3f ms (%.0f GB/s)   DUAL %.3f ms for two encoders (%.0f GB/s)' % (
                 half, pr, t1, B * bb / t1 / 1e6, t2, 2 * B * bb / t2 / 1e6))
 
