@@ -27,7 +27,10 @@
 
 namespace {
 
-constexpr uint32_t CH = 2048;    // chunk stride of 128-row activation tiles
+// chunk stride of 128-row activation tiles: 2048 B of rows + a pad that makes the warp-cooperative (coalesced) staging of
+// the input rows bank-conflict free (chunk c of row r lands in bank 4 (r + c * pad / 16) mod 32: the pad spreads the
+// in/8 chunks of one row over distinct banks; row-owner accesses -- 512 contiguous bytes per chunk -- never conflict)
+__host__ __device__ constexpr uint32_t ch_for(int in_kt) { return in_kt == 1 ? 2112u : in_kt == 2 ? 2080u : 2064u; }
 constexpr uint32_t CHW = 1024;   // chunk stride of 64-row weight tiles (W1, Wh)
 constexpr uint32_t CHO = 256;    // chunk stride of the 16-row output weight tile
 constexpr int TC_ROWS = 128;     // row-owner threads (warps 0-3)
@@ -82,6 +85,41 @@ __device__ __forceinline__ uint4 load_chunk(const void* __restrict__ base, int d
         for (int j = 0; j < 8; j++) v[j] = (8 * c + j < n) ? p[j] : 0.0f;
     }
     return make_uint4(tpack(v[0], v[1]), tpack(v[2], v[3]), tpack(v[4], v[5]), tpack(v[6], v[7]));
+}
+
+// The input rows of a 128-row tile -> registers -> the chunked shared-memory tile.  coal: warp-cooperative mapping over
+// the warp's 32 rows x CPR chunks (piece i * 32 + lane: consecutive lanes read consecutive 16-byte pieces of global
+// memory -- 4 cache lines per request instead of 16 for the row-owner mapping; ncu showed the MLP kernels L1TEX-bound);
+// otherwise every thread reads its own row (f32 inputs, odd widths).
+template <int CPR>
+__device__ __forceinline__ void load_x_tile(uint4 (&xr)[CPR], const void* __restrict__ x, int x_dt, size_t tile_row0, bool tile_ok, uint32_t B,
+                                            uint32_t n_in, bool x_vec, bool coal, int warp, int lane, int tid) {
+    if (coal) {
+#pragma unroll
+        for (int i = 0; i < CPR; i++) {
+            const int idx = i * 32 + lane, r = idx / CPR, c = idx - r * CPR;
+            const size_t row = tile_row0 + warp * 32 + r;
+            xr[i] = (tile_ok && row < B) ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(x) + row * n_in) + c)
+                                         : make_uint4(0u, 0u, 0u, 0u);
+        }
+    } else {
+        const size_t row = tile_row0 + tid;
+#pragma unroll
+        for (int c = 0; c < CPR; c++) xr[c] = load_chunk(x, x_dt, row, c, n_in, tile_ok && row < B, x_vec);
+    }
+}
+template <int CPR>
+__device__ __forceinline__ void stage_x_tile(const uint4 (&xr)[CPR], uint8_t* sX, uint32_t CH, bool coal, int warp, int lane, int tid) {
+    if (coal) {
+#pragma unroll
+        for (int i = 0; i < CPR; i++) {
+            const int idx = i * 32 + lane, r = idx / CPR, c = idx - r * CPR;
+            *reinterpret_cast<uint4*>(sX + c * CH + (warp * 32 + r) * 16) = xr[i];
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < CPR; c++) *reinterpret_cast<uint4*>(sX + c * CH + tid * 16) = xr[c];
+    }
 }
 
 // 8 consecutive f32 values -> columns [8c, 8c+8) of row `row` of a row-major matrix with n columns and row stride ld
@@ -189,7 +227,7 @@ __device__ __forceinline__ void stage_weight(uint8_t* dst, uint32_t ch, const __
 // forward hidden-layer epilogue: 64 f32 accumulator columns of this thread's row -> f16 -> relu -> chunks of `dst_row`.
 // relu is applied AFTER the rounding on packed halfs (rounding is monotonic and sign-preserving: same result, half the
 // instructions: one cvt.rn.f16x2.f32 + one HMNMX2 per pair of columns).
-__device__ __forceinline__ void hidden_fwd_epilogue(uint32_t tacc_lane, uint8_t* dst_row, bool relu) {
+__device__ __forceinline__ void hidden_fwd_epilogue(uint32_t tacc_lane, uint8_t* dst_row, bool relu, uint32_t CH) {
     const __half2 zero = __float2half2_rn(0.0f);
 #pragma unroll
     for (int half = 0; half < 2; half++) {
@@ -212,7 +250,7 @@ __device__ __forceinline__ void hidden_fwd_epilogue(uint32_t tacc_lane, uint8_t*
 
 // backward hidden-layer epilogue: dH = round_f16(acc) masked by relu'(h), where h is this row of the recomputed
 // activation tile in shared memory (h > 0 <=> pre-activation > 0): one cvt + one HSET2 + one LOP3 per pair of columns.
-__device__ __forceinline__ void hidden_bwd_epilogue(uint32_t tacc_lane, const uint8_t* h_row, uint8_t* dst_row, bool relu) {
+__device__ __forceinline__ void hidden_bwd_epilogue(uint32_t tacc_lane, const uint8_t* h_row, uint8_t* dst_row, bool relu, uint32_t CH) {
     const __half2 zero = __float2half2_rn(0.0f);
 #pragma unroll
     for (int half = 0; half < 2; half++) {
@@ -254,6 +292,7 @@ struct TcSmem { uint32_t W1, Wh, Wo, X, H1, H2, dZ, dH1, dH2, total; };
 
 template <int IN_KT, int NH>
 __host__ __device__ constexpr TcSmem fwd_smem() {
+    constexpr uint32_t CH = ch_for(IN_KT);
     TcSmem s{};
     uint32_t o = 0;
     s.W1 = o; o += IN_KT * 2 * CHW;
@@ -268,6 +307,7 @@ __host__ __device__ constexpr TcSmem fwd_smem() {
 //   NH=1:  [X | dZ]  and  [dH1 | H1]          NH=2:  [X | H1]  and  [dH1 | dH2]
 template <int IN_KT, int NH>
 __host__ __device__ constexpr TcSmem bwd_smem() {
+    constexpr uint32_t CH = ch_for(IN_KT);
     TcSmem s{};
     uint32_t o = 0;
     s.W1 = o; o += IN_KT * 2 * CHW;
@@ -297,6 +337,8 @@ __global__ void __launch_bounds__(TC_THREADS, 5)
 k_mlp_fwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ params, uint32_t B, uint32_t n_in, uint32_t n_out,
              int hidden_act, int out_act, void* __restrict__ y, int y_dt, uint32_t ld_y) {
     constexpr int IN_PAD = IN_KT * 16;
+    constexpr int CPR = IN_PAD / 8;                      // 16-byte chunks per input row
+    constexpr uint32_t CH = ch_for(IN_KT);
     constexpr TcSmem L = fwd_smem<IN_KT, NH>();
     constexpr uint32_t TCOLS = 64;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -351,31 +393,23 @@ k_mlp_fwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ pa
         // whose exp is evaluated in f32 on the f16-rounded pre-activation (tcnn_nerf.py:55-62)
         const bool round_y = y_dt == NRF_DTYPE_F32 && out_act != NRF_ACT_TRUNC_EXP;
         uint32_t phase = 0;
-        uint8_t* xrow = smem + L.X + tid * 16;
         uint8_t* hrow = smem + L.H1 + tid * 16;
-        uint4 xr[IN_PAD / 8];
-        {
-            const size_t row0 = (size_t)blockIdx.x * 128 + tid;
-#pragma unroll
-            for (int c = 0; c < IN_PAD / 8; c++) xr[c] = load_chunk(x, x_dt, row0, c, n_in, row0 < B, x_vec);
-        }
+        const bool coal = x_vec && x_dt == NRF_DTYPE_F16 && n_in == (uint32_t)IN_PAD;
+        uint4 xr[CPR];
+        load_x_tile<CPR>(xr, x, x_dt, (size_t)blockIdx.x * 128, true, B, n_in, x_vec, coal, warp, lane, tid);
         for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const size_t row = (size_t)tile * 128 + tid;
             const bool row_ok = row < B;
-#pragma unroll
-            for (int c = 0; c < IN_PAD / 8; c++) *reinterpret_cast<uint4*>(xrow + c * CH) = xr[c];
+            stage_x_tile<CPR>(xr, smem + L.X, CH, coal, warp, lane, tid);
             publish(&bar_ready);
             {   // prefetch the next tile's rows (in flight until the top of the next iteration)
                 const uint32_t nt = tile + gridDim.x;
-                const size_t nrow = (size_t)nt * 128 + tid;
-                const bool nok = nt < ntiles && nrow < B;
-#pragma unroll
-                for (int c = 0; c < IN_PAD / 8; c++) xr[c] = load_chunk(x, x_dt, nrow, c, n_in, nok, x_vec);
+                load_x_tile<CPR>(xr, x, x_dt, (size_t)nt * 128, nt < ntiles, B, n_in, x_vec, coal, warp, lane, tid);
             }
 #pragma unroll
             for (int l = 0; l < NH; l++) {
                 tc05::mbar_wait(&bar_done, phase); phase ^= 1; tc05::fence_after_sync();
-                hidden_fwd_epilogue(tacc_lane, hrow, relu);
+                hidden_fwd_epilogue(tacc_lane, hrow, relu, CH);
                 publish(&bar_ready);
             }
             tc05::mbar_wait(&bar_done, phase); phase ^= 1; tc05::fence_after_sync();
@@ -417,6 +451,8 @@ k_mlp_bwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ pa
              uint32_t ld_dy, uint32_t B, uint32_t n_in, uint32_t n_out, int hidden_act, int out_act, float loss_scale,
              void* __restrict__ dx, int dx_accumulate, float* __restrict__ dparams, unsigned long long* __restrict__ prof) {
     constexpr int IN_PAD = IN_KT * 16;
+    constexpr int CPR = IN_PAD / 8;                      // 16-byte chunks per input row
+    constexpr uint32_t CH = ch_for(IN_KT);
     constexpr TcSmem L = bwd_smem<IN_KT, NH>();
     constexpr uint32_t TCOLS = bwd_tmem_cols<IN_KT, NH>();
     constexpr uint32_t NS = IN_PAD + (NH == 1 ? 16 : 64);       // N of the stacked weight-gradient product
@@ -529,7 +565,7 @@ k_mlp_bwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ pa
         const float inv_scale = 1.0f / loss_scale;
         uint32_t phase = 0, phase_w = 0;
         bool first = true;
-        uint8_t* const xrow = smem + L.X + tid * 16;
+        const bool coal = x_vec && x_dt == NRF_DTYPE_F16 && n_in == (uint32_t)IN_PAD;
         uint8_t* const h1row = smem + L.H1 + tid * 16;
         uint8_t* const h2row = smem + L.H2 + tid * 16;
         uint8_t* const dzrow = smem + L.dZ + tid * 16;
@@ -539,12 +575,11 @@ k_mlp_bwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ pa
         uint8_t* const dhlastrow = (NH == 2) ? dh2row : dh1row;
 
         // software pipeline: rows of tile i+1 are fetched from HBM while tile i is processed
-        uint4 xr[IN_PAD / 8];
+        uint4 xr[CPR];
         uint32_t dyraw[16];
         {
             const size_t row0 = (size_t)blockIdx.x * 128 + tid;
-#pragma unroll
-            for (int c = 0; c < IN_PAD / 8; c++) xr[c] = load_chunk(x, x_dt, row0, c, n_in, row0 < B, x_vec);
+            load_x_tile<CPR>(xr, x, x_dt, (size_t)blockIdx.x * 128, true, B, n_in, x_vec, coal, warp, lane, tid);
             dy_load_raw(dy, dy_dt, row0, n_out, ld_dy, row0 < B, dy_vec, dyraw);
         }
         for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -555,8 +590,7 @@ k_mlp_bwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ pa
             PROF_MARK(0);
             if (!first) { tc05::mbar_wait(&bar_wdone, phase_w); phase_w ^= 1; }      // operand tiles are free again
             PROF_MARK(1);      // previous tile's weight-gradient MMAs done
-#pragma unroll
-            for (int c = 0; c < IN_PAD / 8; c++) *reinterpret_cast<uint4*>(xrow + c * CH) = xr[c];
+            stage_x_tile<CPR>(xr, smem + L.X, CH, coal, warp, lane, tid);
             if (linear_out) {
                 *reinterpret_cast<uint4*>(dzrow) = make_uint4(dyc[0], dyc[1], dyc[2], dyc[3]);
                 *reinterpret_cast<uint4*>(dzrow + CH) = make_uint4(dyc[4], dyc[5], dyc[6], dyc[7]);
@@ -566,19 +600,18 @@ k_mlp_bwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ pa
                 const uint32_t nt = tile + gridDim.x;
                 const size_t nrow = (size_t)nt * 128 + tid;
                 const bool nok = nt < ntiles && nrow < B;
-#pragma unroll
-                for (int c = 0; c < IN_PAD / 8; c++) xr[c] = load_chunk(x, x_dt, nrow, c, n_in, nok, x_vec);
+                load_x_tile<CPR>(xr, x, x_dt, (size_t)nt * 128, nt < ntiles, B, n_in, x_vec, coal, warp, lane, tid);
                 dy_load_raw(dy, dy_dt, nrow, n_out, ld_dy, nok, dy_vec, dyraw);
             }
             PROF_MARK(2);      // operands staged, prefetch issued
             tc05::mbar_wait(&bar_done, phase); phase ^= 1; tc05::fence_after_sync();
             PROF_MARK(3);      // H1 MMA round trip
-            hidden_fwd_epilogue(tacc_lane, h1row, relu);
+            hidden_fwd_epilogue(tacc_lane, h1row, relu, CH);
             publish(&bar_ready);
             PROF_MARK(4);      // H1 epilogue
             if constexpr (NH == 2) {
                 tc05::mbar_wait(&bar_done, phase); phase ^= 1; tc05::fence_after_sync();
-                hidden_fwd_epilogue(tacc_lane, h2row, relu);
+                hidden_fwd_epilogue(tacc_lane, h2row, relu, CH);
                 publish(&bar_ready);
             }
             PROF_MARK(5);      // H2 round trip + epilogue
@@ -606,12 +639,12 @@ k_mlp_bwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ pa
             }
             tc05::mbar_wait(&bar_done, phase); phase ^= 1; tc05::fence_after_sync();
             PROF_MARK(8);      // dHlast MMA round trip
-            hidden_bwd_epilogue(tacc_lane, hlastrow, dhlastrow, relu);
+            hidden_bwd_epilogue(tacc_lane, hlastrow, dhlastrow, relu, CH);
             publish(&bar_ready);
             PROF_MARK(9);      // dHlast epilogue
             if constexpr (NH == 2) {
                 tc05::mbar_wait(&bar_done, phase); phase ^= 1; tc05::fence_after_sync();
-                hidden_bwd_epilogue(tacc_lane, h1row, dh1row, relu);
+                hidden_bwd_epilogue(tacc_lane, h1row, dh1row, relu, CH);
                 publish(&bar_ready);
             }
             tc05::mbar_wait(&bar_done, phase); phase ^= 1; tc05::fence_after_sync();
