@@ -216,6 +216,10 @@ int nrf_mlp_backward_ex(const void* x, int x_dtype, const void* params_f16, cons
                         uint32_t width, int hidden_act, int out_act, float loss_scale, void* dx, int dx_dtype,
                         int dx_accumulate, float* dparams, void* stream);
 
+/* tcnn.Encoding {'otype': 'SphericalHarmonics', 'degree': d} (networks/style_nerf.py:33-42, tcnn_nerf.py:87-95), d <= 4:
+ * inputs01 [B,3] f32 in [0,1] (mapped to [-1,1] inside, as tiny-cuda-nn does) -> outputs [B, d*d] (f16 or f32). */
+int nrf_sh_encode_forward(const float* inputs01, uint32_t B, uint32_t degree, void* outputs, int out_dtype, void* stream);
+
 /* ------------------------------------------------------------------ nearest-neighbour feature matching */
 
 /* loss.py:32-36,199-214.  a [N1,K] f16 (rows already L2-normalised), b [N2,K] f16 (normalised);

@@ -571,3 +571,53 @@ NRF_EXPORT int nrf_mlp_backward_ex(const void* x, int x_dtype, const void* param
 #undef BWD_CASE
     return NRF_E_UNSUPPORTED;
 }
+
+// ------------------------------------------------------------------------------------------------
+// tcnn.Encoding 'SphericalHarmonics' (networks/style_nerf.py:33-42, networks/tcnn_nerf.py:87-95; use_dir=True models)
+// ------------------------------------------------------------------------------------------------
+// tiny-cuda-nn is un-vendored; this restates its published real-SH basis (degree <= 4; the reference's dir_enc_sh_deg is 4):
+// inputs in [0,1]^3 are mapped to [-1,1]^3 (x*2-1) and evaluated as polynomials.  Forward only: the encoding has no
+// parameters and ray directions never carry gradients on this path.
+template <typename OT>
+__global__ void k_sh_encode(const float* __restrict__ in, uint32_t B, uint32_t degree, OT* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const float x = __ldg(in + 3 * (size_t)i) * 2.0f - 1.0f, y = __ldg(in + 3 * (size_t)i + 1) * 2.0f - 1.0f, z = __ldg(in + 3 * (size_t)i + 2) * 2.0f - 1.0f;
+    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+    float o[16];
+    o[0] = 0.28209479177387814f;
+    o[1] = -0.48860251190291987f * y;
+    o[2] = 0.48860251190291987f * z;
+    o[3] = -0.48860251190291987f * x;
+    o[4] = 1.0925484305920792f * xy;
+    o[5] = -1.0925484305920792f * yz;
+    o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+    o[7] = -1.0925484305920792f * xz;
+    o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+    o[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+    o[10] = 2.8906114426405538f * xy * z;
+    o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+    o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+    o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+    o[14] = 1.4453057213202769f * z * (x2 - y2);
+    o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+    const uint32_t n = degree * degree;
+    OT* dst = out + (size_t)i * n;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if ((uint32_t)k < n) {
+            if constexpr (sizeof(OT) == 2) dst[k] = __float2half_rn(o[k]); else dst[k] = o[k];
+        }
+    }
+}
+
+NRF_EXPORT int nrf_sh_encode_forward(const float* inputs01, uint32_t B, uint32_t degree, void* outputs, int out_dtype, void* stream) {
+    if (B == 0) return NRF_OK;
+    if (!inputs01 || !outputs) return NRF_E_INVALID;
+    if (degree < 1 || degree > 4) return NRF_E_UNSUPPORTED;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (out_dtype == NRF_DTYPE_F16) k_sh_encode<__half><<<ceil_div_u32(B, 256), 256, 0, s>>>(inputs01, B, degree, (__half*)outputs);
+    else if (out_dtype == NRF_DTYPE_F32) k_sh_encode<float><<<ceil_div_u32(B, 256), 256, 0, s>>>(inputs01, B, degree, (float*)outputs);
+    else return NRF_E_UNSUPPORTED;
+    return nrf_check_launch();
+}

@@ -255,12 +255,36 @@ class Network(nn.Module):
 
 
 class Encoding(nn.Module):
-    """tcnn.Encoding look-alike.  Only needed when the model is built with use_dir=True (SphericalHarmonics,
-    networks/style_nerf.py:33-42), which no shipped trainer / renderer does (trainers/base.py:149-151); see
-    SURVEY.md 8f NEXT-3."""
+    """tcnn.Encoding look-alike for {'otype': 'SphericalHarmonics', 'degree': d <= 4} (networks/style_nerf.py:33-42,
+    networks/tcnn_nerf.py:87-95; only built when the model uses view directions).  Inputs in [0,1]^3 (the callers map
+    directions with (d + 1) / 2), output `dtype` [B, d*d].  The encoding has no parameters (`params` is empty, as in
+    tinycudann) and is forward-only: ray directions never carry gradients on this path."""
 
     def __init__(self, n_input_dims, encoding_config, seed=1337, dtype=None):
         super().__init__()
-        raise NotImplementedError(
-            'nerfstyle_b200.tcnn.Encoding(%r) is not implemented yet (off the default path; SURVEY.md 8f NEXT-3)'
-            % (encoding_config.get('otype'),))
+        otype = encoding_config.get('otype')
+        if otype != 'SphericalHarmonics':
+            raise NotImplementedError('nerfstyle_b200.tcnn.Encoding: only SphericalHarmonics is implemented (got %r)' % (otype,))
+        if int(n_input_dims) != 3:
+            raise RuntimeError('nerfstyle_b200.tcnn.Encoding(SphericalHarmonics) needs n_input_dims = 3')
+        self.n_input_dims = 3
+        self.degree = int(encoding_config.get('degree', 4))
+        if not 1 <= self.degree <= 4:
+            raise RuntimeError('nerfstyle_b200.tcnn.Encoding(SphericalHarmonics): degree 1..4 supported')
+        self.n_output_dims = self.degree * self.degree
+        self.encoding_config = dict(encoding_config)
+        self.seed = seed
+        self.dtype = torch.float16 if dtype is None else dtype
+        self.params = nn.Parameter(torch.zeros(0), requires_grad=False)
+
+    def forward(self, x):
+        L.require_cuda(x)
+        if x.requires_grad:
+            raise NotImplementedError('nerfstyle_b200.tcnn.Encoding(SphericalHarmonics) is forward-only')
+        lead = x.shape[:-1]
+        xi = x.reshape(-1, 3).float().contiguous()
+        out = torch.empty(xi.shape[0], self.n_output_dims, dtype=self.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            L.check(L.lib().nrf_sh_encode_forward(L.ptr(xi), xi.shape[0], self.degree, L.ptr(out), L.dtype_code(self.dtype),
+                                                  L.stream_of(xi)), 'sh_encode_forward')
+        return out.view(*lead, self.n_output_dims)

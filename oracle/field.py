@@ -227,3 +227,22 @@ def train_step_loss(out, target_rgb, target_cls=None, class_lambda=0.001):
     if target_cls is not None:
         loss = loss + class_lambda * torch.nn.functional.cross_entropy(out['classes'], target_cls)
     return loss
+
+
+def sh_encode(dirs01, degree=4):
+    """tcnn 'SphericalHarmonics' encoding (tiny-cuda-nn is un-vendored and unpinned, README.md:25-26; call sites
+    networks/style_nerf.py:33-42, networks/tcnn_nerf.py:87-95).  Restates the published real spherical-harmonics basis:
+    inputs in [0,1]^3 -> [-1,1]^3, Y_lm as polynomials in (x, y, z), l < degree <= 4.  Pinned by the orthonormality of the
+    basis over the unit sphere (tests/test_oracle_kat.py), not by the reference (parity unpinned)."""
+    import numpy as np
+    d = np.asarray(dirs01, dtype=np.float64) * 2.0 - 1.0
+    x, y, z = d[:, 0], d[:, 1], d[:, 2]
+    xy, xz, yz, x2, y2, z2 = x * y, x * z, y * z, x * x, y * y, z * z
+    o = [np.full_like(x, 0.28209479177387814),
+         -0.48860251190291987 * y, 0.48860251190291987 * z, -0.48860251190291987 * x,
+         1.0925484305920792 * xy, -1.0925484305920792 * yz, 0.94617469575755997 * z2 - 0.31539156525251999,
+         -1.0925484305920792 * xz, 0.54627421529603959 * x2 - 0.54627421529603959 * y2,
+         0.59004358992664352 * y * (-3.0 * x2 + y2), 2.8906114426405538 * xy * z, 0.45704579946446572 * y * (1.0 - 5.0 * z2),
+         0.3731763325901154 * z * (5.0 * z2 - 3.0), 0.45704579946446572 * x * (1.0 - 5.0 * z2),
+         1.4453057213202769 * z * (x2 - y2), 0.59004358992664352 * x * (-x2 + 3.0 * y2)]
+    return np.stack(o[:degree * degree], axis=1)

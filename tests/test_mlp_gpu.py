@@ -102,3 +102,22 @@ def test_large_batch_many_tiles_per_cta(cuda_lib, dev):
     gp, egp = net.params.grad.cpu().numpy(), pc.grad.numpy()
     assert np.abs(gx - egx).max() <= 2e-2 * np.abs(egx).max()     # max over 3 M elements of fp16-rounded dH
     assert np.abs(gp - egp).max() <= 1e-2 * np.abs(egp).max()
+
+
+@pytest.mark.parametrize('degree', [1, 2, 3, 4])
+@pytest.mark.parametrize('dtype', [torch.float16, torch.float32])
+def test_sh_encoding(cuda_lib, dev, degree, dtype):
+    """tcnn.Encoding(SphericalHarmonics) against the oracle restatement (f32: 1e-6; f16: half an ulp of the output)."""
+    from nerfstyle_b200 import tcnn
+    from oracle import field
+    enc = tcnn.Encoding(3, {'otype': 'SphericalHarmonics', 'degree': degree}, dtype=dtype).to(dev)
+    assert enc.n_output_dims == degree * degree and enc.params.numel() == 0
+    g = torch.Generator().manual_seed(degree)
+    d = torch.nn.functional.normalize(torch.randn(5000, 3, generator=g), dim=1)
+    x = ((d + 1) / 2).to(dev)
+    out = enc(x)
+    assert out.shape == (5000, degree * degree) and out.dtype == dtype
+    ref = field.sh_encode(x.cpu().numpy(), degree)
+    err = np.abs(out.float().cpu().numpy() - ref)
+    tol = 2e-6 if dtype == torch.float32 else 2.0 ** -11 * np.maximum(np.abs(ref), 2.0 ** -14) + 1e-7
+    assert (err <= tol).all(), err.max()

@@ -211,3 +211,19 @@ def test_inference_loop_matches_train_march(oracle):
         alive = np.ascontiguousarray(alive[alive >= 0])
         step += n_step
     assert np.array_equal(emitted, rays[:, 2].astype(np.int64))
+
+
+def test_spherical_harmonics_basis_is_orthonormal():
+    """The SH restatement (oracle.field.sh_encode) is pinned by a closed-form property: the 16 basis functions are
+    orthonormal over the unit sphere (Gauss-Legendre in cos(theta) x uniform in phi integrates degree-6 polynomials exactly)."""
+    import numpy as np
+    from oracle import field
+    ct, wt = np.polynomial.legendre.leggauss(16)
+    phi = (np.arange(32) + 0.5) * (2 * np.pi / 32)
+    CT, PH = np.meshgrid(ct, phi, indexing='ij')
+    ST = np.sqrt(1 - CT ** 2)
+    d = np.stack([ST * np.cos(PH), ST * np.sin(PH), CT], axis=-1).reshape(-1, 3)
+    w = (wt[:, None] * np.full((1, 32), 2 * np.pi / 32)).reshape(-1)
+    Y = field.sh_encode((d + 1) / 2, 4)
+    G = (Y * w[:, None]).T @ Y
+    assert np.abs(G - np.eye(16)).max() < 1e-12
