@@ -117,7 +117,11 @@ def bernoulli_density_grid(cascade=2, H=128, p=0.5, seed=1):
 def frame_indices(intr, n_rays, generator):
     """A random subset of pixel ids without replacement (nerf_lib.py:134 uses np.random.choice)."""
     total = int(intr['w']) * int(intr['h'])
-    return torch.randperm(total, generator=generator)[:n_rays]
+    if n_rays <= total:
+        return torch.randperm(total, generator=generator)[:n_rays]
+    # more rays than pixels (ray-batch sweeps): whole extra permutations of the frame, so the batch really has n_rays rays
+    reps = -(-n_rays // total)
+    return torch.cat([torch.randperm(total, generator=generator) for _ in range(reps)])[:n_rays]
 
 
 def psnr(mse):

@@ -131,6 +131,7 @@ def sweep(args):
         n_local = n_global // world
         ts = B.build_trainer(dev, True, world)
         host, devb = B.make_batches(10, n_local, rank, world, dev)
+        assert devb[0].shape[0] == n_local
         for s in range(4):
             ts.step(*B.unpack(devb[s]), n_global=n_global)
         sync(world)
