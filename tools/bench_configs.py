@@ -129,6 +129,12 @@ def sweep(args):
     for log2n in range(14, 21):
         n_global = 1 << log2n
         n_local = n_global // world
+        # ~520 samples per room-shaped ray at random init, ~600 B of activations + gradients per sample
+        need = n_local * 520 * 600
+        free, _ = torch.cuda.mem_get_info(dev)
+        if need > 0.6 * free:
+            out.append({'rays_per_step': n_global, 'skipped': 'needs ~%d GB per GPU' % (need >> 30)})
+            continue
         ts = B.build_trainer(dev, True, world)
         host, devb = B.make_batches(10, n_local, rank, world, dev)
         assert devb[0].shape[0] == n_local
