@@ -45,6 +45,7 @@ def parse():
     ap.add_argument('--cpu-sample-rays', type=int, default=1024)
     ap.add_argument('--skip-cpu-baseline', action='store_true')
     ap.add_argument('--skip-ref-ext', action='store_true')
+    ap.add_argument('--skip-extras', action='store_true')
     return ap.parse_args()
 
 
@@ -325,6 +326,11 @@ def run_ours(args):
     }
     if world == 1 and not args.skip_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline(args.cpu_sample_rays)
+    if world == 1 and not args.skip_extras:
+        try:
+            line['extras'] = extras(device, peaks)
+        except Exception as e:          # secondary evidence only; never fails the headline line
+            line['extras'] = {'unavailable': '%s: %s' % (type(e).__name__, str(e)[:200])}
     if world == 1 and not args.skip_ref_ext:
         try:
             from bench_ref_ext import time_reference_ext
@@ -334,6 +340,87 @@ def run_ours(args):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ secondary measurements
+def extras(device, peaks):
+    """The other two numbers BASELINE.json's metric names, measured in the same run (N = 1 only, a few seconds):
+    full-frame render Mrays/s (config 3, trained-like case) and the tensor-core kernels against the measured bf16 peak."""
+    import torch
+    from nerfstyle_b200 import _lib, model as M, nnfm, raymarching, scenes
+    out = {}
+    tf_peak = float(peaks.get('bf16_tflops', 1590.0))
+    # ---- config 3: 1008 x 756 frame through march_rays / composite_rays (analytic occupancy, density_scale 50)
+    torch.manual_seed(0)
+    m = M.StyleTCNerf([-2., -2., -2.], [2., 2., 2.], class_dim=N_CLASSES).to(device)
+    r = M.Renderer(m, 2.0, raymarch_channels=3 + N_CLASSES, density_scale=50.0).to(device)
+    r.density_bitfield = raymarching.packbits(scenes.analytic_density_grid(2, 128, 2.0).to(device), 0.5)
+    intr = scenes.scaled_intrinsics(1008, 756)
+    poses = scenes.synthetic_poses(4, 1)
+    idx = torch.arange(0, 1008 * 756, device=device)
+    ms = []
+    for f in range(4):
+        o, d = scenes.generate_rays(poses[f], intr, device, idx)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.no_grad(), torch.autocast('cuda', dtype=torch.float16):
+            img, depth, cls = r.render_test(o, d)
+        float(img.sum().item())              # D2H read of the frame's checksum
+        if f > 0:
+            ms.append((time.perf_counter() - t0) * 1e3)
+    out['render_full_frame'] = {'w': 1008, 'h': 756, 'ms_per_frame': round(sum(ms) / len(ms), 2),
+                                'mrays_per_s': round(1008 * 756 / (sum(ms) / len(ms)) / 1e3, 2),
+                                'case': 'analytic occupancy, density_scale 50 (trained-like early termination)'}
+    del m, r
+    # ---- config 4: matching GEMM (tcgen05) at room size
+    N1, N2, K = 11844, 15876, 768
+    g = torch.Generator().manual_seed(0)
+    a = torch.nn.functional.normalize(torch.randn(N1, K, generator=g), dim=1).to(device).half()
+    b = torch.nn.functional.normalize(torch.randn(N2, K, generator=g), dim=1).to(device).half()
+    preds = torch.randint(0, 8, (N1,), generator=g).to(device)
+    clusters = (torch.arange(N2) * 8 // N2).to(device)
+    for _ in range(2):
+        nnfm.nn_match(a, b, preds, clusters, list(range(8)))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        nnfm.nn_match(a, b, preds, clusters, list(range(8)))
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / 10
+    tf = 2.0 * N1 * N2 * K / t / 1e9
+    out['nnfm_matching'] = {'N1': N1, 'N2': N2, 'K': K, 'ms': round(t, 3),
+                            'roofline': {'bound': 'tensor', 'achieved': round(tf, 1), 'peak': tf_peak, 'unit': 'TFLOP/s',
+                                         'frac': round(tf / tf_peak, 4), 'kernel': 'k_nnfm_gemm_tc (tcgen05, incl. operand packing)'}}
+    # ---- the fused MLPs (tcgen05): forward + backward of the density net on 4 Mi rows
+    B = 1 << 22
+    x = torch.randn(B, 32, device=device).half()
+    dy = (torch.randn(B, 1, device=device) * 0.01).half()
+    prm = (torch.randn(64 * 32 + 16 * 64, device=device) * 0.1).half()
+    y = torch.empty(B, 1, device=device, dtype=torch.float16)
+    dx = torch.empty_like(x)
+    dp = torch.zeros(prm.numel(), device=device)
+    st = torch.cuda.current_stream().cuda_stream
+    lib = _lib.lib()
+
+    def fb():
+        lib.nrf_mlp_forward(x.data_ptr(), 1, prm.data_ptr(), B, 32, 1, 1, 64, 1, 0, y.data_ptr(), 1, st)
+        lib.nrf_mlp_backward(x.data_ptr(), 1, prm.data_ptr(), dy.data_ptr(), 1, B, 32, 1, 1, 64, 1, 0, 128.0, dx.data_ptr(), 1,
+                             dp.data_ptr(), st)
+    for _ in range(3):
+        fb()
+    e0.record()
+    for _ in range(10):
+        fb()
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / 10
+    flop = 3 * 2 * (64 * 32 + 64 * 1) * B                 # un-padded MACs x 2, forward + 2x backward (SURVEY 8d)
+    io = B * (32 * 2 + 2 + 32 * 2 + 2 + 32 * 2)           # x, y, x again, dy, dx
+    out['mlp_density_fwd_bwd'] = {'rows': B, 'ms': round(t, 3), 'tflops_unpadded': round(flop / t / 1e9, 1),
+                                  'io_gbs': round(io / t / 1e6, 1), 'hbm_frac': round(io / t / 1e6 / float(peaks.get('hbm_gbs', 6650.0)), 4),
+                                  'kernel': 'k_mlp_fwd_tc + k_mlp_bwd_tc (tcgen05); bound by row traffic, not by the tensor pipe'}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ CPU oracle arms
