@@ -255,15 +255,20 @@ def run_ours(args):
 
     # -------- phase B: end to end through the public API with host inputs (H2D + D2H every step)
     ts = fresh_trainer()
-    stage = torch.empty_like(devb[0])
+    stage = [torch.empty_like(devb[0]), torch.empty_like(devb[0])]
+    loss_pin = torch.zeros(1, dtype=torch.float32).pin_memory()
     for s in range(W):
-        stage.copy_(host[s], non_blocking=True)
-        float(ts.step(*unpack(stage)).item())
+        stage[s & 1].copy_(host[s], non_blocking=True)
+        ts.step(*unpack(stage[s & 1]), loss_host=loss_pin)
+        ts.loss_ready.synchronize()
+        float(loss_pin[0])
     barrier()
     t0 = time.perf_counter()
     for s in range(W, W + K):
-        stage.copy_(host[s], non_blocking=True)                       # H2D from pinned memory
-        lv = float(ts.step(*unpack(stage)).item())                    # D2H read of the loss
+        stage[s & 1].copy_(host[s], non_blocking=True)                 # H2D from pinned memory (double-buffered staging)
+        ts.step(*unpack(stage[s & 1]), loss_host=loss_pin)             # D2H of the loss on a side stream, after the forward
+        ts.loss_ready.synchronize()
+        lv = float(loss_pin[0])                                        # the step's loss, on the host, every step
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], device=device, dtype=torch.float64)

@@ -22,6 +22,8 @@ class TrainStep:
         self.class_lambda = class_lambda
         self.world_size = world_size
         self.iter_ctr = 0
+        self._side = None
+        self.loss_ready = None
         self.fused = None
         if fused_optimizer:
             # GradScaler + Adam + LambdaLR + EMA + fp16 table copies in one device pass per tensor, no host sync
@@ -50,14 +52,31 @@ class TrainStep:
         from .parallel import allreduce_grads
         return allreduce_grads(self.params, self.world_size)
 
-    def step(self, rays_o, rays_d, target_rgb, target_cls, n_global=None):
+    def step(self, rays_o, rays_d, target_rgb, target_cls, n_global=None, loss_host=None):
         """rays_* [n,3], target_rgb [n,3] f32, target_cls [n] int64 -- all on the device.  Returns the loss tensor
-        (device; no host sync here beyond the one inside march_rays_train and GradScaler.step)."""
+        (device; no host sync here beyond the one inside march_rays_train).
+
+        loss_host: optional pinned f32[1] host tensor.  The loss is copied into it on a side stream as soon as the
+        FORWARD pass has produced it (the backward + optimizer kernels are still being enqueued / executed), and the
+        event to wait on before reading it is returned as `self.loss_ready`; a logging read-back therefore never
+        stalls the step behind its own backward."""
         n_local = rays_o.shape[0]
         n_global = n_global or n_local * self.world_size
         with torch.autocast('cuda', dtype=torch.float16, enabled=self.enable_amp):
             image, depth, classes = self.renderer.render_train(rays_o, rays_d)
             loss, mse = self.loss_fn(image, classes, target_rgb, target_cls)
+        if loss_host is not None:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=rays_o.device)
+            produced = torch.cuda.Event()
+            produced.record()
+            ld = loss.detach()
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(produced)
+                loss_host.copy_(ld.reshape(1), non_blocking=True)
+                self.loss_ready = torch.cuda.Event()
+                self.loss_ready.record()
+            ld.record_stream(self._side)
         back = loss * (n_local / n_global) if self.world_size > 1 else loss
         if self.fused is not None:
             self.fused.zero_grad()
