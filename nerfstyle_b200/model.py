@@ -274,9 +274,13 @@ class Renderer(nn.Module):
         n_alive = N
         rays_alive = torch.arange(n_alive, dtype=torch.int32, device=self.device)
         rays_t = nears.clone()[:, None]
-        step = 0
-        it = 0
-        cnt = None
+        with tcnn.cache_half_params():          # the weights do not change inside one frame
+            return self._render_loop(rays_o, rays_d, nears, fars, N, n_alive, rays_alive, rays_t, weights_sum, depth, image,
+                                     sync_every, kwargs)
+
+    def _render_loop(self, rays_o, rays_d, nears, fars, N, n_alive, rays_alive, rays_t, weights_sum, depth, image, sync_every,
+                     kwargs):
+        step, it, cnt = 0, 0, None
         while step < self.max_steps:
             if sync_every <= 1:
                 n_alive = len(rays_alive)

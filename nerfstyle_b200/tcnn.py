@@ -71,16 +71,38 @@ class _mlp_function(Function):
         return dx, dparams, None, None
 
 
+_cache_epoch = 0          # > 0 and odd while a cache_half_params() scope is open
+
+
+class cache_half_params:
+    """Scope in which the fp16 casts of the networks' parameters are cached (an inference loop calls each network
+    hundreds of times per frame with unchanged weights).  Outside such a scope every forward re-casts, exactly like
+    tinycudann: a version-counter check alone would miss writes through `param.data` (torch_ema's copy_to / restore)."""
+
+    def __enter__(self):
+        global _cache_epoch
+        self._outer = _cache_epoch
+        if _cache_epoch % 2 == 0:
+            _cache_epoch += 1
+        return self
+
+    def __exit__(self, *exc):
+        global _cache_epoch
+        if self._outer % 2 == 0:
+            _cache_epoch += 1          # leaving the outermost scope invalidates everything cached inside it
+        return False
+
+
 def half_params(params, owner=None):
     """fp16 copy of a flat parameter vector for the kernels.  FusedAdamEMA keeps one current on the parameter
-    (`_nrf_half_copy`, written by the optimizer kernel); otherwise the cast is cached on `owner` until the parameter's
-    version counter or storage changes (inference loops call the networks hundreds of times per frame)."""
+    (`_nrf_half_copy`, written by the optimizer kernel); inside a cache_half_params() scope the cast is cached on
+    `owner`; otherwise it is made afresh."""
     h = getattr(params, '_nrf_half_copy', None)
     if h is not None:
         return h
-    if owner is None:
+    if owner is None or _cache_epoch % 2 == 0:
         return params.detach().to(torch.float16).contiguous()
-    key = (params._version, params.data_ptr())
+    key = (_cache_epoch, params._version, params.data_ptr())
     if getattr(owner, '_half_key', None) != key:
         owner._half = params.detach().to(torch.float16).contiguous()
         owner._half_key = key

@@ -121,3 +121,21 @@ def test_sh_encoding(cuda_lib, dev, degree, dtype):
     err = np.abs(out.float().cpu().numpy() - ref)
     tol = 2e-6 if dtype == torch.float32 else 2.0 ** -11 * np.maximum(np.abs(ref), 2.0 ** -14) + 1e-7
     assert (err <= tol).all(), err.max()
+
+
+def test_half_param_cache_is_scoped(cuda_lib, dev):
+    """Outside a cache_half_params() scope every forward re-casts the parameters (writes through `param.data`, which do
+    not bump the version counter, must be seen -- torch_ema does exactly that); inside, the cast is reused."""
+    from nerfstyle_b200 import tcnn
+    net, (ni, no, nh, act) = _net('density', dev)
+    x = torch.randn(256, ni, device=dev).half()
+    y0 = net(x).clone()
+    net.params.data.mul_(2.0)                         # no version bump; two bias-free layers -> the output scales by 4
+    y1 = net(x)
+    assert float((y1.float() - 4 * y0.float()).abs().max()) <= 2e-2 * float(y0.float().abs().max()) + 1e-3
+    with tcnn.cache_half_params():
+        a = tcnn.half_params(net.params, net)
+        b = tcnn.half_params(net.params, net)
+        assert a is b
+    c = tcnn.half_params(net.params, net)
+    assert c is not a
