@@ -117,6 +117,12 @@ def test_reference_modules_import_unchanged_on_dropin():
         model = sn.StyleTCNerf(Cfg, BBox([-2., -2., -2.], [2., 2., 2.]), 8, torch.float16, use_dir=False)
         assert model.x_density_embedder.offsets[-1].item() == 6299960
         assert model.color2_net.params.numel() == 6144
+        # use_dir=True builds tcnn.Encoding(SphericalHarmonics, degree 4) and a 32-wide colour-2 input (style_nerf.py:33-42,72-85)
+        model_d = sn.StyleTCNerf(Cfg, BBox([-2., -2., -2.], [2., 2., 2.]), 8, torch.float16, use_dir=True)
+        assert model_d.d_embedder.n_output_dims == 16 and model_d.color2_net.n_input_dims == 32
+        # the single-grid TCNerf of networks/tcnn_nerf.py: 16-wide density head, 31-wide rgb input (tcnn_nerf.py:97-122)
+        tc = tn.TCNerf(Cfg, BBox([-2., -2., -2.], [2., 2., 2.]), torch.float16)
+        assert tc.d_embedder.n_output_dims == 16 and tc.density_net.n_output_dims == 16 and tc.rgb_net.n_input_dims == 31
     finally:
         for k, v in saved.items():
             if v is None:
