@@ -296,3 +296,22 @@ def test_inference_loop_matches_oracle(cuda_lib, oracle, dev, T_thresh):
         assert (~close).mean() < 0.01                      # a handful of threshold-straddling rays
         assert np.abs(n(image) - eimage).max() <= 2 * T_thresh * max(1.0, float(np.abs(eimage).max()))
         assert np.abs(n(ws) - ews).max() <= 2 * T_thresh
+
+
+def test_plain_c_host_of_the_abi(cuda_lib, dev):
+    """examples/c_host.c drives the C ABI with nothing but the CUDA runtime (no Python objects, no torch types): built
+    with gcc against include/nerfstyle_b200.h and run as a separate process."""
+    import os
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, 'examples', 'c_host')
+    src = os.path.join(root, 'examples', 'c_host.c')
+    if shutil.which('gcc') is None:
+        pytest.skip('no gcc')
+    if not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(src):
+        subprocess.check_call(['gcc', '-O2', '-I', os.path.join(root, 'include'), '-I', '/usr/local/cuda/include', src, '-o', exe,
+                               '-L', os.path.join(root, 'nerfstyle_b200'), '-lnerfstyle_b200', '-L', '/usr/local/cuda/lib64', '-lcudart',
+                               '-Wl,-rpath,' + os.path.join(root, 'nerfstyle_b200'), '-lm'])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and 'C HOST OK' in out.stdout, out.stdout + out.stderr
