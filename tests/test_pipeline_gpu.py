@@ -186,3 +186,25 @@ def test_fused_optimizer_matches_torch(cuda_lib, dev):
     torch.testing.assert_close(pa[0]._nrf_half_copy.float(), pa[0].detach().half().float())
     for p in pa[1:]:       # the small (MLP-sized) tensors keep a current fp16 copy in every mode
         torch.testing.assert_close(p._nrf_half_copy.float(), p.detach().half().float())
+
+
+def test_trainstep_async_loss_readback(cuda_lib, dev):
+    """TrainStep.step(loss_host=pinned): the loss lands in pinned host memory through a side stream right after the
+    forward; the value equals the returned device loss."""
+    from nerfstyle_b200 import model as M, scenes
+    from nerfstyle_b200.trainer import TrainStep
+    torch.manual_seed(0)
+    m = M.StyleTCNerf([-2., -2., -2.], [2., 2., 2.], class_dim=8).to(dev)
+    r = M.Renderer(m, 2.0, raymarch_channels=11).to(dev)
+    ts = TrainStep(r, enable_amp=True)
+    intr = dict(scenes.ROOM)
+    pose = scenes.synthetic_poses(2, 0)[0]
+    gen = torch.Generator().manual_seed(0)
+    pin = torch.zeros(1).pin_memory()
+    for it in range(3):
+        idx = scenes.frame_indices(intr, 512, gen).to(dev)
+        o, d = scenes.generate_rays(pose, intr, dev, idx)
+        tgt, seg = scenes.synthetic_target(idx, intr)
+        loss = ts.step(o, d, tgt, seg, loss_host=pin)
+        ts.loss_ready.synchronize()
+        assert abs(float(pin[0]) - float(loss)) < 1e-7 and np.isfinite(float(pin[0]))
