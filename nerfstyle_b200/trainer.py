@@ -7,7 +7,6 @@ n_local / n_global, then the hash-table and MLP gradients are summed with one NC
 group before the (identical) optimizer step on every rank.
 """
 import torch
-import torch.distributed as dist
 import torch.nn.functional as F
 
 

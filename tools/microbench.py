@@ -10,7 +10,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from nerfstyle_b200 import _lib, model as M, raymarching, scenes, tcnn  # noqa: E402
-from nerfstyle_b200.gridencoder import grid_encode  # noqa: E402
+
 
 dev = torch.device('cuda:0')
 lib = _lib.lib()
