@@ -319,7 +319,8 @@ def run_ours(args):
                    'occupancy': 'H128 C2 update every 16 steps', 'amp': amp, 'optimizer': 'Adam(fused)+EMA',
                    'l2_policy': 'no flush: per-step working set (~%d MB of samples/activations + 96 MB tables) exceeds the 126 MB L2'
                                 % (samples_last * 700 // (1 << 20)),
-                   'parallelism': 'dp%d (rays sharded, NCCL all-reduce of table+MLP grads)' % world},
+                   'parallelism': 'dp%d (rays sharded; table grads reduce-scattered, Adam on 1/N table shards, fp16 tables all-gathered; '
+                                  'MLP grads all-reduced -- NCCL over NVLink)' % world},
         'e2e': {'value': round(n_global * K / e2e_s, 1), 'unit': 'rays/s', 'h2d_bytes_per_step': int(host[0].numel() * 4),
                 'd2h_bytes_per_step': 4 + 8, 'ms_per_step': round(e2e_s * 1e3 / K, 4)},
         'gpu_launches': int(launches),

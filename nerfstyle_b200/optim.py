@@ -14,16 +14,41 @@ from . import _lib as L
 class FusedAdamEMA:
     def __init__(self, params, lr=0.01, betas=(0.9, 0.999), eps=1e-15, lr_decay_steps=30000, ema_decay=0.95,
                  init_scale=65536.0, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000, enable_amp=True,
-                 half_copy_min_numel=1 << 20):
+                 half_copy_min_numel=1 << 20, world_size=1, rank=0, shard_big=True):
+        """world_size > 1 makes step() own the gradient exchange of the data-parallel step:
+        * small tensors (the MLPs): one flattened all-reduce, replicated update;
+        * big tensors (the hash tables), under AMP: REDUCE-SCATTER of the gradient, Adam / EMA on this rank's 1/world
+          shard only (optimizer state is allocated for the shard), then ALL-GATHER of the fp16 table copy -- the only
+          form the next forward reads.  That moves 3/4 of an all-reduce's bytes and divides the optimizer pass by world.
+          The fp32 master table is then current only inside each rank's shard (gather_master() rebuilds it, e.g. for a
+          checkpoint); without AMP the tables are read in fp32 and the big tensors fall back to all-reduce."""
         self.params = [p for p in params]
         dev = self.params[0].device
+        self.world_size, self.rank = int(world_size), int(rank)
         self.lr, self.betas, self.eps, self.lr_decay_steps = lr, betas, eps, float(lr_decay_steps)
         self.ema_decay = ema_decay
         self.growth_factor, self.backoff_factor, self.growth_interval = growth_factor, backoff_factor, growth_interval
         self.enable_amp = enable_amp
-        self.exp_avg = [torch.zeros_like(p) for p in self.params]
-        self.exp_avg_sq = [torch.zeros_like(p) for p in self.params]
-        self.ema = [p.detach().clone() for p in self.params] if ema_decay is not None else None
+        # shard plan: (lo, hi) element range of this rank for every sharded tensor, None for replicated ones
+        self.shard = []
+        for p in self.params:
+            n = p.numel()
+            if self.world_size > 1 and shard_big and enable_amp and n >= half_copy_min_numel and n % self.world_size == 0:
+                per = n // self.world_size
+                self.shard.append((self.rank * per, (self.rank + 1) * per))
+            else:
+                self.shard.append(None)
+
+        def state_like(p, sh, init=None):
+            if sh is None:
+                return torch.zeros_like(p) if init is None else p.detach().clone()
+            flat = p.detach().reshape(-1)[sh[0]:sh[1]]
+            return torch.zeros_like(flat) if init is None else flat.clone()
+        self.exp_avg = [state_like(p, sh) for p, sh in zip(self.params, self.shard)]
+        self.exp_avg_sq = [state_like(p, sh) for p, sh in zip(self.params, self.shard)]
+        self.ema = [state_like(p, sh, 'copy') for p, sh in zip(self.params, self.shard)] if ema_decay is not None else None
+        self.grad_shard = [torch.empty(sh[1] - sh[0], dtype=torch.float32, device=dev) if sh is not None else None
+                           for sh in self.shard]
         self.num_updates = 0
         nbytes = int(L.lib().nrf_opt_state_bytes())
         raw = struct.pack('fiii', float(init_scale if enable_amp else 1.0), 0, 0, 0) + b'\0' * (nbytes - 16)
@@ -58,7 +83,17 @@ class FusedAdamEMA:
             p.grad = None
 
     @torch.no_grad()
+    def gather_master(self):
+        """Rebuild the full fp32 master copy of every sharded tensor on every rank (checkpointing)."""
+        from . import parallel
+        for p, sh in zip(self.params, self.shard):
+            if sh is not None:
+                flat = p.data.view(-1)
+                parallel.all_gather_shards(flat, flat[sh[0]:sh[1]].clone(), self.world_size)
+
+    @torch.no_grad()
     def step(self):
+        from . import parallel
         lib = L.lib()
         dev = self.params[0].device
         self.num_updates += 1
@@ -72,19 +107,41 @@ class FusedAdamEMA:
             grads = []
             for p in self.params:
                 g = p.grad
-                if g is None:
-                    grads.append(None)
-                    continue
-                if g.dtype != torch.float32 or not g.is_contiguous():
+                if g is not None and (g.dtype != torch.float32 or not g.is_contiguous()):
                     g = g.float().contiguous()
                 grads.append(g)
-                L.check(lib.nrf_grads_check(g.data_ptr(), g.numel(), self.state.data_ptr(), st), 'grads_check')
+            if self.world_size > 1:
+                # ---- gradient exchange: reduce-scatter the sharded tensors, one flattened all-reduce for the rest
+                for i, sh in enumerate(self.shard):
+                    if sh is not None and grads[i] is not None:
+                        parallel.reduce_scatter_sum(grads[i].view(-1), self.grad_shard[i], self.world_size, self.rank)
+                        grads[i] = self.grad_shard[i]
+                parallel.allreduce_tensors([g for g, sh in zip(grads, self.shard) if sh is None and g is not None], self.world_size)
+            for g in grads:
+                if g is not None:
+                    L.check(lib.nrf_grads_check(g.data_ptr(), g.numel(), self.state.data_ptr(), st), 'grads_check')
+            if self.world_size > 1 and any(sh is not None for sh in self.shard):
+                # an inf seen in ANY rank's shard skips the step everywhere (the replicated GradScaler decision)
+                parallel.allreduce_max_int(self.state[4:8].view(torch.int32), self.world_size)
             for i, p in enumerate(self.params):
                 if grads[i] is None:
                     continue
-                L.check(lib.nrf_adam_step(p.data_ptr(), grads[i].data_ptr(), self.exp_avg[i].data_ptr(),
-                                          self.exp_avg_sq[i].data_ptr(), L.ptr(self.ema[i]) if self.ema is not None else None,
-                                          L.ptr(self.half[i]), p.numel(), self.state.data_ptr(), self.lr, self.lr_decay_steps,
-                                          self.betas[0], self.betas[1], self.eps, omd, st), 'adam_step')
+                sh = self.shard[i]
+                if sh is None:
+                    p_ptr, h_ptr, n = p.data_ptr(), L.ptr(self.half[i]), p.numel()
+                else:
+                    n = sh[1] - sh[0]
+                    p_ptr = p.data_ptr() + 4 * sh[0]
+                    h_ptr = (self.half[i].data_ptr() + 2 * sh[0]) if self.half[i] is not None else None
+                L.check(lib.nrf_adam_step(p_ptr, grads[i].data_ptr(), self.exp_avg[i].data_ptr(), self.exp_avg_sq[i].data_ptr(),
+                                          L.ptr(self.ema[i]) if self.ema is not None else None, h_ptr, n,
+                                          self.state.data_ptr(), self.lr, self.lr_decay_steps, self.betas[0], self.betas[1],
+                                          self.eps, omd, st), 'adam_step')
+            if self.world_size > 1:
+                # ---- the next forward reads only the fp16 table copies: gather their shards (in place)
+                for i, sh in enumerate(self.shard):
+                    if sh is not None and grads[i] is not None:
+                        hflat = self.half[i].view(-1)
+                        parallel.all_gather_shards(hflat, hflat[sh[0]:sh[1]], self.world_size)
             L.check(lib.nrf_scaler_update(self.state.data_ptr(), self.growth_factor, self.backoff_factor,
                                           int(self.growth_interval) if self.enable_amp else (1 << 30), st), 'scaler_update')

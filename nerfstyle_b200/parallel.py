@@ -47,6 +47,53 @@ def allreduce_grads(params, world, bucket_small_below=1 << 20):
     return nbytes
 
 
+def _is_nccl():
+    return dist.get_backend() == 'nccl'
+
+
+def allreduce_tensors(tensors, world, bucket_small_below=1 << 20):
+    """Sum a list of tensors over all ranks in place (big ones on their own, small ones as one flattened message)."""
+    if world <= 1 or not tensors:
+        return
+    small = [t for t in tensors if t.numel() < bucket_small_below]
+    for t in tensors:
+        if t.numel() >= bucket_small_below:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    if small:
+        flat = torch.cat([t.reshape(-1) for t in small])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        o = 0
+        for t in small:
+            t.copy_(flat[o:o + t.numel()].view_as(t))
+            o += t.numel()
+
+
+def reduce_scatter_sum(full, shard_out, world, rank):
+    """shard_out <- this rank's 1/world slice of the sum of `full` over all ranks (full.numel() % world == 0).
+    NCCL: one reduce-scatter; gloo (CPU tests) has none: all-reduce + slice."""
+    per = full.numel() // world
+    if _is_nccl():
+        dist.reduce_scatter_tensor(shard_out, full, op=dist.ReduceOp.SUM)
+    else:
+        dist.all_reduce(full, op=dist.ReduceOp.SUM)
+        shard_out.copy_(full[rank * per:(rank + 1) * per])
+
+
+def all_gather_shards(full, shard, world):
+    """full <- concatenation of every rank's `shard` (which may be the matching slice of `full` itself: in place)."""
+    if _is_nccl():
+        dist.all_gather_into_tensor(full, shard)
+    else:
+        parts = [torch.empty_like(shard) for _ in range(world)]
+        dist.all_gather(parts, shard.clone())
+        full.copy_(torch.cat(parts))
+
+
+def allreduce_max_int(t, world):
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+
+
 def gather_rows(local, n_total, rank, world, dst=0):
     """Gather row shards (render tiles) on `dst`; returns the full [n_total, ...] tensor there, None elsewhere."""
     if world <= 1:

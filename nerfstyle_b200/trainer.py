@@ -12,7 +12,7 @@ import torch.nn.functional as F
 
 class TrainStep:
     def __init__(self, renderer, lr=0.01, mlp_lr=None, lr_decay=30000, ema_decay=0.95, class_lambda=0.001, enable_amp=True,
-                 fused_adam=True, world_size=1, fused_optimizer=True):
+                 fused_adam=True, world_size=1, fused_optimizer=True, rank=None, shard_optimizer=True):
         self.renderer = renderer
         self.model = renderer.model
         params = list(self.model.parameters())
@@ -27,8 +27,12 @@ class TrainStep:
         if fused_optimizer:
             # GradScaler + Adam + LambdaLR + EMA + fp16 table copies in one device pass per tensor, no host sync
             from .optim import FusedAdamEMA
+            if rank is None:
+                import torch.distributed as dist
+                rank = dist.get_rank() if (world_size > 1 and dist.is_initialized()) else 0
+            # with world_size > 1 the optimizer owns the gradient exchange (reduce-scatter / sharded Adam / all-gather)
             self.fused = FusedAdamEMA(params, lr=lr, eps=1e-15, lr_decay_steps=lr_decay, ema_decay=ema_decay,
-                                      enable_amp=enable_amp)
+                                      enable_amp=enable_amp, world_size=world_size, rank=rank, shard_big=shard_optimizer)
             self.ema = self.fused.ema
             return
         self.optim = torch.optim.Adam([{'params': params}], lr=lr, betas=(0.9, 0.999), eps=1e-15, fused=fused_adam)
@@ -80,8 +84,7 @@ class TrainStep:
         if self.fused is not None:
             self.fused.zero_grad()
             self.fused.scale_loss(back).backward()
-            self.allreduce_grads()
-            self.fused.step()
+            self.fused.step()            # includes the gradient exchange when world_size > 1
             self.iter_ctr += 1
             return loss.detach()
         self.optim.zero_grad(set_to_none=True)

@@ -87,3 +87,41 @@ def test_dp2_gradients_equal_whole_batch():
         assert np.abs(b).max() > 0, n
         np.testing.assert_allclose(a, b, rtol=2e-4, atol=2e-6 * np.abs(b).max(), err_msg=n)
     np.testing.assert_allclose(ret['img'].numpy(), out['rgb'].detach().numpy(), rtol=1e-6, atol=1e-7)
+
+
+def _shard_worker(rank, world, port, ret):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from nerfstyle_b200 import parallel
+    n = 24
+    full = torch.arange(n, dtype=torch.float32) * (rank + 1)              # rank r holds (r+1) * [0..n)
+    shard = torch.empty(n // world)
+    parallel.reduce_scatter_sum(full.clone(), shard, world, rank)          # sum over ranks = 3 * [0..n) for world 2
+    table = torch.zeros(n)
+    per = n // world
+    table[rank * per:(rank + 1) * per] = shard                             # "update" only the own shard ...
+    parallel.all_gather_shards(table, table[rank * per:(rank + 1) * per], world)   # ... then gather in place
+    flag = torch.tensor([1 if rank == 1 else 0], dtype=torch.int32)
+    parallel.allreduce_max_int(flag, world)
+    small = [torch.full((3,), float(rank + 1)), torch.full((2, 2), 10.0 * (rank + 1))]
+    parallel.allreduce_tensors(small, world, bucket_small_below=1 << 10)
+    if rank == 0:
+        ret['table'] = table
+        ret['flag'] = int(flag)
+        ret['small'] = [t.clone() for t in small]
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_exchange_primitives():
+    """The collectives behind the sharded optimizer step (reduce-scatter of the gradient, in-place all-gather of the
+    updated shards, MAX of the found-inf flag, flattened all-reduce of the small tensors) on world_size-2 gloo."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_shard_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    torch.testing.assert_close(ret['table'], torch.arange(24, dtype=torch.float32) * 3)
+    assert ret['flag'] == 1
+    torch.testing.assert_close(ret['small'][0], torch.full((3,), 3.0))
+    torch.testing.assert_close(ret['small'][1], torch.full((2, 2), 30.0))
