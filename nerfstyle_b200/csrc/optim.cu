@@ -16,9 +16,15 @@ struct OptState {        // lives in device memory, 8 x 4 bytes
 
 __global__ void k_grads_check(const float* __restrict__ g, uint64_t n, OptState* st) {
     bool bad = false;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t n4 = ((((uintptr_t)g) & 15) == 0) ? n / 4 : 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(g)[i];
+        bad |= !(fabsf(v.x) <= 3.402823466e38f) || !(fabsf(v.y) <= 3.402823466e38f) || !(fabsf(v.z) <= 3.402823466e38f) ||
+               !(fabsf(v.w) <= 3.402823466e38f);      // inf or nan
+    }
+    for (uint64_t i = 4 * n4 + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const float v = g[i];
-        bad |= !(fabsf(v) <= 3.402823466e38f);      // inf or nan
+        bad |= !(fabsf(v) <= 3.402823466e38f);
     }
     if (__syncthreads_or(bad) && threadIdx.x == 0) st->found_inf = 1;
 }
@@ -33,19 +39,43 @@ __global__ void k_adam_ema(float* __restrict__ p, const float* __restrict__ g, f
     const float bc1 = 1.0f - powf(beta1, (float)t);
     const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)t));
     const float step_size = lr / bc1;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        float pi = p[i];
+    auto update = [&](float pi, float gi_raw, float& mi, float& vi, float& e) -> float {
         if (!skip) {
-            const float gi = g[i] * inv_scale;
-            const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
-            const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
-            m[i] = mi;
-            v[i] = vi;
+            const float gi = gi_raw * inv_scale;
+            mi = beta1 * mi + (1.0f - beta1) * gi;
+            vi = beta2 * vi + (1.0f - beta2) * gi * gi;
             pi -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
-            p[i] = pi;
+        }
+        e = e - ema_one_minus_decay * (e - pi);
+        return pi;
+    };
+    // 8-byte vector path (every pointer 8-byte aligned, the fp16 copy 4-byte): table shards of the data-parallel optimizer
+    // start at element offsets that are even but not multiples of four
+    const bool vec = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)ema) & 7) == 0) && ((((uintptr_t)p_half) & 3) == 0);
+    const uint64_t n2 = vec ? n / 2 : 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * blockDim.x) {
+        float2 pp = reinterpret_cast<float2*>(p)[i];
+        const float2 gg = reinterpret_cast<const float2*>(g)[i];
+        float2 mm = reinterpret_cast<float2*>(m)[i], vv = reinterpret_cast<float2*>(v)[i];
+        float2 ee = ema ? reinterpret_cast<float2*>(ema)[i] : make_float2(0.0f, 0.0f);
+        pp.x = update(pp.x, gg.x, mm.x, vv.x, ee.x);
+        pp.y = update(pp.y, gg.y, mm.y, vv.y, ee.y);
+        if (!skip) {
+            reinterpret_cast<float2*>(m)[i] = mm;
+            reinterpret_cast<float2*>(v)[i] = vv;
+            reinterpret_cast<float2*>(p)[i] = pp;
+            if (p_half) reinterpret_cast<__half2*>(p_half)[i] = __floats2half2_rn(pp.x, pp.y);
+        }
+        if (ema) reinterpret_cast<float2*>(ema)[i] = ee;
+    }
+    for (uint64_t i = 2 * n2 + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        float mi = m[i], vi = v[i], e = ema ? ema[i] : 0.0f;
+        const float pi = update(p[i], g[i], mi, vi, e);
+        if (!skip) {
+            m[i] = mi; v[i] = vi; p[i] = pi;
             if (p_half) p_half[i] = __float2half_rn(pi);
         }
-        if (ema) { const float e = ema[i]; ema[i] = e - ema_one_minus_decay * (e - pi); }
+        if (ema) ema[i] = e;
     }
 }
 
