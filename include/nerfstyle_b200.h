@@ -216,6 +216,32 @@ int nrf_mlp_backward_ex(const void* x, int x_dtype, const void* params_f16, cons
                         uint32_t width, int hidden_act, int out_act, float loss_scale, void* dx, int dx_dtype,
                         int dx_accumulate, float* dparams, void* stream);
 
+/* ------------------------------------------------------------------ device-driven inference loop (SURVEY 8f NEXT-2) */
+
+/* The inference loop of renderer.py:237-293 with its per-iteration host logic moved to the device.  ctl = device int32[8]
+ * {n_alive, n_step, n_rows = n_alive * n_step, steps_done, N, max_steps, iterations, -}; the caller initialises it to
+ * {N, 1, N, 0, N, max_steps, 0, 0} and nrf_compact_alive_dev advances it at the end of every iteration (new alive count,
+ * n_step = max(min(N / n_alive, 8), 1) as renderer.py:253, n_alive = 0 once max_steps is reached).  Every launch is sized
+ * for the caps (n_alive_cap = N rays, B_cap >= N rows since n_alive * n_step <= N), so an iteration is shape-static and
+ * can be captured in a CUDA graph and replayed with no host involvement; the host reads ctl[0] every few iterations to
+ * stop.  Kernels and numerics are those of nrf_march_rays / nrf_composite_rays / nrf_compact_alive /
+ * nrf_grid_encode_forward_dual / nrf_mlp_forward_ex; rows >= ctl[2] are left untouched. */
+int nrf_march_rays_dev(const int32_t* ctl, uint32_t n_alive_cap, const int32_t* rays_alive, const float* rays_t,
+                       const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C,
+                       uint32_t H, const uint8_t* grid, const float* fars, float* xyzs, float* dirs, float* deltas,
+                       void* stream);
+int nrf_composite_rays_dev(const int32_t* ctl, uint32_t n_alive_cap, float T_thresh, int32_t* rays_alive, float* rays_t,
+                           const float* sigmas, const float* rgbs, const float* deltas, uint32_t C, float* weights_sum,
+                           float* depth, float* image, void* stream);
+int nrf_compact_alive_dev(int32_t* ctl, uint32_t n_cap, const int32_t* in, int32_t* out, void* scratch, void* stream);
+int nrf_grid_encode_forward_dual_dev(const float* inputs, const void* embeddings0, const void* embeddings1,
+                                     const int32_t* offsets, void* outputs0, void* outputs1, uint32_t B_cap, uint32_t L,
+                                     float S, uint32_t H, uint32_t gridtype, int align_corners, uint32_t style, int dtype,
+                                     const float* xform, const int32_t* B_dev, void* stream);
+int nrf_mlp_forward_dev(const void* x, int x_dtype, const void* params_f16, uint32_t B_cap, uint32_t n_in, uint32_t n_out,
+                        uint32_t n_hidden, uint32_t width, int hidden_act, int out_act, void* y, int y_dtype,
+                        uint32_t ld_y, const int32_t* B_dev, void* stream);
+
 /* tcnn.Encoding {'otype': 'SphericalHarmonics', 'degree': d} (networks/style_nerf.py:33-42, tcnn_nerf.py:87-95), d <= 4:
  * inputs01 [B,3] f32 in [0,1] (mapped to [-1,1] inside, as tiny-cuda-nn does) -> outputs [B, d*d] (f16 or f32). */
 int nrf_sh_encode_forward(const float* inputs01, uint32_t B, uint32_t degree, void* outputs, int out_dtype, void* stream);

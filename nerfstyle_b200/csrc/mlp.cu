@@ -430,7 +430,7 @@ k_mlp_bwd(const XT* __restrict__ x, const __half* __restrict__ params, const DYT
 // mlp_tc.cu: the tcgen05 / TMEM implementation (default); the mma.sync kernels above stay as the selectable
 // second implementation (nrf_mlp_set_mode(1)) that the parity tests run side by side.
 int nrf_mlp_tc_forward(const void* x, int x_dtype, const void* params_f16, uint32_t B, uint32_t n_in, uint32_t n_out, uint32_t n_hidden,
-                       int hidden_act, int out_act, void* y, int y_dtype, uint32_t ld_y, cudaStream_t s);
+                       int hidden_act, int out_act, void* y, int y_dtype, uint32_t ld_y, const int32_t* B_dev, cudaStream_t s);
 int nrf_mlp_tc_backward(const void* x, int x_dtype, const void* params_f16, const void* dy, int dy_dtype, uint32_t ld_dy, uint32_t B,
                         uint32_t n_in, uint32_t n_out, uint32_t n_hidden, int hidden_act, int out_act, float loss_scale, void* dx,
                         int dx_accumulate, float* dparams, cudaStream_t s);
@@ -482,9 +482,19 @@ NRF_EXPORT int nrf_mlp_forward(const void* x, int x_dtype, const void* params_f1
                                void* stream) {
     return nrf_mlp_forward_ex(x, x_dtype, params_f16, B, n_in, n_out, n_hidden, width, hidden_act, out_act, y, y_dtype, n_out, stream);
 }
+NRF_EXPORT int nrf_mlp_forward_dev(const void* x, int x_dtype, const void* params_f16, uint32_t B_cap, uint32_t n_in, uint32_t n_out,
+                                   uint32_t n_hidden, uint32_t width, int hidden_act, int out_act, void* y, int y_dtype,
+                                   uint32_t ld_y, const int32_t* B_dev, void* stream);
 NRF_EXPORT int nrf_mlp_forward_ex(const void* x, int x_dtype, const void* params_f16, uint32_t B, uint32_t n_in, uint32_t n_out,
                                   uint32_t n_hidden, uint32_t width, int hidden_act, int out_act, void* y, int y_dtype,
                                   uint32_t ld_y, void* stream) {
+    return nrf_mlp_forward_dev(x, x_dtype, params_f16, B, n_in, n_out, n_hidden, width, hidden_act, out_act, y, y_dtype, ld_y, nullptr,
+                               stream);
+}
+// B_dev (device int32, or NULL): rows actually present (<= B_cap, which sizes the launch); tcgen05 implementation only
+NRF_EXPORT int nrf_mlp_forward_dev(const void* x, int x_dtype, const void* params_f16, uint32_t B, uint32_t n_in, uint32_t n_out,
+                                   uint32_t n_hidden, uint32_t width, int hidden_act, int out_act, void* y, int y_dtype,
+                                   uint32_t ld_y, const int32_t* B_dev, void* stream) {
     if (B == 0) return NRF_OK;
     if (ld_y == 0) ld_y = n_out;
     if (ld_y < n_out) return NRF_E_INVALID;
@@ -494,8 +504,8 @@ NRF_EXPORT int nrf_mlp_forward_ex(const void* x, int x_dtype, const void* params
     cudaStream_t s = (cudaStream_t)stream;
     if (x_dtype != NRF_DTYPE_F16 && x_dtype != NRF_DTYPE_F32) return NRF_E_UNSUPPORTED;
     if (y_dtype != NRF_DTYPE_F16 && y_dtype != NRF_DTYPE_F32) return NRF_E_UNSUPPORTED;
-    if (g_mlp_mode == 0) return nrf_mlp_tc_forward(x, x_dtype, params_f16, B, n_in, n_out, n_hidden, hidden_act, out_act, y, y_dtype, ld_y, s);
-    if (ld_y != n_out || out_act == NRF_ACT_TRUNC_EXP) return NRF_E_UNSUPPORTED;      // extensions exist on the tcgen05 path only
+    if (g_mlp_mode == 0) return nrf_mlp_tc_forward(x, x_dtype, params_f16, B, n_in, n_out, n_hidden, hidden_act, out_act, y, y_dtype, ld_y, B_dev, s);
+    if (ld_y != n_out || out_act == NRF_ACT_TRUNC_EXP || B_dev) return NRF_E_UNSUPPORTED;      // extensions exist on the tcgen05 path only
     const int kt = (int)((n_in + 15) / 16), nt = n_out <= 8 ? 1 : 2;
 #define FWD_CASE(K, H, N) if (kt == K && (int)n_hidden == H && nt == N) return launch_fwd_dt<K, H, N>(x, x_dtype, params_f16, B, n_in, n_out, hidden_act, out_act, y, y_dtype, s)
     FWD_CASE(1, 1, 1); FWD_CASE(1, 1, 2); FWD_CASE(1, 2, 1); FWD_CASE(1, 2, 2);

@@ -335,8 +335,9 @@ __host__ __device__ constexpr TcSmem bwd_smem() {
 template <int IN_KT, int NH>
 __global__ void __launch_bounds__(TC_THREADS, 5)
 k_mlp_fwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ params, uint32_t B, uint32_t n_in, uint32_t n_out,
-             int hidden_act, int out_act, void* __restrict__ y, int y_dt, uint32_t ld_y) {
+             int hidden_act, int out_act, void* __restrict__ y, int y_dt, uint32_t ld_y, const int32_t* __restrict__ B_dev) {
     constexpr int IN_PAD = IN_KT * 16;
+    if (B_dev) B = min(B, (uint32_t)*B_dev);      // device-driven inference loop: the launch is sized for the cap
     constexpr int CPR = IN_PAD / 8;                      // 16-byte chunks per input row
     constexpr uint32_t CH = ch_for(IN_KT);
     constexpr TcSmem L = fwd_smem<IN_KT, NH>();
@@ -739,14 +740,14 @@ unsigned long long* g_prof = nullptr;
 
 template <int IN_KT, int NH>
 int launch_fwd(const void* x, int xdt, const void* params, uint32_t B, uint32_t n_in, uint32_t n_out, int hact, int oact, void* y, int ydt,
-               uint32_t ld_y, cudaStream_t s) {
+               uint32_t ld_y, const int32_t* B_dev, cudaStream_t s) {
     constexpr TcSmem L = fwd_smem<IN_KT, NH>();
     auto kern = k_mlp_fwd_tc<IN_KT, NH>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
     const uint32_t ntiles = ceil_div_u32(B, 128);
     const uint32_t per_sm = (uint32_t)max(1, min(min(g_fwd_ctas_per_sm, (int)(220 * 1024 / (L.total + 1024))), 8));
     const uint32_t grid = (uint32_t)min((uint64_t)ntiles, (uint64_t)tc_sm_count() * per_sm);
-    kern<<<grid, TC_THREADS, L.total, s>>>(x, xdt, (const __half*)params, B, n_in, n_out, hact, oact, y, ydt, ld_y);
+    kern<<<grid, TC_THREADS, L.total, s>>>(x, xdt, (const __half*)params, B, n_in, n_out, hact, oact, y, ydt, ld_y, B_dev);
     return nrf_check_launch();
 }
 
@@ -768,9 +769,9 @@ int launch_bwd(const void* x, int xdt, const void* params, const void* dy, int d
 
 // entry points used by mlp.cu's dispatcher (same argument meaning as nrf_mlp_forward / nrf_mlp_backward)
 int nrf_mlp_tc_forward(const void* x, int x_dtype, const void* params_f16, uint32_t B, uint32_t n_in, uint32_t n_out, uint32_t n_hidden,
-                       int hidden_act, int out_act, void* y, int y_dtype, uint32_t ld_y, cudaStream_t s) {
+                       int hidden_act, int out_act, void* y, int y_dtype, uint32_t ld_y, const int32_t* B_dev, cudaStream_t s) {
     const int kt = (int)((n_in + 15) / 16);
-#define TC_FWD(K, H) if (kt == K && (int)n_hidden == H) return launch_fwd<K, H>(x, x_dtype, params_f16, B, n_in, n_out, hidden_act, out_act, y, y_dtype, ld_y, s)
+#define TC_FWD(K, H) if (kt == K && (int)n_hidden == H) return launch_fwd<K, H>(x, x_dtype, params_f16, B, n_in, n_out, hidden_act, out_act, y, y_dtype, ld_y, B_dev, s)
     TC_FWD(1, 1); TC_FWD(2, 1); TC_FWD(3, 1); TC_FWD(4, 1);
     TC_FWD(1, 2); TC_FWD(2, 2); TC_FWD(3, 2); TC_FWD(4, 2);
 #undef TC_FWD

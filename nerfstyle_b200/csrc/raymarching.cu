@@ -853,8 +853,12 @@ k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays
              const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ z_hats, float bound,
              float dt_gamma, uint32_t max_steps, bool is_ndc, uint32_t C, uint32_t H, const uint8_t* __restrict__ grid,
              const float* __restrict__ fars, float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
-             const float* __restrict__ noises, uint32_t Mpad, bool zero_fill) {
+             const float* __restrict__ noises, uint32_t Mpad, bool zero_fill, const int32_t* __restrict__ ctl) {
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ctl) {      // device-driven loop (nrf_march_rays_dev): the launch is sized for the cap, the counts live on the device
+        n_alive = (uint32_t)ctl[0]; n_step = (uint32_t)ctl[1];
+        if (n >= n_alive) return;
+    }
     if (n >= n_alive) {
         // padding rows [n_alive*n_step, Mpad): spread over the surplus threads of the grid
         if (zero_fill) {
@@ -934,15 +938,35 @@ NRF_EXPORT int nrf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* 
     k_march_rays<<<ceil_div_u32(threads, 128), 128, 0, (cudaStream_t)stream>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d,
                                                                              z_hats, bound, dt_gamma, max_steps, is_ndc != 0, C, H,
                                                                              grid, fars, xyzs, dirs, deltas, noises, Mpad,
-                                                                             zero_fill != 0);
+                                                                             zero_fill != 0, nullptr);
+    return nrf_check_launch();
+}
+
+// Device-driven inference loop (SURVEY.md 8f NEXT-2): the same kernels, but n_alive / n_step come from a control block in
+// device memory, ctl = int32[8] {n_alive, n_step, n_rows = n_alive * n_step, steps_done, N, max_steps, iterations, -}, which
+// nrf_compact_alive_dev advances at the end of every iteration.  Every launch is sized for the cap (n_alive_cap rays,
+// n_alive * n_step <= N rows), so an iteration is shape-static and a pair of them can be captured in a CUDA graph and
+// replayed with no host involvement.
+NRF_EXPORT int nrf_march_rays_dev(const int32_t* ctl, uint32_t n_alive_cap, const int32_t* rays_alive, const float* rays_t,
+                                  const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C,
+                                  uint32_t H, const uint8_t* grid, const float* fars, float* xyzs, float* dirs, float* deltas,
+                                  void* stream) {
+    if (!ctl || !rays_alive || !rays_t || !rays_o || !rays_d || !grid || !fars || !xyzs || !dirs || !deltas) return NRF_E_INVALID;
+    if ((((uintptr_t)deltas) & 15) != 0) return NRF_E_INVALID;
+    if (n_alive_cap == 0) return NRF_OK;
+    k_march_rays<<<ceil_div_u32(n_alive_cap, 128), 128, 0, (cudaStream_t)stream>>>(n_alive_cap, 1, rays_alive, rays_t, rays_o, rays_d, nullptr,
+                                                                                 bound, dt_gamma, max_steps, false, C, H, grid, fars, xyzs,
+                                                                                 dirs, deltas, nullptr, 0, true, ctl);
     return nrf_check_launch();
 }
 
 __global__ void __launch_bounds__(128)
 k_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* __restrict__ rays_alive, float* __restrict__ rays_t,
                  const float* __restrict__ sigmas, const float* __restrict__ rgbs, const float* __restrict__ deltas, uint32_t C,
-                 bool is_ndc, float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image) {
+                 bool is_ndc, float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image,
+                 const int32_t* __restrict__ ctl) {
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ctl) { n_alive = (uint32_t)ctl[0]; n_step = (uint32_t)ctl[1]; }
     if (n >= n_alive) return;
     const int32_t index = rays_alive[n];
     if (index < 0) return;          // dead slot (see k_march_rays)
@@ -982,14 +1006,27 @@ NRF_EXPORT int nrf_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thr
     if (!rays_alive || !rays_t || !sigmas || !rgbs || !deltas || !weights_sum || !depth || !image) return NRF_E_INVALID;
     if ((((uintptr_t)deltas) & 15) != 0) return NRF_E_INVALID;
     k_composite_rays<<<ceil_div_u32(n_alive, 128), 128, 0, (cudaStream_t)stream>>>(n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas,
-                                                                                  rgbs, deltas, C, is_ndc != 0, weights_sum, depth, image);
+                                                                                  rgbs, deltas, C, is_ndc != 0, weights_sum, depth, image,
+                                                                                  nullptr);
+    return nrf_check_launch();
+}
+
+NRF_EXPORT int nrf_composite_rays_dev(const int32_t* ctl, uint32_t n_alive_cap, float T_thresh, int32_t* rays_alive, float* rays_t,
+                                      const float* sigmas, const float* rgbs, const float* deltas, uint32_t C, float* weights_sum,
+                                      float* depth, float* image, void* stream) {
+    if (!ctl || !rays_alive || !rays_t || !sigmas || !rgbs || !deltas || !weights_sum || !depth || !image) return NRF_E_INVALID;
+    if ((((uintptr_t)deltas) & 15) != 0) return NRF_E_INVALID;
+    if (n_alive_cap == 0) return NRF_OK;
+    k_composite_rays<<<ceil_div_u32(n_alive_cap, 128), 128, 0, (cudaStream_t)stream>>>(n_alive_cap, 1, T_thresh, rays_alive, rays_t, sigmas, rgbs,
+                                                                                     deltas, C, false, weights_sum, depth, image, ctl);
     return nrf_check_launch();
 }
 
 // stable compaction of the non-negative entries (replaces rays_alive[rays_alive >= 0], renderer.py:284)
 #define COMPACT_BLOCK 256
 __global__ void __launch_bounds__(COMPACT_BLOCK)
-k_compact_count(const int32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ block_sums) {
+k_compact_count(const int32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ block_sums, const int32_t* __restrict__ ctl) {
+    if (ctl) n = (uint32_t)ctl[0];
     const uint32_t i = blockIdx.x * COMPACT_BLOCK + threadIdx.x;
     const bool keep = i < n && in[i] >= 0;
     const int c = __syncthreads_count(keep);
@@ -999,8 +1036,10 @@ __global__ void k_compact_finish(const uint32_t* __restrict__ block_sums_scanned
     *n_out = (int32_t)*block_sums_scanned_end;
 }
 __global__ void __launch_bounds__(COMPACT_BLOCK)
-k_compact_write(const int32_t* __restrict__ in, uint32_t n, const uint32_t* __restrict__ block_offs, int32_t* __restrict__ out) {
+k_compact_write(const int32_t* __restrict__ in, uint32_t n, const uint32_t* __restrict__ block_offs, int32_t* __restrict__ out,
+                const int32_t* __restrict__ ctl) {
     __shared__ uint32_t warp_tot[COMPACT_BLOCK / 32];
+    if (ctl) n = (uint32_t)ctl[0];
     const uint32_t i = blockIdx.x * COMPACT_BLOCK + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int32_t v = i < n ? in[i] : -1;
@@ -1024,9 +1063,36 @@ NRF_EXPORT int nrf_compact_alive(const int32_t* in, uint32_t n, int32_t* out, in
     int32_t* total = (int32_t*)(block_sums + nb);
     cudaMemsetAsync(total, 0, 2 * sizeof(int32_t), s);
     cudaMemsetAsync(out, 0xFF, (size_t)n * sizeof(int32_t), s);      // entries past the new count read -1 (dead slots)
-    k_compact_count<<<nb, COMPACT_BLOCK, 0, s>>>(in, n, block_sums);
+    k_compact_count<<<nb, COMPACT_BLOCK, 0, s>>>(in, n, block_sums, nullptr);
     k_scan_block_sums<<<1, 1024, 0, s>>>(block_sums, nb, total, 0);
-    k_compact_write<<<nb, COMPACT_BLOCK, 0, s>>>(in, n, block_sums, out);
+    k_compact_write<<<nb, COMPACT_BLOCK, 0, s>>>(in, n, block_sums, out, nullptr);
     cudaMemcpyAsync(n_out, total, sizeof(int32_t), cudaMemcpyDeviceToDevice, s);
+    return nrf_check_launch();
+}
+
+// end of one iteration of the device-driven loop: the new alive count, the steps taken so far, the next n_step
+// (renderer.py:253: max(min(N // n_alive, 8), 1)) and the row count the next iteration's kernels will process
+__global__ void k_ctl_update(int32_t* __restrict__ ctl, const int32_t* __restrict__ total) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int n_alive = total[0];
+    const int steps = ctl[3] + ctl[1];
+    if (steps >= ctl[5]) n_alive = 0;                    // max_steps reached (renderer.py:249)
+    const int n_step = n_alive > 0 ? max(min(ctl[4] / n_alive, 8), 1) : 0;
+    ctl[0] = n_alive; ctl[1] = n_step; ctl[2] = n_alive * n_step; ctl[3] = steps; ctl[6] += 1;
+}
+
+NRF_EXPORT int nrf_compact_alive_dev(int32_t* ctl, uint32_t n_cap, const int32_t* in, int32_t* out, void* scratch, void* stream) {
+    if (!ctl || !in || !out || !scratch) return NRF_E_INVALID;
+    if (n_cap == 0) return NRF_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t nb = ceil_div_u32(n_cap, COMPACT_BLOCK);
+    uint32_t* block_sums = (uint32_t*)scratch;
+    int32_t* total = (int32_t*)(block_sums + nb);
+    cudaMemsetAsync(total, 0, 2 * sizeof(int32_t), s);
+    cudaMemsetAsync(out, 0xFF, (size_t)n_cap * sizeof(int32_t), s);
+    k_compact_count<<<nb, COMPACT_BLOCK, 0, s>>>(in, n_cap, block_sums, ctl);
+    k_scan_block_sums<<<1, 1024, 0, s>>>(block_sums, nb, total, 0);
+    k_compact_write<<<nb, COMPACT_BLOCK, 0, s>>>(in, n_cap, block_sums, out, ctl);
+    k_ctl_update<<<1, 32, 0, s>>>(ctl, total);
     return nrf_check_launch();
 }

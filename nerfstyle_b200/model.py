@@ -308,3 +308,125 @@ class Renderer(nn.Module):
         image = image + (1 - weights_sum).unsqueeze(-1)
         depth = torch.clamp(depth - nears, min=0) / (fars - nears)
         return image, depth, classes
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # device-driven inference loop (SURVEY.md 8f NEXT-2)
+    # ------------------------------------------------------------------------------------------------------------------
+    def _graph_state(self, N):
+        """Static buffers + the captured two-iteration CUDA graph for frames of N rays (built on first use)."""
+        st = getattr(self, '_gs', None)
+        if st is not None and st['N'] == N and st['dev'] == self.device:
+            return st
+        dev, Cch = self.device, self.raymarch_channels
+        cap = (N + 127) // 128 * 128                       # rows per iteration never exceed N (n_alive * n_step <= N)
+        f32, i32 = torch.float32, torch.int32
+        st = {'N': N, 'dev': dev, 'cap': cap, 'graph': None,
+              'rays_o': torch.empty(N, 3, dtype=f32, device=dev), 'rays_d': torch.empty(N, 3, dtype=f32, device=dev),
+              'nears': torch.empty(N, dtype=f32, device=dev), 'fars': torch.empty(N, dtype=f32, device=dev),
+              'rays_t': torch.empty(N, 1, dtype=f32, device=dev),
+              'alive': [torch.empty(N, dtype=i32, device=dev), torch.empty(N, dtype=i32, device=dev)],
+              'ctl': torch.zeros(8, dtype=i32, device=dev),
+              'xyzs': torch.zeros(cap, 3, dtype=f32, device=dev), 'dirs': torch.zeros(cap, 3, dtype=f32, device=dev),
+              'deltas': torch.zeros(cap, 4, dtype=f32, device=dev),
+              'enc_d': torch.zeros(cap, 32, dtype=torch.float16, device=dev), 'enc_c': torch.zeros(cap, 32, dtype=torch.float16, device=dev),
+              'c1': torch.zeros(cap, 16, dtype=torch.float16, device=dev),
+              'sigmas': torch.zeros(cap, 1, dtype=f32, device=dev), 'rgbs': torch.zeros(cap, Cch, dtype=f32, device=dev),
+              'weights_sum': torch.empty(N, dtype=f32, device=dev), 'depth': torch.empty(N, dtype=f32, device=dev),
+              'image': torch.empty(N, Cch, dtype=f32, device=dev),
+              'tab': [torch.empty_like(self.model.x_density_embedder.embeddings, dtype=torch.float16),
+                      torch.empty_like(self.model.x_color_embedder.embeddings, dtype=torch.float16)],
+              'w': {n: torch.empty(getattr(self.model, n).params.numel(), dtype=torch.float16, device=dev)
+                    for n in ('density_net', 'class_net', 'color1_net', 'color2_net')},
+              'scratch': torch.empty(int(raymarching.L.lib().nrf_march_scratch_bytes(N)) + 64, dtype=torch.uint8, device=dev)}
+        self._gs = st
+        return st
+
+    def _graph_iteration(self, st, a_in, a_out):
+        """One iteration of renderer.py:249-286 with every count on the device (ctl) and every launch sized for the cap."""
+        L = raymarching.L
+        lib, m = L.lib(), self.model
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        N, cap, ctl = st['N'], st['cap'], st['ctl']
+        enc = m.x_density_embedder
+        S = float(np.float32(np.log2(enc.per_level_scale)))
+        rows = ctl.data_ptr() + 8                                  # &ctl[2] = n_alive * n_step
+        L.check(lib.nrf_march_rays_dev(ctl.data_ptr(), N, a_in.data_ptr(), st['rays_t'].data_ptr(), st['rays_o'].data_ptr(),
+                                       st['rays_d'].data_ptr(), float(self.bound), 0.0, int(self.max_steps), int(self.cascade),
+                                       int(self.grid_size), self.density_bitfield.data_ptr(), st['fars'].data_ptr(),
+                                       st['xyzs'].data_ptr(), st['dirs'].data_ptr(), st['deltas'].data_ptr(), s), 'march_rays_dev')
+        L.check(lib.nrf_grid_encode_forward_dual_dev(st['xyzs'].data_ptr(), st['tab'][0].data_ptr(), st['tab'][1].data_ptr(),
+                                                     enc.offsets.data_ptr(), st['enc_d'].data_ptr(), st['enc_c'].data_ptr(), cap,
+                                                     enc.num_levels, S, int(enc.base_resolution), enc.gridtype_id,
+                                                     int(enc.align_corners), 0, L.DTYPE_F16, m._xform.data_ptr(), rows, s),
+                'grid_encode_forward_dual_dev')
+
+        def mlp(net, x, y, col, n_out, act):
+            L.check(lib.nrf_mlp_forward_dev(x.data_ptr(), L.dtype_code(x.dtype), st['w'][net].data_ptr(), cap,
+                                            getattr(m, net).n_input_dims, n_out, getattr(m, net).n_hidden_layers, 64,
+                                            getattr(m, net).hidden_act, act, y.data_ptr() + col * y.element_size(),
+                                            L.dtype_code(y.dtype), y.shape[1], rows, s), 'mlp_forward_dev')
+        mlp('density_net', st['enc_d'], st['sigmas'], 0, 1, L.ACT['trunc_exp'])
+        mlp('color1_net', st['enc_c'], st['c1'], 0, 16, m.color1_net.out_act)
+        mlp('color2_net', st['c1'], st['rgbs'], 0, 3, m.color2_net.out_act)
+        mlp('class_net', st['enc_c'], st['rgbs'], 3, m.class_dim, m.class_net.out_act)
+        if self.density_scale != 1.0:
+            st['sigmas'].mul_(self.density_scale)
+        L.check(lib.nrf_composite_rays_dev(ctl.data_ptr(), N, float(self.t_thresh), a_in.data_ptr(), st['rays_t'].data_ptr(),
+                                           st['sigmas'].data_ptr(), st['rgbs'].data_ptr(), st['deltas'].data_ptr(),
+                                           self.raymarch_channels, st['weights_sum'].data_ptr(), st['depth'].data_ptr(),
+                                           st['image'].data_ptr(), s), 'composite_rays_dev')
+        L.check(lib.nrf_compact_alive_dev(ctl.data_ptr(), N, a_in.data_ptr(), a_out.data_ptr(), st['scratch'].data_ptr(), s),
+                'compact_alive_dev')
+
+    @torch.no_grad()
+    def render_test_graph(self, rays_o, rays_d, check_every=4):
+        """render_test with the loop driven from the device: the per-iteration host logic of renderer.py:249-286 (alive
+        count, n_step, buffer sizes) lives in a control block updated by the compaction kernel, every launch is sized for
+        the cap, and a PAIR of iterations (the alive list ping-pongs between two buffers) is captured once in a CUDA graph
+        and replayed; the host only reads the alive count every `check_every` replays.  Same kernels and numerics as
+        render_test; needs the fused-head model (default) under AMP-style fp16 tables."""
+        m = self.model
+        if not (getattr(m, 'fused_heads', False) and m.class_dim + 3 == self.raymarch_channels):
+            raise RuntimeError('render_test_graph needs the fused-head StyleTCNerf')
+        if m._dual is None:
+            m._dual = bool(same_geometry(m.x_density_embedder, m.x_color_embedder))
+            m._xform = torch.cat([m.bbox_min, m.bbox_size, m.bbox_min.new_ones(1)]).contiguous()
+        if not m._dual:
+            raise RuntimeError('render_test_graph needs the two encoders to share their geometry')
+        rays_o = rays_o.float().contiguous().view(-1, 3)
+        rays_d = rays_d.float().contiguous().view(-1, 3)
+        N = rays_o.shape[0]
+        st = self._graph_state(N)
+        st['rays_o'].copy_(rays_o); st['rays_d'].copy_(rays_d)
+        nears, fars = raymarching.near_far_from_aabb(st['rays_o'], st['rays_d'], self.aabb, self.min_near)
+        st['nears'].copy_(nears); st['fars'].copy_(fars)
+        st['rays_t'].copy_(nears[:, None])
+        st['weights_sum'].zero_(); st['depth'].zero_(); st['image'].zero_()
+        st['alive'][0].copy_(torch.arange(N, dtype=torch.int32, device=self.device))
+        st['ctl'].copy_(torch.tensor([N, 1, N, 0, N, self.max_steps, 0, 0], dtype=torch.int32))
+        for i, e in enumerate((m.x_density_embedder, m.x_color_embedder)):       # fp16 tables / weights for this frame
+            st['tab'][i].copy_(getattr(e.embeddings, '_nrf_half_copy', e.embeddings.detach()))
+        for n in st['w']:
+            st['w'][n].copy_(getattr(m, n).params.detach())
+        if st['graph'] is None:
+            # the first pair runs eagerly (it is real work: the two largest iterations, and it initialises the kernels'
+            # attributes), then the same pair is captured for every later replay
+            self._graph_iteration(st, st['alive'][0], st['alive'][1])
+            self._graph_iteration(st, st['alive'][1], st['alive'][0])
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._graph_iteration(st, st['alive'][0], st['alive'][1])
+                self._graph_iteration(st, st['alive'][1], st['alive'][0])
+            st['graph'] = g
+        it = 0
+        while True:
+            if it % check_every == 0 and int(st['ctl'][0].item()) <= 0:      # the loop's only host sync
+                break
+            st['graph'].replay()
+            it += 1
+        image = st['image']
+        classes = image[:, 3:].clone()
+        rgb = image[:, :3] + (1 - st['weights_sum']).unsqueeze(-1)
+        depth = torch.clamp(st['depth'] - st['nears'], min=0) / (st['fars'] - st['nears'])
+        return rgb, depth, classes

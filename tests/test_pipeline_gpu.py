@@ -208,3 +208,23 @@ def test_trainstep_async_loss_readback(cuda_lib, dev):
         loss = ts.step(o, d, tgt, seg, loss_host=pin)
         ts.loss_ready.synchronize()
         assert abs(float(pin[0]) - float(loss)) < 1e-7 and np.isfinite(float(pin[0]))
+
+
+def test_render_test_graph_equals_reference_loop(cuda_lib, dev):
+    """The device-driven loop (control block on the device, a pair of iterations replayed from a CUDA graph) renders
+    the same image as the reference's host-driven loop -- first frame (eager pair + capture) and later frames (replay
+    only), with early termination active."""
+    of, m, r, o, d, bits = _build(dev, half_tables=True, n_rays=3000, table_std=0.5)
+    r.density_scale = 20.0
+    with torch.no_grad(), torch.autocast('cuda', dtype=torch.float16):
+        a = r.render_test(o, d, sync_every=1)
+        for frame in range(3):
+            b = r.render_test_graph(o, d)
+            for x, y in zip(a, b):
+                torch.testing.assert_close(x, y, rtol=1e-5, atol=1e-6)
+        o2, d2 = o.flip(0).contiguous(), d.flip(0).contiguous()          # another frame through the same captured graph
+        a2 = r.render_test(o2, d2, sync_every=1)
+        b2 = r.render_test_graph(o2, d2)
+        for x, y in zip(a2, b2):
+            torch.testing.assert_close(x, y, rtol=1e-5, atol=1e-6)
+    assert int(r._gs['ctl'][0]) == 0 and int(r._gs['ctl'][6]) > 0

@@ -58,7 +58,10 @@ def render(args):
         sync(world)
         t0 = time.perf_counter()
         with torch.no_grad(), torch.autocast('cuda', dtype=torch.float16):
-            img, depth, cls = r.render_test(o, d, sync_every=args.sync_every)
+            if args.loop == 'graph':
+                img, depth, cls = r.render_test_graph(o, d)
+            else:
+                img, depth, cls = r.render_test(o, d, sync_every=args.sync_every)
         full = parallel.gather_rows(torch.cat([img, depth[:, None], cls], dim=1), n_total, rank, world)
         sync(world)
         if f > 0:
@@ -71,7 +74,7 @@ def render(args):
         print(json.dumps({'config': 'render_full_frame', 'w': args.w, 'h': args.h, 'n_gpus': world, 'rays_per_frame': n_total,
                           'ms_per_frame': round(sec * 1e3, 2), 'mrays_per_s': round(n_total / sec / 1e6, 3),
                           'occupancy': args.occupancy, 'density_scale': args.density_scale, 'frames': args.frames,
-                          'sync_every': args.sync_every,
+                          'sync_every': args.sync_every, 'loop': args.loop,
                           'gathered_bytes': int(n_total * (4 + B.N_CLASSES) * 4)}))
     if world > 1:
         dist.destroy_process_group()
@@ -169,5 +172,6 @@ if __name__ == '__main__':
     ap.add_argument('--occupancy', default='field', choices=['field', 'analytic'])
     ap.add_argument('--density-scale', type=float, default=1.0)
     ap.add_argument('--sync-every', type=int, default=4)
+    ap.add_argument('--loop', default='graph', choices=['graph', 'host'])
     a = ap.parse_args()
     {'render': render, 'nnfm': nnfm_bench, 'sweep': sweep}[a.what](a)
