@@ -370,7 +370,7 @@ def extras(device, peaks):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         with torch.no_grad(), torch.autocast('cuda', dtype=torch.float16):
-            img, depth, cls = r.render_test(o, d)
+            img, depth, cls = r.render_test_graph(o, d)       # device-driven loop (CUDA graph), nerfstyle_b200/model.py
         float(img.sum().item())              # D2H read of the frame's checksum
         if f > 0:
             ms.append((time.perf_counter() - t0) * 1e3)
