@@ -225,7 +225,8 @@ int nrf_mlp_backward_ex(const void* x, int x_dtype, const void* params_f16, cons
  * for the caps (n_alive_cap = N rays, B_cap >= N rows since n_alive * n_step <= N), so an iteration is shape-static and
  * can be captured in a CUDA graph and replayed with no host involvement; the host reads ctl[0] every few iterations to
  * stop.  Kernels and numerics are those of nrf_march_rays / nrf_composite_rays / nrf_compact_alive /
- * nrf_grid_encode_forward_dual / nrf_mlp_forward_ex; rows >= ctl[2] are left untouched. */
+ * nrf_grid_encode_forward_dual / nrf_mlp_forward_ex; rows >= ctl[2] are left untouched.  row_deltas (the [B,4] deltas of
+ * march_rays, or NULL) lets the encoder skip padding slots (delta == 0: composite_rays never reads them). */
 int nrf_march_rays_dev(const int32_t* ctl, uint32_t n_alive_cap, const int32_t* rays_alive, const float* rays_t,
                        const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C,
                        uint32_t H, const uint8_t* grid, const float* fars, float* xyzs, float* dirs, float* deltas,
@@ -237,7 +238,7 @@ int nrf_compact_alive_dev(int32_t* ctl, uint32_t n_cap, const int32_t* in, int32
 int nrf_grid_encode_forward_dual_dev(const float* inputs, const void* embeddings0, const void* embeddings1,
                                      const int32_t* offsets, void* outputs0, void* outputs1, uint32_t B_cap, uint32_t L,
                                      float S, uint32_t H, uint32_t gridtype, int align_corners, uint32_t style, int dtype,
-                                     const float* xform, const int32_t* B_dev, void* stream);
+                                     const float* xform, const int32_t* B_dev, const float* row_deltas, void* stream);
 int nrf_mlp_forward_dev(const void* x, int x_dtype, const void* params_f16, uint32_t B_cap, uint32_t n_in, uint32_t n_out,
                         uint32_t n_hidden, uint32_t width, int hidden_act, int out_act, void* y, int y_dtype,
                         uint32_t ld_y, const int32_t* B_dev, void* stream);

@@ -60,7 +60,7 @@ SIGNATURES = {
     'nrf_composite_rays_dev': (_i32, [_vp, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
     'nrf_compact_alive_dev': (_i32, [_vp, _u32, _vp, _vp, _vp, _vp]),
     'nrf_grid_encode_forward_dual_dev': (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _f32, _u32, _u32, _i32, _u32, _i32,
-                                                _vp, _vp, _vp]),
+                                                _vp, _vp, _vp, _vp]),
     'nrf_mlp_forward_dev': (_i32, [_vp, _i32, _vp, _u32, _u32, _u32, _u32, _u32, _i32, _i32, _vp, _i32, _u32, _vp, _vp]),
     'nrf_sh_encode_forward': (_i32, [_vp, _u32, _u32, _vp, _i32, _vp]),
     'nrf_nnfm_forward': (_i32, [_vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),

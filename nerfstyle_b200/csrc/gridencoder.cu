@@ -121,10 +121,11 @@ __global__ void __launch_bounds__(GRID_BLOCK)
 k_grid_fwd_d3c2(const float* __restrict__ inputs, const T* __restrict__ table0, const T* __restrict__ table1,
                 const int32_t* __restrict__ offsets, T* __restrict__ outputs0, T* __restrict__ outputs1, uint32_t B, uint32_t L,
                 float S, uint32_t H, uint32_t gridtype, bool align_corners, uint32_t style, bool point_major,
-                const float* __restrict__ xform, const int32_t* __restrict__ B_dev) {
+                const float* __restrict__ xform, const int32_t* __restrict__ B_dev, const float4* __restrict__ row_deltas) {
     typedef typename Vec2<T>::type V2;
     __shared__ LevelP lp[LPT];
     if (B_dev) B = min(B, (uint32_t)*B_dev);      // device-driven inference loop: the launch is sized for the cap
+    if (blockIdx.x * GRID_BLOCK >= B) return;     // (block-uniform) nothing to do: leave before the level set-up
     const uint32_t l0 = blockIdx.y * LPT;
     if (threadIdx.x < LPT && l0 + threadIdx.x < L) level_setup(lp[threadIdx.x], offsets, l0 + threadIdx.x, 3, S, H, gridtype, align_corners, style);
     __syncthreads();
@@ -132,7 +133,10 @@ k_grid_fwd_d3c2(const float* __restrict__ inputs, const T* __restrict__ table0, 
     if (b >= B) return;
     float x = __ldg(inputs + 3 * (size_t)b), y = __ldg(inputs + 3 * (size_t)b + 1), z = __ldg(inputs + 3 * (size_t)b + 2);
     if (xform) { x = xform1(x, xform, 0); y = xform1(y, xform, 1); z = xform1(z, xform, 2); }
-    const bool oob = (x < 0 || x > 1) || (y < 0 || y > 1) || (z < 0 || z > 1);   // gridencoder.cu:107-114
+    bool oob = (x < 0 || x > 1) || (y < 0 || y > 1) || (z < 0 || z > 1);   // gridencoder.cu:107-114
+    // inference loop: a sample slot with delta == 0 is padding (its ray left the volume before the slot was used);
+    // composite_rays stops at it (raymarching.cu:1173), so its encoding is never read -- skip the 256 gathers
+    if (row_deltas && __ldg(&row_deltas[b]).x == 0.0f) oob = true;
     V2 res[NE][LPT];
 #pragma unroll
     for (int j = 0; j < LPT; j++) {
@@ -327,7 +331,7 @@ static int launch_fwd(const float* inputs, const void* embeddings, const int32_t
     const uint32_t nbx = ceil_div_u32(B, GRID_BLOCK);
     if (D == 3 && C == 2 && !calc && (((uintptr_t)embeddings) & 7) == 0) {
         const int lpt = g_fwd_lpt;
-#define FWD_FAST(LPT) k_grid_fwd_d3c2<T, LPT, 1><<<dim3(nbx, ceil_div_u32(L, LPT)), GRID_BLOCK, 0, s>>>(inputs, tab, nullptr, offsets, out, nullptr, B, L, S, H, gridtype, ac, style, pm, nullptr, nullptr)
+#define FWD_FAST(LPT) k_grid_fwd_d3c2<T, LPT, 1><<<dim3(nbx, ceil_div_u32(L, LPT)), GRID_BLOCK, 0, s>>>(inputs, tab, nullptr, offsets, out, nullptr, B, L, S, H, gridtype, ac, style, pm, nullptr, nullptr, nullptr)
         if (lpt >= 16) FWD_FAST(16); else if (lpt >= 8) FWD_FAST(8); else if (lpt >= 4) FWD_FAST(4); else if (lpt >= 2) FWD_FAST(2); else FWD_FAST(1);
 #undef FWD_FAST
         return nrf_check_launch();
@@ -614,39 +618,40 @@ NRF_EXPORT int nrf_grid_encode_backward(const void* grad, const float* inputs, c
 template <typename T>
 static int launch_fwd_dual(const float* inputs, const void* e0, const void* e1, const int32_t* offsets, void* o0, void* o1, uint32_t B,
                            uint32_t L, float S, uint32_t H, uint32_t gridtype, bool ac, uint32_t style, const float* xform,
-                           const int32_t* B_dev, cudaStream_t s) {
+                           const int32_t* B_dev, const float* row_deltas, cudaStream_t s) {
     const uint32_t nbx = ceil_div_u32(B, GRID_BLOCK);
     // 8 levels per thread keeps the register footprint of the two result sets at the single-encoder kernel's (48 regs)
     k_grid_fwd_d3c2<T, 8, 2><<<dim3(nbx, ceil_div_u32(L, 8)), GRID_BLOCK, 0, s>>>(inputs, (const T*)e0, (const T*)e1, offsets, (T*)o0, (T*)o1,
-                                                                                B, L, S, H, gridtype, ac, style, true, xform, B_dev);
+                                                                                B, L, S, H, gridtype, ac, style, true, xform, B_dev, reinterpret_cast<const float4*>(row_deltas));
     return nrf_check_launch();
 }
 
 NRF_EXPORT int nrf_grid_encode_forward_dual_dev(const float* inputs, const void* embeddings0, const void* embeddings1,
                                                 const int32_t* offsets, void* outputs0, void* outputs1, uint32_t B_cap, uint32_t L,
                                                 float S, uint32_t H, uint32_t gridtype, int align_corners, uint32_t style, int dtype,
-                                                const float* xform, const int32_t* B_dev, void* stream);
+                                                const float* xform, const int32_t* B_dev, const float* row_deltas, void* stream);
 
 NRF_EXPORT int nrf_grid_encode_forward_dual(const float* inputs, const void* embeddings0, const void* embeddings1,
                                             const int32_t* offsets, void* outputs0, void* outputs1, uint32_t B, uint32_t L, float S,
                                             uint32_t H, uint32_t gridtype, int align_corners, uint32_t style, int dtype,
                                             const float* xform, void* stream) {
     return nrf_grid_encode_forward_dual_dev(inputs, embeddings0, embeddings1, offsets, outputs0, outputs1, B, L, S, H, gridtype,
-                                            align_corners, style, dtype, xform, nullptr, stream);
+                                            align_corners, style, dtype, xform, nullptr, nullptr, stream);
 }
 
-// B_dev (device int32, or NULL): the number of rows actually present (<= B_cap, which sizes the launch)
+// B_dev (device int32, or NULL): the number of rows actually present (<= B_cap, which sizes the launch).
+// row_deltas (the [B,4] deltas of march_rays, or NULL): rows whose delta is 0 are padding slots and get zeros.
 NRF_EXPORT int nrf_grid_encode_forward_dual_dev(const float* inputs, const void* embeddings0, const void* embeddings1,
                                                 const int32_t* offsets, void* outputs0, void* outputs1, uint32_t B, uint32_t L,
                                                 float S, uint32_t H, uint32_t gridtype, int align_corners, uint32_t style, int dtype,
-                                                const float* xform, const int32_t* B_dev, void* stream) {
+                                                const float* xform, const int32_t* B_dev, const float* row_deltas, void* stream) {
     if (B == 0) return NRF_OK;
     if (!inputs || !embeddings0 || !embeddings1 || !offsets || !outputs0 || !outputs1) return NRF_E_INVALID;
     if (L == 0 || L > GRID_MAX_LEVELS) return NRF_E_UNSUPPORTED;
     if ((((uintptr_t)embeddings0) & 7) || (((uintptr_t)embeddings1) & 7)) return NRF_E_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
-    if (dtype == NRF_DTYPE_F32) return launch_fwd_dual<float>(inputs, embeddings0, embeddings1, offsets, outputs0, outputs1, B, L, S, H, gridtype, align_corners != 0, style, xform, B_dev, s);
-    if (dtype == NRF_DTYPE_F16) return launch_fwd_dual<__half>(inputs, embeddings0, embeddings1, offsets, outputs0, outputs1, B, L, S, H, gridtype, align_corners != 0, style, xform, B_dev, s);
+    if (dtype == NRF_DTYPE_F32) return launch_fwd_dual<float>(inputs, embeddings0, embeddings1, offsets, outputs0, outputs1, B, L, S, H, gridtype, align_corners != 0, style, xform, B_dev, row_deltas, s);
+    if (dtype == NRF_DTYPE_F16) return launch_fwd_dual<__half>(inputs, embeddings0, embeddings1, offsets, outputs0, outputs1, B, L, S, H, gridtype, align_corners != 0, style, xform, B_dev, row_deltas, s);
     return NRF_E_UNSUPPORTED;
 }
 

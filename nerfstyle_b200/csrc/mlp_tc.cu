@@ -338,6 +338,7 @@ k_mlp_fwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ pa
              int hidden_act, int out_act, void* __restrict__ y, int y_dt, uint32_t ld_y, const int32_t* __restrict__ B_dev) {
     constexpr int IN_PAD = IN_KT * 16;
     if (B_dev) B = min(B, (uint32_t)*B_dev);      // device-driven inference loop: the launch is sized for the cap
+    if (blockIdx.x >= (B + 127) / 128) return;    // a CTA without a tile leaves before it allocates TMEM / stages weights
     constexpr int CPR = IN_PAD / 8;                      // 16-byte chunks per input row
     constexpr uint32_t CH = ch_for(IN_KT);
     constexpr TcSmem L = fwd_smem<IN_KT, NH>();

@@ -979,19 +979,44 @@ k_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* __r
     if (is_ndc) { t_rm = rt[0]; t_phy = rt[1]; } else { t_phy = rt[0]; }
     float weight_sum = weights_sum[index], d = depth[index];
     uint32_t step = 0;
-    while (step < n_step) {
-        const float4 dl = __ldg(dl4 + step);
-        if (dl.x == 0.0f) break;
-        const float alpha = alpha_from(__ldg(s + step), is_ndc ? dl.z : dl.x);
-        const float T = 1.0f - weight_sum;
-        const float w = alpha * T;
-        weight_sum += w;
-        if (is_ndc) { t_rm += dl.y; t_phy += dl.w; } else { t_phy += dl.y; }
-        d = __fmaf_rn(w, t_phy, d);
-        const float* rr = r + (size_t)step * C;
-        for (uint32_t c = 0; c < C; c++) img[c] = __fmaf_rn(w, __ldg(rr + c), img[c]);
-        if (T < T_thresh) break;
-        step++;
+    if (C <= 16) {
+        // the ray's image row stays in registers across its n_step samples (the reference does a global read-modify-write
+        // per sample per channel, raymarching.cu:1196-1198); same fma order per channel -> same bits
+        float acc[16];
+#pragma unroll
+        for (int c = 0; c < 16; c++) acc[c] = ((uint32_t)c < C) ? img[c] : 0.0f;
+        while (step < n_step) {
+            const float4 dl = __ldg(dl4 + step);
+            if (dl.x == 0.0f) break;
+            const float alpha = alpha_from(__ldg(s + step), is_ndc ? dl.z : dl.x);
+            const float T = 1.0f - weight_sum;
+            const float w = alpha * T;
+            weight_sum += w;
+            if (is_ndc) { t_rm += dl.y; t_phy += dl.w; } else { t_phy += dl.y; }
+            d = __fmaf_rn(w, t_phy, d);
+            const float* rr = r + (size_t)step * C;
+#pragma unroll
+            for (int c = 0; c < 16; c++) if ((uint32_t)c < C) acc[c] = __fmaf_rn(w, __ldg(rr + c), acc[c]);
+            if (T < T_thresh) break;
+            step++;
+        }
+#pragma unroll
+        for (int c = 0; c < 16; c++) if ((uint32_t)c < C) img[c] = acc[c];
+    } else {
+        while (step < n_step) {
+            const float4 dl = __ldg(dl4 + step);
+            if (dl.x == 0.0f) break;
+            const float alpha = alpha_from(__ldg(s + step), is_ndc ? dl.z : dl.x);
+            const float T = 1.0f - weight_sum;
+            const float w = alpha * T;
+            weight_sum += w;
+            if (is_ndc) { t_rm += dl.y; t_phy += dl.w; } else { t_phy += dl.y; }
+            d = __fmaf_rn(w, t_phy, d);
+            const float* rr = r + (size_t)step * C;
+            for (uint32_t c = 0; c < C; c++) img[c] = __fmaf_rn(w, __ldg(rr + c), img[c]);
+            if (T < T_thresh) break;
+            step++;
+        }
     }
     if (step < n_step) rays_alive[n] = -1;
     else { if (is_ndc) { rt[0] = t_rm; rt[1] = t_phy; } else rt[0] = t_phy; }

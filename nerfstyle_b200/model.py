@@ -357,7 +357,8 @@ class Renderer(nn.Module):
         L.check(lib.nrf_grid_encode_forward_dual_dev(st['xyzs'].data_ptr(), st['tab'][0].data_ptr(), st['tab'][1].data_ptr(),
                                                      enc.offsets.data_ptr(), st['enc_d'].data_ptr(), st['enc_c'].data_ptr(), cap,
                                                      enc.num_levels, S, int(enc.base_resolution), enc.gridtype_id,
-                                                     int(enc.align_corners), 0, L.DTYPE_F16, m._xform.data_ptr(), rows, s),
+                                                     int(enc.align_corners), 0, L.DTYPE_F16, m._xform.data_ptr(), rows,
+                                                     st['deltas'].data_ptr(), s),
                 'grid_encode_forward_dual_dev')
 
         def mlp(net, x, y, col, n_out, act):
