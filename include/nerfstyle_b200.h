@@ -22,6 +22,7 @@
  *   gridencoder/src/gridencoder.h:14  grid_initialize      nrf_grid_initialize
  *   tinycudann Network fwd/bwd (networks/style_nerf.py:44-98)   nrf_mlp_forward / nrf_mlp_backward
  *   loss.py:32-36,199-214 cosine_dists + mask + amin       nrf_nnfm_forward (backward = gather, nnfm.py)
+ *   nerf_lib.py:69-142 NerfLib.generate_rays (+ RayBatch)  nrf_generate_rays
  *
  * Conventions: all pointers are DEVICE pointers owned by the caller; the callee never
  * allocates, never synchronises and never throws.  Every function launches on `stream` (a
@@ -177,6 +178,18 @@ int nrf_grid_encode_backward_dual(const void* grad0, const void* grad1, const fl
                                   uint32_t gridtype, int align_corners, uint32_t style, int dtype, int grad_table_dtype,
                                   const float* xform, void* stream);
 
+/* Paired forms of the dual entry points: the two tables of a same-geometry encoder pair live in ONE interleaved buffer
+ * [row][encoder][2] (`table_pair`, in the tables' dtype; 16-byte aligned) and so do their f32 gradients (`grad_pair`), so a
+ * corner of both encoders is one vector gather / one 16-byte reduction.  Values are those of the dual forms.
+ * B_dev / row_deltas as in nrf_grid_encode_forward_dual_dev (NULL, NULL for the plain call). */
+int nrf_grid_encode_forward_pair(const float* inputs, const void* table_pair, const int32_t* offsets, void* outputs0,
+                                 void* outputs1, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                                 int align_corners, uint32_t style, int dtype, const float* xform, const int32_t* B_dev,
+                                 const float* row_deltas, void* stream);
+int nrf_grid_encode_backward_pair(const void* grad0, const void* grad1, const float* inputs, const int32_t* offsets,
+                                  float* grad_pair, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                                  int align_corners, uint32_t style, int dtype, const float* xform, void* stream);
+
 /* gridencoder.cu:551-571 (D=3, C=2, f32 like the reference's only use). */
 int nrf_grid_initialize(const float* ref_embeddings, float* embeddings, const int32_t* ref_offsets,
                         const int32_t* offsets, uint32_t L, float S, uint32_t H, uint32_t Ns, void* stream);
@@ -274,6 +287,19 @@ int nrf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   uint64_t n, const void* state, float lr0, float lr_decay_steps, float beta1, float beta2, float eps,
                   float ema_one_minus_decay, void* stream);
 int nrf_scaler_update(void* state, float growth, float backoff, int growth_interval, void* stream);
+
+/* ------------------------------------------------------------------ ray generation (SURVEY 8f NEXT-1) */
+
+/* NerfLib.generate_rays (nerf_lib.py:69-142) + RayBatch.__post_init__ (common.py:139-147) for K rays in one launch.
+ * pose: row-major 4x4 camera-to-world f32 (device).  fx, fy, cx, cy: intrinsics rounded to f32 (numpy does the same).
+ * The crop window starts at pixel (x0, y0) and is win_w pixels wide (precrop / patch, nerf_lib.py:109-116); ray k is
+ * window pixel id = indices ? indices[k] : k (row-major: row = id / win_w, col = id % win_w -- the `indices_1d` of
+ * nerf_lib.py:132-134).  camera_flip: bit 2/1/0 negates x/y/z of the camera-frame direction (:122-123).
+ * Outputs rays_o, rays_d [K,3] f32 (rays_d unit length).  img ([3,img_h,img_w] f32, or NULL): target [K,3] receives the
+ * pixel under each ray (:135-137). */
+int nrf_generate_rays(const float* pose, float fx, float fy, float cx, float cy, uint32_t x0, uint32_t y0, uint32_t win_w,
+                      uint32_t K, const int64_t* indices, int camera_flip, const float* img, uint32_t img_w,
+                      uint32_t img_h, float* rays_o, float* rays_d, float* target, void* stream);
 
 #ifdef __cplusplus
 }

@@ -49,6 +49,9 @@ SIGNATURES = {
                                             _vp]),
     'nrf_grid_encode_backward_dual': (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _f32, _u32, _u32, _i32, _u32, _i32, _i32,
                                              _vp, _vp]),
+    'nrf_grid_encode_forward_pair': (_i32, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _f32, _u32, _u32, _i32, _u32, _i32, _vp, _vp,
+                                            _vp, _vp]),
+    'nrf_grid_encode_backward_pair': (_i32, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _f32, _u32, _u32, _i32, _u32, _i32, _vp, _vp]),
     'nrf_grid_initialize': (_i32, [_vp, _vp, _vp, _vp, _u32, _f32, _u32, _u32, _vp]),
     'nrf_mlp_forward': (_i32, [_vp, _i32, _vp, _u32, _u32, _u32, _u32, _u32, _i32, _i32, _vp, _i32, _vp]),
     'nrf_mlp_backward': (_i32, [_vp, _i32, _vp, _vp, _i32, _u32, _u32, _u32, _u32, _u32, _i32, _i32, _f32, _vp, _i32,
@@ -69,6 +72,8 @@ SIGNATURES = {
     'nrf_grads_check': (_i32, [_vp, _u64, _vp, _vp]),
     'nrf_adam_step': (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _u64, _vp, _f32, _f32, _f32, _f32, _f32, _f32, _vp]),
     'nrf_scaler_update': (_i32, [_vp, _f32, _f32, _i32, _vp]),
+    'nrf_generate_rays': (_i32, [_vp, _f32, _f32, _f32, _f32, _u32, _u32, _u32, _u32, _vp, _i32, _vp, _u32, _u32, _vp, _vp,
+                                 _vp, _vp]),
 }
 # tuning / extension entry points that are not part of the reference-replacing ABI
 EXTRA_SIGNATURES = {
@@ -91,10 +96,10 @@ KERNELS_PER_CALL = {
     'nrf_march_rays_train_count': 4, 'nrf_march_rays_train_write': 1, 'nrf_march_rays_train': 4,
     'nrf_composite_rays_train_forward': 1, 'nrf_composite_rays_train_backward': 1, 'nrf_march_rays': 1,
     'nrf_composite_rays': 1, 'nrf_compact_alive': 3, 'nrf_grid_encode_forward': 1, 'nrf_grid_encode_backward': 1, 'nrf_grid_encode_forward_dual': 1,
-    'nrf_grid_encode_backward_dual': 1,
+    'nrf_grid_encode_backward_dual': 1, 'nrf_grid_encode_forward_pair': 1, 'nrf_grid_encode_backward_pair': 1,
     'nrf_grid_initialize': 1, 'nrf_mlp_forward': 1, 'nrf_mlp_backward': 1, 'nrf_sh_encode_forward': 1, 'nrf_march_rays_dev': 1,
     'nrf_composite_rays_dev': 1, 'nrf_compact_alive_dev': 4, 'nrf_grid_encode_forward_dual_dev': 1, 'nrf_mlp_forward_dev': 1, 'nrf_mlp_forward_ex': 1, 'nrf_mlp_backward_ex': 1, 'nrf_nnfm_forward': 5,
-    'nrf_adam_step': 1, 'nrf_grads_check': 1, 'nrf_scaler_update': 1,
+    'nrf_adam_step': 1, 'nrf_grads_check': 1, 'nrf_scaler_update': 1, 'nrf_generate_rays': 1,
 }
 
 

@@ -116,7 +116,15 @@ __device__ __forceinline__ uint32_t h2u(float2) { return 0u; }
 // NE = 2: two encoders with IDENTICAL geometry (offsets, scale, resolution) evaluated in one pass -- positions, hash rows
 // and trilinear weights are computed once and reused for both tables (the model's x_density_embedder / x_color_embedder,
 // networks/style_nerf.py:29-30, are such a pair).
-template <typename T, int LPT, int NE>
+// PAIR (NE = 2 only): the two tables are ONE interleaved buffer [row][encoder][2] (table0; 8 bytes per row in f16, 16 in
+// f32), so a corner of both encoders is a single vector gather from a single sector instead of two.
+template <typename T> struct Vec4;
+template <> struct Vec4<float> { typedef float4 type; };
+template <> struct Vec4<__half> { typedef uint2 type; };
+__device__ __forceinline__ float2 pair_part(const float4& q, int e) { return e == 0 ? make_float2(q.x, q.y) : make_float2(q.z, q.w); }
+__device__ __forceinline__ __half2 pair_part(const uint2& q, int e) { uint32_t u = e == 0 ? q.x : q.y; return *reinterpret_cast<__half2*>(&u); }
+
+template <typename T, int LPT, int NE, bool PAIR = false>
 __global__ void __launch_bounds__(GRID_BLOCK)
 k_grid_fwd_d3c2(const float* __restrict__ inputs, const T* __restrict__ table0, const T* __restrict__ table1,
                 const int32_t* __restrict__ offsets, T* __restrict__ outputs0, T* __restrict__ outputs1, uint32_t B, uint32_t L,
@@ -153,12 +161,23 @@ k_grid_fwd_d3c2(const float* __restrict__ inputs, const T* __restrict__ table0, 
         uint32_t rows[8]; float w[8];
         corner_rows_d3(p, cx, cy, cz, rows);
         corner_weights_d3(fx, fy, fz, w);
+        typename Vec4<T>::type q[PAIR ? 8 : 1];
+        if constexpr (PAIR) {
+            const typename Vec4<T>::type* tp = reinterpret_cast<const typename Vec4<T>::type*>(table0) + p.offset;
+#pragma unroll
+            for (int k = 0; k < 8; k++) q[k] = __ldg(tp + rows[k]);
+        }
 #pragma unroll
         for (int e = 0; e < NE; e++) {
-            const V2* tl = reinterpret_cast<const V2*>(e == 0 ? table0 : table1) + p.offset;
             V2 v[8];
+            if constexpr (PAIR) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) v[k] = __ldg(tl + rows[k]);
+                for (int k = 0; k < 8; k++) v[k] = pair_part(q[k], e);
+            } else {
+                const V2* tl = reinterpret_cast<const V2*>(e == 0 ? table0 : table1) + p.offset;
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[k] = __ldg(tl + rows[k]);
+            }
             if constexpr (sizeof(T) == 4) {
                 float r0 = 0.0f, r1 = 0.0f;   // gridencoder.cu:177 compiles to fma.rn
 #pragma unroll
@@ -382,8 +401,10 @@ __device__ __forceinline__ void scatter_cell(TO* gl, const uint32_t (&rows)[8], 
 
 // NE = 2: the gradients of two encoders with identical geometry are scattered in one pass (cells, hash rows, weights
 // and the warp-aggregation bookkeeping are computed once).
-template <typename T, typename TO, int LPT, int NE>
-__global__ void __launch_bounds__(GRID_BLOCK, NE == 1 ? 1 : 4)
+// PAIR (NE = 2, TO = float only): grad_table0 is ONE interleaved gradient buffer [row][encoder][2] and a corner of both
+// encoders is a single 16-byte reduction.
+template <typename T, typename TO, int LPT, int NE, bool PAIR = false>
+__global__ void __launch_bounds__(GRID_BLOCK, NE == 1 ? 1 : (PAIR ? 3 : 4))
 k_grid_bwd_d3c2(const T* __restrict__ grad0, const T* __restrict__ grad1, const float* __restrict__ inputs,
                 const int32_t* __restrict__ offsets, TO* __restrict__ grad_table0, TO* __restrict__ grad_table1, uint32_t B, uint32_t L,
                 float S, uint32_t H, uint32_t gridtype, bool align_corners, uint32_t style, bool point_major, int agg_max_groups,
@@ -468,6 +489,52 @@ k_grid_bwd_d3c2(const T* __restrict__ grad0, const T* __restrict__ grad1, const 
             const uint32_t span = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
             agg = __all_sync(NRF_FULL_MASK, cellmask == span);
             if (agg) maxlen = (int)__reduce_max_sync(NRF_FULL_MASK, (unsigned)(hi - lo + 1));
+        }
+        if constexpr (PAIR) {
+            float g[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            if (active) {
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    if constexpr (sizeof(T) == 4) {
+                        g[2 * e] = __uint_as_float(sg[e][threadIdx.x * ROW + j * 2]);
+                        g[2 * e + 1] = __uint_as_float(sg[e][threadIdx.x * ROW + j * 2 + 1]);
+                    } else {
+                        uint32_t u = sg[e][threadIdx.x * ROW + j];
+                        const float2 gg = __half22float2(*reinterpret_cast<__half2*>(&u));
+                        g[2 * e] = gg.x; g[2 * e + 1] = gg.y;
+                    }
+                }
+            }
+            const uint32_t nzmask = __ballot_sync(NRF_FULL_MASK, g[0] != 0.0f || g[1] != 0.0f || g[2] != 0.0f || g[3] != 0.0f);
+            if (nzmask == 0u) continue;
+            float4* gl = reinterpret_cast<float4*>(grad_table0) + p.offset;
+            float4 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const float wk = active ? w[k] : 0.0f;
+                v[k] = make_float4(__fmul_rn(wk, g[0]), __fmul_rn(wk, g[1]), __fmul_rn(wk, g[2]), __fmul_rn(wk, g[3]));
+            }
+            if (agg) {
+                for (int d = 1; d < maxlen; d <<= 1) {
+                    const bool take = (lane + d <= hi);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const float o0 = __shfl_down_sync(NRF_FULL_MASK, v[k].x, d);
+                        const float o1 = __shfl_down_sync(NRF_FULL_MASK, v[k].y, d);
+                        const float o2 = __shfl_down_sync(NRF_FULL_MASK, v[k].z, d);
+                        const float o3 = __shfl_down_sync(NRF_FULL_MASK, v[k].w, d);
+                        if (take) { v[k].x += o0; v[k].y += o1; v[k].z += o2; v[k].w += o3; }
+                    }
+                }
+                if (active && lane == lo && (nzmask & cellmask)) {
+#pragma unroll
+                    for (int k = 0; k < 8; k++) atomicAdd(gl + rows[k], v[k]);       // RED.ADD.F32x4
+                }
+            } else if (active && ((nzmask >> lane) & 1u)) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) atomicAdd(gl + rows[k], v[k]);
+            }
+            continue;
         }
 #pragma unroll
         for (int e = 0; e < NE; e++) {
@@ -678,6 +745,51 @@ NRF_EXPORT int nrf_grid_encode_backward_dual(const void* grad0, const void* grad
         k_grid_bwd_d3c2<float, float, 8, 2><<<dim3(nbx, ceil_div_u32(L, 8)), GRID_BLOCK, 0, s>>>(
             (const float*)grad0, (const float*)grad1, inputs, offsets, (float*)grad_embeddings0, (float*)grad_embeddings1, B, L, S, H,
             gridtype, ac, style, true, g_bwd_agg, xform);
+    else return NRF_E_UNSUPPORTED;
+    return nrf_check_launch();
+}
+
+// Interleaved ("paired") forms: both tables in ONE buffer [row][encoder][2] -- `table_pair` in the tables' dtype for the
+// forward, `grad_pair` in f32 for the backward.  Same arithmetic as the dual forms; half the gathers / reductions.
+NRF_EXPORT int nrf_grid_encode_forward_pair(const float* inputs, const void* table_pair, const int32_t* offsets, void* outputs0,
+                                            void* outputs1, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                                            int align_corners, uint32_t style, int dtype, const float* xform, const int32_t* B_dev,
+                                            const float* row_deltas, void* stream) {
+    if (B == 0) return NRF_OK;
+    if (!inputs || !table_pair || !offsets || !outputs0 || !outputs1) return NRF_E_INVALID;
+    if (L == 0 || L > GRID_MAX_LEVELS) return NRF_E_UNSUPPORTED;
+    if (((uintptr_t)table_pair) & 15) return NRF_E_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t nbx = ceil_div_u32(B, GRID_BLOCK);
+    const dim3 grid(nbx, ceil_div_u32(L, 8));
+    const float4* rd = reinterpret_cast<const float4*>(row_deltas);
+    const bool ac = align_corners != 0;
+    if (dtype == NRF_DTYPE_F16)
+        k_grid_fwd_d3c2<__half, 8, 2, true><<<grid, GRID_BLOCK, 0, s>>>(inputs, (const __half*)table_pair, nullptr, offsets, (__half*)outputs0,
+                                                                      (__half*)outputs1, B, L, S, H, gridtype, ac, style, true, xform, B_dev, rd);
+    else if (dtype == NRF_DTYPE_F32)
+        k_grid_fwd_d3c2<float, 8, 2, true><<<grid, GRID_BLOCK, 0, s>>>(inputs, (const float*)table_pair, nullptr, offsets, (float*)outputs0,
+                                                                     (float*)outputs1, B, L, S, H, gridtype, ac, style, true, xform, B_dev, rd);
+    else return NRF_E_UNSUPPORTED;
+    return nrf_check_launch();
+}
+
+NRF_EXPORT int nrf_grid_encode_backward_pair(const void* grad0, const void* grad1, const float* inputs, const int32_t* offsets,
+                                             float* grad_pair, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                                             int align_corners, uint32_t style, int dtype, const float* xform, void* stream) {
+    if (B == 0) return NRF_OK;
+    if (!grad0 || !grad1 || !inputs || !offsets || !grad_pair) return NRF_E_INVALID;
+    if (L == 0 || L > GRID_MAX_LEVELS) return NRF_E_UNSUPPORTED;
+    if (((uintptr_t)grad_pair) & 15) return NRF_E_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool ac = align_corners != 0;
+    const uint32_t nbx = ceil_div_u32(B, GRID_BLOCK);
+    if (dtype == NRF_DTYPE_F16)
+        k_grid_bwd_d3c2<__half, float, 16, 2, true><<<dim3(nbx, ceil_div_u32(L, 16)), GRID_BLOCK, 0, s>>>(
+            (const __half*)grad0, (const __half*)grad1, inputs, offsets, grad_pair, nullptr, B, L, S, H, gridtype, ac, style, true, g_bwd_agg, xform);
+    else if (dtype == NRF_DTYPE_F32)
+        k_grid_bwd_d3c2<float, float, 8, 2, true><<<dim3(nbx, ceil_div_u32(L, 8)), GRID_BLOCK, 0, s>>>(
+            (const float*)grad0, (const float*)grad1, inputs, offsets, grad_pair, nullptr, B, L, S, H, gridtype, ac, style, true, g_bwd_agg, xform);
     else return NRF_E_UNSUPPORTED;
     return nrf_check_launch();
 }

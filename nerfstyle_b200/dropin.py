@@ -4,6 +4,7 @@
     import raymarching                      # -> nerfstyle_b200.raymarching
     from gridencoder import GridEncoder     # -> nerfstyle_b200.gridencoder
     import tinycudann as tcnn               # -> nerfstyle_b200.tcnn
+    from nerf_lib import nerf_lib           # -> nerfstyle_b200.nerf_lib (device-side generate_rays), opt-in
 
 After install() the reference's renderer.py (`import raymarching`, renderer.py:11),
 networks/tcnn_nerf.py (`import tinycudann as tcnn`, `from gridencoder import GridEncoder`, :5,10) and
@@ -13,7 +14,7 @@ import sys
 import types
 
 
-def install(force=False):
+def install(force=False, nerf_lib=False):
     from . import gridencoder as _ge
     from . import raymarching as _rm
     from . import tcnn as _tcnn
@@ -36,4 +37,9 @@ def install(force=False):
     gsub = alias('gridencoder.grid', _ge, ['GridEncoder', 'grid_encode'])
     ge.grid = gsub
     alias('tinycudann', _tcnn, ['Network', 'Encoding'])
+    if nerf_lib:
+        # renderer.py:9 / trainers/base.py:19 / render.py:14 do `from nerf_lib import nerf_lib`; the returned RayBatch has
+        # the reference's fields (origins, dirs).  Opt-in: the reference's own nerf_lib.py also runs on this machine.
+        from . import nerf_lib as _nl
+        alias('nerf_lib', _nl, ['nerf_lib', 'NerfLib'])
     return rm, ge, sys.modules['tinycudann']

@@ -67,6 +67,15 @@ def test_dropin_surface():
                  'composite_rays_train', 'march_rays', 'composite_rays']:
         assert callable(getattr(raymarching, name))
     assert hasattr(tcnn, 'Network') and hasattr(tcnn, 'Encoding')
+    saved = sys.modules.get('nerf_lib')
+    try:
+        dropin.install(force=True, nerf_lib=True)
+        from nerf_lib import nerf_lib               # renderer.py:9
+        assert callable(nerf_lib.generate_rays) and nerf_lib.device is None
+    finally:
+        sys.modules.pop('nerf_lib', None)
+        if saved is not None:
+            sys.modules['nerf_lib'] = saved
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason='reference checkout not mounted (GPU box)')
