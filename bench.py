@@ -73,6 +73,14 @@ class ClockSampler:
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
             self.nv = None
+        if self.nv is not None:
+            # the FIRST query of each NVML counter initialises driver state (tens of ms, under a lock that stalls kernel
+            # launches): pay for it here, outside the timed region, and drop the values
+            try:
+                self._sample()
+            except Exception:
+                pass
+            self.sm, self.reasons, self.power = [], set(), []
 
     def _sample(self):
         if self.nv is not None:
@@ -163,6 +171,9 @@ ALGO_BYTES = {   # SURVEY.md 8d, per point per encoder (fp32 tables / fp16 table
     # one pass over the points for TWO encoders: the xyz read is shared
     'nrf_grid_encode_forward_dual': {False: 12 + 2 * (16 * 8 * 2 * 4 + 16 * 2 * 4), True: 12 + 2 * (16 * 8 * 2 * 2 + 16 * 2 * 2)},
     'nrf_grid_encode_backward_dual': {False: 12 + 2 * (128 + 2 * 1024), True: 12 + 2 * (64 + 2 * 512)},
+    # paired (interleaved-table) forms: same algorithmic bytes as the dual forms, half the gathers / reductions
+    'nrf_grid_encode_forward_pair': {False: 12 + 2 * (16 * 8 * 2 * 4 + 16 * 2 * 4), True: 12 + 2 * (16 * 8 * 2 * 2 + 16 * 2 * 2)},
+    'nrf_grid_encode_backward_pair': {False: 12 + 2 * (128 + 2 * 1024), True: 12 + 2 * (64 + 2 * 512)},
 }
 
 
@@ -195,18 +206,20 @@ def run_ours(args):
         return build_trainer(device, amp, world)
 
     # -------- phase A: device-resident inputs (value) + live per-kernel CUDA-event timing
+    from nerfstyle_b200.trainer import TrainStep
+    TrainStep.reserve_workspace(device)      # set-up, not a step: one arena instead of cudaMallocs at every new high-water mark
     ts = fresh_trainer()
     for s in range(W):
         ts.step(*unpack(devb[s]))
     # live CUDA-event timing inside the timed region: only the roofline candidates (4 calls per step); the full per-op
     # breakdown (`kernels`) is taken in a separate instrumented pass afterwards so that it does not perturb `value`
     all_ops = ['nrf_grid_encode_forward', 'nrf_grid_encode_backward', 'nrf_grid_encode_forward_dual',
-               'nrf_grid_encode_backward_dual', 'nrf_mlp_forward', 'nrf_mlp_backward',
+               'nrf_grid_encode_backward_dual', 'nrf_grid_encode_forward_pair', 'nrf_grid_encode_backward_pair', 'nrf_mlp_forward', 'nrf_mlp_backward',
                'nrf_mlp_forward_ex', 'nrf_mlp_backward_ex',
                'nrf_composite_rays_train_forward', 'nrf_composite_rays_train_backward', 'nrf_march_rays_train_count',
                'nrf_march_rays_train_write']
     timed_ops = ['nrf_grid_encode_forward', 'nrf_grid_encode_backward', 'nrf_grid_encode_forward_dual',
-                 'nrf_grid_encode_backward_dual']
+                 'nrf_grid_encode_backward_dual', 'nrf_grid_encode_forward_pair', 'nrf_grid_encode_backward_pair']
     barrier()
     clocks = ClockSampler(local)
     clocks.start()

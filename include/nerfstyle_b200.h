@@ -286,6 +286,12 @@ int nrf_grads_check(const float* grad, uint64_t n, void* state, void* stream);
 int nrf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, void* param_half,
                   uint64_t n, const void* state, float lr0, float lr_decay_steps, float beta1, float beta2, float eps,
                   float ema_one_minus_decay, void* stream);
+/* nrf_adam_step with strided gradient / fp16-copy rows: `grad` and `param_half` may point into the interleaved
+ * [row][encoder][2] buffers of the paired hash-grid kernels (pre-offset to this tensor's encoder slot); the strides are in
+ * 2-element rows (1 = contiguous, 2 = interleaved pair).  n must be even when a stride is > 1. */
+int nrf_adam_step_ex(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, void* param_half,
+                     uint64_t n, const void* state, float lr0, float lr_decay_steps, float beta1, float beta2, float eps,
+                     float ema_one_minus_decay, uint32_t grad_row_stride, uint32_t half_row_stride, void* stream);
 int nrf_scaler_update(void* state, float growth, float backoff, int growth_interval, void* stream);
 
 /* ------------------------------------------------------------------ ray generation (SURVEY 8f NEXT-1) */

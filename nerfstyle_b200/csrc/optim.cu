@@ -31,7 +31,11 @@ __global__ void k_grads_check(const float* __restrict__ g, uint64_t n, OptState*
 
 __global__ void k_adam_ema(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                            float* __restrict__ ema, __half* __restrict__ p_half, uint64_t n, const OptState* __restrict__ st,
-                           float lr0, float lr_decay_steps, float beta1, float beta2, float eps, float ema_one_minus_decay) {
+                           float lr0, float lr_decay_steps, float beta1, float beta2, float eps, float ema_one_minus_decay,
+                           uint32_t g_stride, uint32_t h_stride) {
+    // g_stride / h_stride: distance, in 2-element rows, between consecutive rows of the gradient / of the fp16 copy
+    // (1 = contiguous; 2 = the interleaved [row][encoder][2] buffers of the paired hash-grid kernels, pointers pre-offset
+    // to this tensor's encoder slot)
     const bool skip = st->found_inf != 0;
     const int t = st->good_steps + 1;
     const float inv_scale = 1.0f / st->scale;
@@ -55,7 +59,7 @@ __global__ void k_adam_ema(float* __restrict__ p, const float* __restrict__ g, f
     const uint64_t n2 = vec ? n / 2 : 0;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * blockDim.x) {
         float2 pp = reinterpret_cast<float2*>(p)[i];
-        const float2 gg = reinterpret_cast<const float2*>(g)[i];
+        const float2 gg = reinterpret_cast<const float2*>(g)[i * g_stride];
         float2 mm = reinterpret_cast<float2*>(m)[i], vv = reinterpret_cast<float2*>(v)[i];
         float2 ee = ema ? reinterpret_cast<float2*>(ema)[i] : make_float2(0.0f, 0.0f);
         pp.x = update(pp.x, gg.x, mm.x, vv.x, ee.x);
@@ -64,16 +68,16 @@ __global__ void k_adam_ema(float* __restrict__ p, const float* __restrict__ g, f
             reinterpret_cast<float2*>(m)[i] = mm;
             reinterpret_cast<float2*>(v)[i] = vv;
             reinterpret_cast<float2*>(p)[i] = pp;
-            if (p_half) reinterpret_cast<__half2*>(p_half)[i] = __floats2half2_rn(pp.x, pp.y);
+            if (p_half) reinterpret_cast<__half2*>(p_half)[i * h_stride] = __floats2half2_rn(pp.x, pp.y);
         }
         if (ema) reinterpret_cast<float2*>(ema)[i] = ee;
     }
     for (uint64_t i = 2 * n2 + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         float mi = m[i], vi = v[i], e = ema ? ema[i] : 0.0f;
-        const float pi = update(p[i], g[i], mi, vi, e);
+        const float pi = update(p[i], g[(i >> 1) * 2 * g_stride + (i & 1)], mi, vi, e);
         if (!skip) {
             m[i] = mi; v[i] = vi; p[i] = pi;
-            if (p_half) p_half[i] = __float2half_rn(pi);
+            if (p_half) p_half[(i >> 1) * 2 * h_stride + (i & 1)] = __float2half_rn(pi);
         }
         if (ema) ema[i] = e;
     }
@@ -102,16 +106,26 @@ NRF_EXPORT int nrf_grads_check(const float* grad, uint64_t n, void* state, void*
     return nrf_check_launch();
 }
 
-NRF_EXPORT int nrf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, void* param_half,
-                             uint64_t n, const void* state, float lr0, float lr_decay_steps, float beta1, float beta2,
-                             float eps, float ema_one_minus_decay, void* stream) {
+NRF_EXPORT int nrf_adam_step_ex(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, void* param_half,
+                                uint64_t n, const void* state, float lr0, float lr_decay_steps, float beta1, float beta2,
+                                float eps, float ema_one_minus_decay, uint32_t grad_row_stride, uint32_t half_row_stride,
+                                void* stream) {
     if (n == 0) return NRF_OK;
     if (!param || !grad || !exp_avg || !exp_avg_sq || !state) return NRF_E_INVALID;
+    if (grad_row_stride == 0 || half_row_stride == 0) return NRF_E_INVALID;
+    if ((grad_row_stride > 1 || half_row_stride > 1) && (n & 1)) return NRF_E_INVALID;      // strided forms address whole rows
     const uint32_t nb = (uint32_t)min((uint64_t)148 * 16, (n + 255) / 256);
     k_adam_ema<<<nb, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, ema, (__half*)param_half, n,
                                                     (const OptState*)state, lr0, lr_decay_steps, beta1, beta2, eps,
-                                                    ema_one_minus_decay);
+                                                    ema_one_minus_decay, grad_row_stride, half_row_stride);
     return nrf_check_launch();
+}
+
+NRF_EXPORT int nrf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, void* param_half,
+                             uint64_t n, const void* state, float lr0, float lr_decay_steps, float beta1, float beta2,
+                             float eps, float ema_one_minus_decay, void* stream) {
+    return nrf_adam_step_ex(param, grad, exp_avg, exp_avg_sq, ema, param_half, n, state, lr0, lr_decay_steps, beta1, beta2, eps,
+                            ema_one_minus_decay, 1, 1, stream);
 }
 
 NRF_EXPORT int nrf_scaler_update(void* state, float growth, float backoff, int growth_interval, void* stream) {

@@ -110,6 +110,30 @@ class _grid_encode_dual(Function):
             raise RuntimeError('grid_encode_dual: D=3, C=2 and equal table shapes are required')
         S = float(np.float32(np.log2(per_level_scale)))
         H = int(base_resolution)
+        offsets = offsets.contiguous()
+        # interleaved fp16 copies kept by the fused optimizer (optim.FusedAdamEMA, pair_tables): one gather serves both tables
+        pair = None
+        if torch.is_autocast_enabled('cuda'):
+            pa, pb = getattr(emb0, '_nrf_half_pair', None), getattr(emb1, '_nrf_half_pair', None)
+            if pa is not None and pb is not None and pa[0] is pb[0] and (pa[1], pb[1]) == (0, 1):
+                pair = pa[0]
+        ctx.sink = None
+        sa, sb = getattr(emb0, '_nrf_grad_sink', None), getattr(emb1, '_nrf_grad_sink', None)
+        if pair is not None and sa is not None and sb is not None and sa[0] is sb[0] and (sa[1], sb[1]) == (0, 1):
+            ctx.sink = sa[0]
+        L.Stats.units = B
+        if pair is not None:
+            out0 = torch.empty(B, Lv * C, device=inputs.device, dtype=pair.dtype)
+            out1 = torch.empty_like(out0)
+            with torch.cuda.device(inputs.device):
+                L.check(L.lib().nrf_grid_encode_forward_pair(L.ptr(inputs), L.ptr(pair), L.ptr(offsets), L.ptr(out0), L.ptr(out1),
+                                                             B, Lv, S, H, int(gridtype), int(bool(align_corners)), int(style),
+                                                             L.dtype_code(pair.dtype), L.ptr(xform), None, None,
+                                                             L.stream_of(inputs)),
+                        'grid_encode_forward_pair')
+            ctx.save_for_backward(inputs, offsets, xform)
+            ctx.meta = (B, Lv, S, H, gridtype, align_corners, style, pair.dtype, emb0.shape)
+            return out0, out1
         embs = []
         for e in (emb0, emb1):
             if torch.is_autocast_enabled('cuda'):
@@ -118,11 +142,9 @@ class _grid_encode_dual(Function):
             embs.append(e.contiguous())
         if embs[0].dtype != embs[1].dtype:
             raise RuntimeError('grid_encode_dual: tables must share a dtype')
-        offsets = offsets.contiguous()
         dt = L.dtype_code(embs[0].dtype)
         out0 = torch.empty(B, Lv * C, device=inputs.device, dtype=embs[0].dtype)
         out1 = torch.empty_like(out0)
-        L.Stats.units = B
         with torch.cuda.device(inputs.device):
             L.check(L.lib().nrf_grid_encode_forward_dual(L.ptr(inputs), L.ptr(embs[0]), L.ptr(embs[1]), L.ptr(offsets),
                                                          L.ptr(out0), L.ptr(out1), B, Lv, S, H, int(gridtype),
@@ -145,9 +167,19 @@ class _grid_encode_dual(Function):
                 g = torch.zeros(B, Lv * 2, dtype=dtype, device=dev)
             g = g.contiguous()
             gs.append(g if g.dtype == dtype else g.to(dtype))
+        L.Stats.units = B
+        if ctx.sink is not None:
+            # the optimizer owns ONE interleaved f32 gradient buffer for both tables and reads it directly: the tables'
+            # .grad stays None (FusedAdamEMA.grad_of); repeated backwards before a step accumulate in the buffer
+            gp = ctx.sink.grad_pair_buffer()
+            with torch.cuda.device(dev):
+                L.check(L.lib().nrf_grid_encode_backward_pair(L.ptr(gs[0]), L.ptr(gs[1]), L.ptr(inputs), L.ptr(offsets), L.ptr(gp),
+                                                              B, Lv, S, H, int(gridtype), int(bool(align_corners)), int(style),
+                                                              L.dtype_code(dtype), L.ptr(xform), L.stream_of(inputs)),
+                        'grid_encode_backward_pair')
+            return None, None, None, None, None, None, None, None, None, None
         ge0 = torch.zeros(shape, dtype=torch.float32, device=dev)
         ge1 = torch.zeros(shape, dtype=torch.float32, device=dev)
-        L.Stats.units = B
         with torch.cuda.device(dev):
             L.check(L.lib().nrf_grid_encode_backward_dual(L.ptr(gs[0]), L.ptr(gs[1]), L.ptr(inputs), L.ptr(offsets), L.ptr(ge0),
                                                           L.ptr(ge1), B, Lv, S, H, int(gridtype), int(bool(align_corners)),

@@ -333,8 +333,8 @@ class Renderer(nn.Module):
               'sigmas': torch.zeros(cap, 1, dtype=f32, device=dev), 'rgbs': torch.zeros(cap, Cch, dtype=f32, device=dev),
               'weights_sum': torch.empty(N, dtype=f32, device=dev), 'depth': torch.empty(N, dtype=f32, device=dev),
               'image': torch.empty(N, Cch, dtype=f32, device=dev),
-              'tab': [torch.empty_like(self.model.x_density_embedder.embeddings, dtype=torch.float16),
-                      torch.empty_like(self.model.x_color_embedder.embeddings, dtype=torch.float16)],
+              # both fp16 tables of this frame, interleaved [row][table][2]: one 8-byte gather per corner serves both
+              'pair': torch.empty(self.model.x_density_embedder.embeddings.shape[0], 2, 2, dtype=torch.float16, device=dev),
               'w': {n: torch.empty(getattr(self.model, n).params.numel(), dtype=torch.float16, device=dev)
                     for n in ('density_net', 'class_net', 'color1_net', 'color2_net')},
               'scratch': torch.empty(int(raymarching.L.lib().nrf_march_scratch_bytes(N)) + 64, dtype=torch.uint8, device=dev)}
@@ -354,12 +354,11 @@ class Renderer(nn.Module):
                                        st['rays_d'].data_ptr(), float(self.bound), 0.0, int(self.max_steps), int(self.cascade),
                                        int(self.grid_size), self.density_bitfield.data_ptr(), st['fars'].data_ptr(),
                                        st['xyzs'].data_ptr(), st['dirs'].data_ptr(), st['deltas'].data_ptr(), s), 'march_rays_dev')
-        L.check(lib.nrf_grid_encode_forward_dual_dev(st['xyzs'].data_ptr(), st['tab'][0].data_ptr(), st['tab'][1].data_ptr(),
-                                                     enc.offsets.data_ptr(), st['enc_d'].data_ptr(), st['enc_c'].data_ptr(), cap,
-                                                     enc.num_levels, S, int(enc.base_resolution), enc.gridtype_id,
-                                                     int(enc.align_corners), 0, L.DTYPE_F16, m._xform.data_ptr(), rows,
-                                                     st['deltas'].data_ptr(), s),
-                'grid_encode_forward_dual_dev')
+        L.check(lib.nrf_grid_encode_forward_pair(st['xyzs'].data_ptr(), st['pair'].data_ptr(), enc.offsets.data_ptr(),
+                                                 st['enc_d'].data_ptr(), st['enc_c'].data_ptr(), cap, enc.num_levels, S,
+                                                 int(enc.base_resolution), enc.gridtype_id, int(enc.align_corners), 0,
+                                                 L.DTYPE_F16, m._xform.data_ptr(), rows, st['deltas'].data_ptr(), s),
+                'grid_encode_forward_pair')
 
         def mlp(net, x, y, col, n_out, act):
             L.check(lib.nrf_mlp_forward_dev(x.data_ptr(), L.dtype_code(x.dtype), st['w'][net].data_ptr(), cap,
@@ -406,7 +405,7 @@ class Renderer(nn.Module):
         st['alive'][0].copy_(torch.arange(N, dtype=torch.int32, device=self.device))
         st['ctl'].copy_(torch.tensor([N, 1, N, 0, N, self.max_steps, 0, 0], dtype=torch.int32))
         for i, e in enumerate((m.x_density_embedder, m.x_color_embedder)):       # fp16 tables / weights for this frame
-            st['tab'][i].copy_(getattr(e.embeddings, '_nrf_half_copy', e.embeddings.detach()))
+            st['pair'][:, i].copy_(getattr(e.embeddings, '_nrf_half_copy', e.embeddings.detach()))
         for n in st['w']:
             st['w'][n].copy_(getattr(m, n).params.detach())
         if st['graph'] is None:

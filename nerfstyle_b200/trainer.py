@@ -12,7 +12,7 @@ import torch.nn.functional as F
 
 class TrainStep:
     def __init__(self, renderer, lr=0.01, mlp_lr=None, lr_decay=30000, ema_decay=0.95, class_lambda=0.001, enable_amp=True,
-                 fused_adam=True, world_size=1, fused_optimizer=True, rank=None, shard_optimizer=True):
+                 fused_adam=True, world_size=1, fused_optimizer=True, rank=None, shard_optimizer=True, pair_tables=True):
         self.renderer = renderer
         self.model = renderer.model
         params = list(self.model.parameters())
@@ -32,7 +32,8 @@ class TrainStep:
                 rank = dist.get_rank() if (world_size > 1 and dist.is_initialized()) else 0
             # with world_size > 1 the optimizer owns the gradient exchange (reduce-scatter / sharded Adam / all-gather)
             self.fused = FusedAdamEMA(params, lr=lr, eps=1e-15, lr_decay_steps=lr_decay, ema_decay=ema_decay,
-                                      enable_amp=enable_amp, world_size=world_size, rank=rank, shard_big=shard_optimizer)
+                                      enable_amp=enable_amp, world_size=world_size, rank=rank, shard_big=shard_optimizer,
+                                      pair_tables=pair_tables)
             self.ema = self.fused.ema
             return
         self.optim = torch.optim.Adam([{'params': params}], lr=lr, betas=(0.9, 0.999), eps=1e-15, fused=fused_adam)
@@ -45,6 +46,14 @@ class TrainStep:
         self.ema = [p.detach().clone() for p in params] if ema_decay > 0 else None
         self.world_size = world_size
         self.iter_ctr = 0
+
+    @staticmethod
+    def reserve_workspace(device, nbytes=12 << 30):
+        """One arena for the step's sample buffers: allocate-and-release `nbytes` once so that the caching allocator holds
+        a single large block it can split for every later request.  The number of samples per step drifts as the field
+        trains, and without the arena each new high-water mark costs a cudaMalloc (a device-wide synchronisation) in the
+        middle of training; a 180 GB part has the room."""
+        torch.empty(int(nbytes), dtype=torch.uint8, device=device)
 
     def loss_fn(self, image, classes, target_rgb, target_cls):
         mse = torch.mean((image - target_rgb) ** 2)

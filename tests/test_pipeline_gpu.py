@@ -228,3 +228,70 @@ def test_render_test_graph_equals_reference_loop(cuda_lib, dev):
         for x, y in zip(a2, b2):
             torch.testing.assert_close(x, y, rtol=1e-5, atol=1e-6)
     assert int(r._gs['ctl'][0]) == 0 and int(r._gs['ctl'][6]) > 0
+
+
+def test_paired_tables_match_unpaired(cuda_lib, dev):
+    """FusedAdamEMA(pair_tables=True): the two hash tables share one interleaved fp16 copy and one interleaved f32 gradient
+    buffer (nrf_grid_encode_forward_pair / _backward_pair, strided nrf_adam_step_ex).  Forward values are identical to
+    the unpaired path, gradients equal up to the order of the float atomics, and the optimizer step lands on the same
+    parameters / EMA / fp16 copies."""
+    from nerfstyle_b200 import model as M, scenes
+    from nerfstyle_b200.trainer import TrainStep
+    intr = dict(scenes.ROOM)
+    pose = scenes.synthetic_poses(2, 0)[0]
+    runs = []
+    for pair in (True, False):
+        torch.manual_seed(0)
+        m = M.StyleTCNerf([-2., -2., -2.], [2., 2., 2.], class_dim=8).to(dev)
+        with torch.no_grad():                          # tables large enough for non-trivial outputs
+            for e in (m.x_density_embedder, m.x_color_embedder):
+                e.embeddings.uniform_(-0.5, 0.5, generator=torch.Generator(device=dev).manual_seed(5))
+        r = M.Renderer(m, 2.0, raymarch_channels=11).to(dev)
+        ts = TrainStep(r, enable_amp=True, pair_tables=pair)
+        f = ts.fused
+        assert (f.pair_idx is not None) == pair
+        if pair:
+            assert m.x_density_embedder.embeddings._nrf_half_pair[0] is m.x_color_embedder.embeddings._nrf_half_pair[0]
+            torch.testing.assert_close(m.x_color_embedder.embeddings._nrf_half_copy.float(),
+                                       m.x_color_embedder.embeddings.detach().half().float(), rtol=0, atol=0)
+        gen = torch.Generator().manual_seed(0)
+        idx = scenes.frame_indices(intr, 2048, gen).to(dev)
+        o, d = scenes.generate_rays(pose, intr, dev, idx)
+        tgt, seg = scenes.synthetic_target(idx, intr)
+        # one manual forward / backward through the same path TrainStep.step takes
+        with torch.autocast('cuda', dtype=torch.float16):
+            image, depth, classes = r.render_train(o, d)
+            loss, _ = ts.loss_fn(image, classes, tgt, seg)
+        f.zero_grad()
+        f.scale_loss(loss).backward()
+        grads = {n: f.grad_of(p).detach().clone() for n, p in m.named_parameters()}
+        if pair:
+            assert m.x_density_embedder.embeddings.grad is None and f.grad_pair_valid
+        before = {n: p.detach().clone() for n, p in m.named_parameters()}
+        f.step()
+        runs.append(dict(image=image.detach().clone(), loss=float(loss), grads=grads, before=before,
+                         after={n: p.detach().clone() for n, p in m.named_parameters()},
+                         half={n: p._nrf_half_copy.float().clone() for n, p in m.named_parameters()},
+                         ema=[e.clone() for e in f.ema]))
+        # two more ordinary steps must stay finite and keep the fp16 copies current
+        for it in range(2):
+            idx = scenes.frame_indices(intr, 2048, gen).to(dev)
+            o, d = scenes.generate_rays(pose, intr, dev, idx)
+            tgt, seg = scenes.synthetic_target(idx, intr)
+            assert np.isfinite(float(ts.step(o, d, tgt, seg)))
+        for n, p in m.named_parameters():
+            torch.testing.assert_close(p._nrf_half_copy.float(), p.detach().half().float(), rtol=0, atol=0)
+        assert int(f.good_steps.item()) == 3
+    a, b = runs
+    assert torch.equal(a['image'], b['image']) and a['loss'] == b['loss']          # same gathers, same arithmetic
+    for n in a['grads']:
+        ga, gb = a['grads'][n], b['grads'][n]
+        assert float((ga - gb).abs().max()) <= 1e-5 * float(gb.abs().max()) + 1e-30, n
+    # the step itself: where the two runs' gradients agree in sign and are not rounding noise, Adam's first step is
+    # -lr * sign(g) in both; compare on the rows that received a meaningful gradient
+    for n in a['after']:
+        g = b['grads'][n]
+        mask = g.abs() > 1e-3 * g.abs().max()
+        da, db = (a['after'][n] - a['before'][n])[mask], (b['after'][n] - b['before'][n])[mask]
+        torch.testing.assert_close(da, db, rtol=1e-3, atol=1e-6)
+        assert mask.sum() > 0

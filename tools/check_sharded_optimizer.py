@@ -25,15 +25,17 @@ def main():
     dist.init_process_group('nccl', device_id=dev)
     ok = True
     # ---- 1. optimizer equivalence on synthetic gradients
-    shapes = [(1 << 21, 2), (3072,), ((1 << 20) + 8 * world, 2)]
+    # tensors 0 and 3 share a shape: the sharded optimizer pairs them (interleaved fp16 copies + interleaved gradient buffer)
+    shapes = [(1 << 21, 2), (3072,), ((1 << 20) + 8 * world, 2), (1 << 21, 2)]
     torch.manual_seed(0)
     init = [torch.randn(s, device=dev) * 0.1 for s in shapes]
     opts = []
     for shard in (True, False):
         ps = [torch.nn.Parameter(t.clone()) for t in init]
         opts.append((ps, FusedAdamEMA(ps, lr=0.01, lr_decay_steps=50, ema_decay=0.95, init_scale=1024.0, growth_interval=3,
-                                      world_size=world, rank=rank, shard_big=shard)))
+                                      world_size=world, rank=rank, shard_big=shard, pair_tables=shard)))
     assert any(sh is not None for sh in opts[0][1].shard) and all(sh is None for sh in opts[1][1].shard)
+    assert opts[0][1].pair_idx == (0, 3) and opts[1][1].pair_idx is None
     gen = torch.Generator(device=dev).manual_seed(100 + rank)                    # every rank has its own gradients
     for it in range(7):
         grads = [torch.randn(s, device=dev, generator=gen) for s in shapes]
@@ -41,8 +43,13 @@ def main():
             grads[0][12345, 1] = float('inf')                                    # one rank, inside ANOTHER rank's shard
         for ps, opt in opts:
             scale = float(opt.scale.item())
-            for p, g in zip(ps, grads):
-                p.grad = g * scale
+            opt.zero_grad()
+            for i, (p, g) in enumerate(zip(ps, grads)):
+                if opt.pair_idx is not None and i in opt.pair_idx and it % 2 == 0:
+                    # what the paired scatter kernel does: accumulate into the optimizer's interleaved buffer, .grad stays None
+                    opt.grad_pair_buffer()[:, opt.pair_idx.index(i)] += g * scale
+                else:
+                    p.grad = g * scale
             opt.step()
     opts[0][1].gather_master()
     for i, (a, b) in enumerate(zip(opts[0][0], opts[1][0])):
@@ -52,6 +59,7 @@ def main():
         ha, hb = getattr(a, '_nrf_half_copy', None), getattr(b, '_nrf_half_copy', None)
         if ha is not None and hb is not None:
             ok &= float((ha.float() - hb.float()).abs().max()) <= (0.0 if world == 2 else 1e-3)
+            ha = ha.contiguous()
             ref = ha.clone()
             dist.broadcast(ref, src=0)
             ok &= bool(torch.equal(ref, ha))                                      # identical gathered tables on every rank
@@ -62,17 +70,18 @@ def main():
     # ---- 2. end to end: same losses
     host, devb = B.make_batches(6, 2048, rank, world, dev)
     losses = []
-    for shard in (True, False):
+    for shard, pair in ((True, True), (False, True), (False, False)):
         torch.manual_seed(0)
         torch.cuda.manual_seed_all(0)
         m = M.StyleTCNerf([-2., -2., -2.], [2., 2., 2.], class_dim=B.N_CLASSES).to(dev)
         r = M.Renderer(m, 2.0, raymarch_channels=3 + B.N_CLASSES).to(dev)
-        ts = TrainStep(r, enable_amp=True, world_size=world, shard_optimizer=shard)
+        ts = TrainStep(r, enable_amp=True, world_size=world, shard_optimizer=shard, pair_tables=pair)
         losses.append([float(ts.step(*B.unpack(devb[s]))) for s in range(6)])
-    ok &= all(abs(a - b) <= 2e-3 * abs(b) for a, b in zip(*losses))
+    ok &= all(abs(a - b) <= 2e-3 * abs(b) and abs(c - b) <= 2e-3 * abs(b) for a, b, c in zip(*losses))
     if rank == 0:
-        print('losses sharded   :', ['%.5f' % v for v in losses[0]])
-        print('losses replicated:', ['%.5f' % v for v in losses[1]])
+        print('losses sharded + paired   :', ['%.5f' % v for v in losses[0]])
+        print('losses replicated + paired:', ['%.5f' % v for v in losses[1]])
+        print('losses replicated, unpaired:', ['%.5f' % v for v in losses[2]])
     t = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
