@@ -292,6 +292,13 @@ int nrf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
 int nrf_adam_step_ex(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, void* param_half,
                      uint64_t n, const void* state, float lr0, float lr_decay_steps, float beta1, float beta2, float eps,
                      float ema_one_minus_decay, uint32_t grad_row_stride, uint32_t half_row_stride, void* stream);
+/* Both tables of an interleaved pair in one pass: grad_pair f32 [rows][2 tables][2] (16-byte aligned), half_pair f16 of the
+ * same layout (8-byte aligned, may be NULL); param / exp_avg / exp_avg_sq / ema are the two tables' own contiguous
+ * [rows, 2] f32 arrays (or this rank's shard of them: all pointers offset to the same first row). */
+int nrf_adam_step_pair(float* param0, float* param1, const float* grad_pair, float* exp_avg0, float* exp_avg1,
+                       float* exp_avg_sq0, float* exp_avg_sq1, float* ema0, float* ema1, void* half_pair, uint64_t rows,
+                       const void* state, float lr0, float lr_decay_steps, float beta1, float beta2, float eps,
+                       float ema_one_minus_decay, void* stream);
 int nrf_scaler_update(void* state, float growth, float backoff, int growth_interval, void* stream);
 
 /* ------------------------------------------------------------------ ray generation (SURVEY 8f NEXT-1) */

@@ -194,23 +194,29 @@ class FusedAdamEMA:
                 # an inf seen in ANY rank's shard skips the step everywhere (the replicated GradScaler decision)
                 parallel.allreduce_max_int(self.state[4:8].view(torch.int32), self.world_size)
             gathered_pair = False
+            if pair_grads:
+                # both tables in one pass over the interleaved gradient rows (16-byte loads) and fp16 rows (8-byte stores)
+                ia, ib = self.pair_idx
+                sh = self.shard[ia]
+                lo, n = (0, self.params[ia].numel()) if sh is None else (sh[0], sh[1] - sh[0])
+                L.check(lib.nrf_adam_step_pair(
+                    self.params[ia].data_ptr() + 4 * lo, self.params[ib].data_ptr() + 4 * lo, pair_src.data_ptr(),
+                    self.exp_avg[ia].data_ptr(), self.exp_avg[ib].data_ptr(), self.exp_avg_sq[ia].data_ptr(),
+                    self.exp_avg_sq[ib].data_ptr(), L.ptr(self.ema[ia]) if self.ema is not None else None,
+                    L.ptr(self.ema[ib]) if self.ema is not None else None, self.half_pair.data_ptr() + (lo // 2) * 8, n // 2,
+                    self.state.data_ptr(), self.lr, self.lr_decay_steps, self.betas[0], self.betas[1], self.eps, omd, st),
+                    'adam_step_pair')
             for i, p in enumerate(self.params):
                 paired = self.pair_idx is not None and i in self.pair_idx
-                if grads[i] is None and not (paired and pair_grads):
+                if grads[i] is None or (paired and pair_grads):
                     continue
                 sh = self.shard[i]
                 lo, n = (0, p.numel()) if sh is None else (sh[0], sh[1] - sh[0])
                 p_ptr = p.data_ptr() + 4 * lo
-                g_stride = h_stride = 1
-                if paired:
-                    e = self.pair_idx.index(i)
-                    h_ptr, h_stride = self.half_pair.data_ptr() + (lo // 2) * 8 + e * 4, 2
-                    if pair_grads:
-                        g_ptr, g_stride = pair_src.data_ptr() + e * 8, 2      # pair_src starts at this rank's first row
-                    else:
-                        g_ptr = grads[i].data_ptr()
+                g_ptr, g_stride, h_stride = grads[i].data_ptr(), 1, 1
+                if paired:         # a paired table whose gradient arrived as an ordinary .grad: only the fp16 copy is strided
+                    h_ptr, h_stride = self.half_pair.data_ptr() + (lo // 2) * 8 + self.pair_idx.index(i) * 4, 2
                 else:
-                    g_ptr = grads[i].data_ptr()
                     h_ptr = (self.half[i].data_ptr() + 2 * lo) if self.half[i] is not None else None
                 L.check(lib.nrf_adam_step_ex(p_ptr, g_ptr, self.exp_avg[i].data_ptr(), self.exp_avg_sq[i].data_ptr(),
                                              L.ptr(self.ema[i]) if self.ema is not None else None, h_ptr, n,
