@@ -321,7 +321,10 @@ def run_ours(args):
                     'frac': round(ach / hbm_peak, 4), 'traffic': (traffic.get(top) or {}).get('dram_bytes_per_launch'),
                     'traffic_source': (traffic.get(top) or {}).get('source'), 'peak_source': peak_src,
                     'algorithmic_bytes_per_point': ALGO_BYTES[top][amp], 'points_per_launch': v['units'] / v['calls'],
-                    'us_per_launch': round(sec_per_launch * 1e6, 1)}
+                    'us_per_launch': round(sec_per_launch * 1e6, 1),
+                    'note': 'algorithmic bytes count every table row touched; both tables (and most of their f32 gradients) stay '
+                            'L2-resident, so real DRAM traffic (`traffic`) is far lower and frac can exceed 1 -- ncu shows the '
+                            'scatter bound by the LSU data pipe (warp shuffles + reductions), profiles/r01f_ncu_kernels.md'}
     line = {
         'metric': 'train_rays_per_s', 'value': round(value, 1), 'unit': 'rays/s', 'n_gpus': world, 'steps': K, 'warmup': W,
         'ms_per_step': round(ms_total / K, 4), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,

@@ -81,6 +81,7 @@ SIGNATURES = {
 # tuning / extension entry points that are not part of the reference-replacing ABI
 EXTRA_SIGNATURES = {
     'nrf_grid_set_tuning': (None, [_i32, _i32, _i32]),
+    'nrf_grid_set_transpose_min': (None, [_i32]),
     'nrf_march_set_mode': (None, [_i32]),
     'nrf_mlp_set_mode': (None, [_i32]),
     'nrf_nnfm_set_mode': (None, [_i32]),

@@ -10,6 +10,8 @@
 
 #define GRID_MAX_LEVELS 32
 #define GRID_BLOCK 256
+#define TR_STRIDE 36      // floats per lane of the backward's transpose buffer: 32 products + 4 pad (conflict-free 16-byte stores)
+#define TR_BYTES (GRID_BLOCK / 32 * 32 * TR_STRIDE * 4)
 
 __host__ __device__ __forceinline__ uint32_t prime_of(int i) {
     // gridencoder.cu:42
@@ -335,6 +337,9 @@ k_grid_fwd_generic(const float* __restrict__ inputs, const T* __restrict__ table
 static int g_fwd_lpt = 16;   // levels per thread of the fast path (tunable: nrf_grid_set_tuning)
 static int g_bwd_lpt = 16;
 static int g_bwd_agg = 1;    // warp aggregation of the scatter on (1) / off (0)
+static int g_bwd_tr_min = 9; // paired scatter: runs of at least this many lanes are reduced through the shared-memory transpose
+
+NRF_EXPORT void nrf_grid_set_transpose_min(int min_run) { if (min_run > 0) g_bwd_tr_min = min_run; }
 
 NRF_EXPORT void nrf_grid_set_tuning(int fwd_lpt, int bwd_lpt, int bwd_agg) {
     if (fwd_lpt > 0) g_fwd_lpt = fwd_lpt;
@@ -408,8 +413,9 @@ __global__ void __launch_bounds__(GRID_BLOCK, NE == 1 ? 1 : (PAIR ? 3 : 4))
 k_grid_bwd_d3c2(const T* __restrict__ grad0, const T* __restrict__ grad1, const float* __restrict__ inputs,
                 const int32_t* __restrict__ offsets, TO* __restrict__ grad_table0, TO* __restrict__ grad_table1, uint32_t B, uint32_t L,
                 float S, uint32_t H, uint32_t gridtype, bool align_corners, uint32_t style, bool point_major, int agg_max_groups,
-                const float* __restrict__ xform) {
+                const float* __restrict__ xform, int tr_min) {
     typedef typename Vec2<T>::type V2;
+    extern __shared__ __align__(16) float tbuf_all[];  // PAIR: per-warp transpose buffers (TR_STRIDE floats per lane)
     constexpr int WPL = (int)sizeof(V2) / 4;           // 32-bit words per level of one point's gradient
     constexpr int ROW = LPT * WPL + 1;                 // padded smem row (conflict-free column reads)
     __shared__ LevelP lp[LPT];
@@ -514,7 +520,44 @@ k_grid_bwd_d3c2(const T* __restrict__ grad0, const T* __restrict__ grad1, const 
                 const float wk = active ? w[k] : 0.0f;
                 v[k] = make_float4(__fmul_rn(wk, g[0]), __fmul_rn(wk, g[1]), __fmul_rn(wk, g[2]), __fmul_rn(wk, g[3]));
             }
-            if (agg) {
+            if (agg && maxlen >= tr_min) {
+                // Long runs (coarse levels): the shuffle butterfly costs 32 shuffles per step -- 160 for a 32-lane run -- and
+                // ncu shows the LSU data pipe (shuffles + reductions) is what bounds this kernel.  Transpose through shared
+                // memory instead: every lane stores its 32 products (8 conflict-free 16-byte stores), then the products are
+                // summed down the lanes of each run from shared memory and each run issues its 8 corner reductions once.
+                float* tb = tbuf_all + (threadIdx.x >> 5) * (32 * TR_STRIDE);
+#pragma unroll
+                for (int k = 0; k < 8; k++) *reinterpret_cast<float4*>(tb + lane * TR_STRIDE + 4 * k) = v[k];
+                __syncwarp();
+                const uint32_t endmask = __ballot_sync(NRF_FULL_MASK, lane == hi);
+                const uint32_t flushmask = __ballot_sync(NRF_FULL_MASK, lane == hi && active && (nzmask & cellmask) != 0u);
+                // lane t owns product t (corner t / 4, component t % 4): all 32 loads are issued back to back (conflict-free),
+                // then summed run by run; a run's flush is ONE 4-byte reduction whose 32 lanes cover 8 rows x 16 bytes.
+                // (Measured and rejected: 8 lanes with 16-byte loads + reductions, 25 % slower; regrouping the sums into 8 lanes
+                //  for 16-byte reductions, 9 % slower; fetching the run's rows with one shuffle instead of eight, 5 % slower.)
+                float q[32];
+#pragma unroll
+                for (int r = 0; r < 32; r++) q[r] = tb[r * TR_STRIDE + lane];
+                float* glf = reinterpret_cast<float*>(gl);
+                float acc = 0.0f;
+#pragma unroll
+                for (int r = 0; r < 32; r++) {
+                    acc += q[r];
+                    if ((endmask >> r) & 1u) {                       // warp-uniform
+                        if ((flushmask >> r) & 1u) {
+                            uint32_t rr = 0;
+#pragma unroll
+                            for (int k = 0; k < 8; k++) {
+                                const uint32_t t = __shfl_sync(NRF_FULL_MASK, rows[k], r);
+                                if ((lane >> 2) == k) rr = t;
+                            }
+                            atomicAdd(glf + (size_t)rr * 4 + (lane & 3), acc);
+                        }
+                        acc = 0.0f;
+                    }
+                }
+                __syncwarp();
+            } else if (agg) {
                 for (int d = 1; d < maxlen; d <<= 1) {
                     const bool take = (lane + d <= hi);
 #pragma unroll
@@ -643,7 +686,7 @@ static int launch_bwd(const void* grad, const float* inputs, const int32_t* offs
     const uint32_t nbx = ceil_div_u32(B, GRID_BLOCK);
     if (D == 3 && C == 2 && (((uintptr_t)grad_embeddings) & 7) == 0) {
         const int lpt = g_bwd_lpt;
-#define BWD_FAST(LPT) k_grid_bwd_d3c2<T, TO, LPT, 1><<<dim3(nbx, ceil_div_u32(L, LPT)), GRID_BLOCK, 0, s>>>(g, nullptr, inputs, offsets, ge, nullptr, B, L, S, H, gridtype, ac, style, pm, g_bwd_agg, nullptr)
+#define BWD_FAST(LPT) k_grid_bwd_d3c2<T, TO, LPT, 1><<<dim3(nbx, ceil_div_u32(L, LPT)), GRID_BLOCK, 0, s>>>(g, nullptr, inputs, offsets, ge, nullptr, B, L, S, H, gridtype, ac, style, pm, g_bwd_agg, nullptr, 1 << 30)
         if (lpt >= 16) BWD_FAST(16); else if (lpt >= 8) BWD_FAST(8); else if (lpt >= 4) BWD_FAST(4); else if (lpt >= 2) BWD_FAST(2); else BWD_FAST(1);
 #undef BWD_FAST
     } else {
@@ -736,15 +779,15 @@ NRF_EXPORT int nrf_grid_encode_backward_dual(const void* grad0, const void* grad
     if (dtype == NRF_DTYPE_F16 && grad_table_dtype == NRF_DTYPE_F32)
         k_grid_bwd_d3c2<__half, float, 16, 2><<<dim3(nbx, ceil_div_u32(L, 16)), GRID_BLOCK, 0, s>>>(
             (const __half*)grad0, (const __half*)grad1, inputs, offsets, (float*)grad_embeddings0, (float*)grad_embeddings1, B, L, S, H,
-            gridtype, ac, style, true, g_bwd_agg, xform);
+            gridtype, ac, style, true, g_bwd_agg, xform, 1 << 30);
     else if (dtype == NRF_DTYPE_F16 && grad_table_dtype == NRF_DTYPE_F16)
         k_grid_bwd_d3c2<__half, __half, 16, 2><<<dim3(nbx, ceil_div_u32(L, 16)), GRID_BLOCK, 0, s>>>(
             (const __half*)grad0, (const __half*)grad1, inputs, offsets, (__half*)grad_embeddings0, (__half*)grad_embeddings1, B, L, S, H,
-            gridtype, ac, style, true, g_bwd_agg, xform);
+            gridtype, ac, style, true, g_bwd_agg, xform, 1 << 30);
     else if (dtype == NRF_DTYPE_F32 && grad_table_dtype == NRF_DTYPE_F32)      // 8 levels per block: the staged f32 gradients of two encoders fit 48 KB
         k_grid_bwd_d3c2<float, float, 8, 2><<<dim3(nbx, ceil_div_u32(L, 8)), GRID_BLOCK, 0, s>>>(
             (const float*)grad0, (const float*)grad1, inputs, offsets, (float*)grad_embeddings0, (float*)grad_embeddings1, B, L, S, H,
-            gridtype, ac, style, true, g_bwd_agg, xform);
+            gridtype, ac, style, true, g_bwd_agg, xform, 1 << 30);
     else return NRF_E_UNSUPPORTED;
     return nrf_check_launch();
 }
@@ -784,12 +827,19 @@ NRF_EXPORT int nrf_grid_encode_backward_pair(const void* grad0, const void* grad
     cudaStream_t s = (cudaStream_t)stream;
     const bool ac = align_corners != 0;
     const uint32_t nbx = ceil_div_u32(B, GRID_BLOCK);
+    static bool attr_set = false;
+    if (!attr_set) {          // static staging (34 KB) + dynamic transpose buffers (36 KB) exceed the 48 KB default
+        cudaFuncSetAttribute(k_grid_bwd_d3c2<__half, float, 16, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_BYTES);
+        cudaFuncSetAttribute(k_grid_bwd_d3c2<float, float, 8, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_BYTES);
+        attr_set = true;
+    }
+    const int tr_min = g_bwd_agg > 0 ? g_bwd_tr_min : (1 << 30);
     if (dtype == NRF_DTYPE_F16)
-        k_grid_bwd_d3c2<__half, float, 16, 2, true><<<dim3(nbx, ceil_div_u32(L, 16)), GRID_BLOCK, 0, s>>>(
-            (const __half*)grad0, (const __half*)grad1, inputs, offsets, grad_pair, nullptr, B, L, S, H, gridtype, ac, style, true, g_bwd_agg, xform);
+        k_grid_bwd_d3c2<__half, float, 16, 2, true><<<dim3(nbx, ceil_div_u32(L, 16)), GRID_BLOCK, TR_BYTES, s>>>(
+            (const __half*)grad0, (const __half*)grad1, inputs, offsets, grad_pair, nullptr, B, L, S, H, gridtype, ac, style, true, g_bwd_agg, xform, tr_min);
     else if (dtype == NRF_DTYPE_F32)
-        k_grid_bwd_d3c2<float, float, 8, 2, true><<<dim3(nbx, ceil_div_u32(L, 8)), GRID_BLOCK, 0, s>>>(
-            (const float*)grad0, (const float*)grad1, inputs, offsets, grad_pair, nullptr, B, L, S, H, gridtype, ac, style, true, g_bwd_agg, xform);
+        k_grid_bwd_d3c2<float, float, 8, 2, true><<<dim3(nbx, ceil_div_u32(L, 8)), GRID_BLOCK, TR_BYTES, s>>>(
+            (const float*)grad0, (const float*)grad1, inputs, offsets, grad_pair, nullptr, B, L, S, H, gridtype, ac, style, true, g_bwd_agg, xform, tr_min);
     else return NRF_E_UNSUPPORTED;
     return nrf_check_launch();
 }

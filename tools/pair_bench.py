@@ -53,3 +53,16 @@ for half in (True, False):
     assert e0 < 1e-5 and e1 < 1e-5
     td, tp = mb.timeit(b_dual), mb.timeit(b_pair)
     print('bwd half=%d  dual %.3f ms   pair %.3f ms' % (half, td, tp))
+    # long runs through the shared-memory transpose instead of the shuffle butterfly: threshold sweep + value check
+    ge0.zero_(); ge1.zero_()
+    assert b_dual() == 0
+    for tr in (1 << 30, 17, 9, 5, 3, 2):
+        lib.nrf_grid_set_transpose_min(tr)
+        gp.zero_()
+        assert b_pair() == 0
+        torch.cuda.synchronize()
+        e0 = float((gp[:, 0] - ge0).abs().max() / ge0.abs().max())
+        e1 = float((gp[:, 1] - ge1).abs().max() / ge1.abs().max())
+        assert e0 < 1e-5 and e1 < 1e-5, (tr, e0, e1)
+        print('bwd half=%d  pair, transpose for runs >= %-10d: %.3f ms   (rel err vs dual %.1e / %.1e)' % (half, tr, mb.timeit(b_pair), e0, e1))
+    lib.nrf_grid_set_transpose_min(9)
