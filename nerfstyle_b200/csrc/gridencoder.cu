@@ -495,6 +495,7 @@ k_grid_bwd_d3c2(const T* __restrict__ grad0, const T* __restrict__ grad1, const 
             const uint32_t span = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
             agg = __all_sync(NRF_FULL_MASK, cellmask == span);
             if (agg) maxlen = (int)__reduce_max_sync(NRF_FULL_MASK, (unsigned)(hi - lo + 1));
+            if (maxlen < agg_max_groups) agg = false;     // runs shorter than this are cheaper as plain per-lane reductions
         }
         if constexpr (PAIR) {
             float g[4] = {0.0f, 0.0f, 0.0f, 0.0f};

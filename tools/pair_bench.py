@@ -66,3 +66,7 @@ for half in (True, False):
         assert e0 < 1e-5 and e1 < 1e-5, (tr, e0, e1)
         print('bwd half=%d  pair, transpose for runs >= %-10d: %.3f ms   (rel err vs dual %.1e / %.1e)' % (half, tr, mb.timeit(b_pair), e0, e1))
     lib.nrf_grid_set_transpose_min(9)
+    for amin in (1, 2, 3, 4, 5):
+        lib.nrf_grid_set_tuning(0, 0, amin)
+        print('bwd half=%d  pair, aggregate only when the longest run >= %d: %.3f ms' % (half, amin, mb.timeit(b_pair)))
+    lib.nrf_grid_set_tuning(0, 0, 1)
