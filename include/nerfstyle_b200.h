@@ -23,6 +23,7 @@
  *   tinycudann Network fwd/bwd (networks/style_nerf.py:44-98)   nrf_mlp_forward / nrf_mlp_backward
  *   loss.py:32-36,199-214 cosine_dists + mask + amin       nrf_nnfm_forward (backward = gather, nnfm.py)
  *   nerf_lib.py:69-142 NerfLib.generate_rays (+ RayBatch)  nrf_generate_rays
+ *   renderer.py:139-194 Renderer.update_state              nrf_occ_* + nrf_packbits_dev (around the density query)
  *
  * Conventions: all pointers are DEVICE pointers owned by the caller; the callee never
  * allocates, never synchronises and never throws.  Every function launches on `stream` (a
@@ -300,6 +301,34 @@ int nrf_adam_step_pair(float* param0, float* param1, const float* grad_pair, flo
                        const void* state, float lr0, float lr_decay_steps, float beta1, float beta2, float eps,
                        float ema_one_minus_decay, void* stream);
 int nrf_scaler_update(void* state, float growth, float backoff, int growth_interval, void* stream);
+
+/* ------------------------------------------------------------------ occupancy-grid update (SURVEY 8f NEXT-2) */
+
+/* Renderer.update_state (renderer.py:120-194) around the density query, as device passes with no host read-back.
+ * scale_hgs: device f32 [C][2] = (bound_c - half_grid_size_c, half_grid_size_c) per cascade, bound_c = min(2^c, bound),
+ * half_grid_size_c = bound_c / H (renderer.py:124-127).  noise: uniform [0,1) per coordinate (torch.rand_like, :129), or NULL.
+ *
+ * nrf_occ_points_full (:143-155): pts [C, H^3, 3] = jittered cell centres of every cascade, in MORTON order, so that the
+ * density of point (c, i) is tmp_grid[c][i] directly (the reference scatters with tmp_grid[cas, morton3D(coords)]).
+ * nrf_occ_points_sparse (:157-181): per cascade, slots [0,N) = random cells rnd_cells [C,N,3] i32, slots [N,2N) = random
+ * OCCUPIED cells occ_list[c][min(floor(pick * occ_count[c]), occ_count[c]-1)] (index -1 when the cascade has none);
+ * writes indices [C,2N] i32 (Morton) and pts [C,2N,3].  occ_list [C,H^3] / occ_count [C] come from nrf_occ_flags +
+ * nrf_compact_alive per cascade.
+ * nrf_occ_scatter_max: tmp[c][indices[c][j]] = max(tmp, sigmas[c][j] * density_scale) (tmp pre-filled with -1).
+ * nrf_occ_update (:183-188): grid = max(grid * decay, values * tmp_scale) where both are >= 0; state[0] = mean(max(grid,0)),
+ * state[1] = min(state[0], density_thresh); scratch: nrf_occ_scratch_bytes().
+ * nrf_packbits_dev (:189): nrf_packbits with the threshold read from device memory (state + 1). */
+int nrf_occ_points_full(float* pts, const float* noise, uint32_t H, uint32_t C, const float* scale_hgs, void* stream);
+int nrf_occ_points_sparse(float* pts, int32_t* indices, const float* noise, const int32_t* rnd_cells, const float* pick,
+                          const int32_t* occ_list, const int32_t* occ_count, uint32_t N, uint32_t H, uint32_t C,
+                          const float* scale_hgs, void* stream);
+int nrf_occ_flags(const float* grid, uint32_t H, uint32_t C, int32_t* flags, void* stream);
+int nrf_occ_scatter_max(float* tmp, const int32_t* indices, const float* sigmas, float density_scale, uint32_t n_per_cas,
+                        uint32_t H, uint32_t C, void* stream);
+uint64_t nrf_occ_scratch_bytes(void);
+int nrf_occ_update(float* grid, const float* values, float tmp_scale, float decay, uint64_t n, float density_thresh,
+                   float* state, void* scratch, void* stream);
+int nrf_packbits_dev(const float* grid, uint32_t N, const float* density_thresh_dev, uint8_t* bitfield, void* stream);
 
 /* ------------------------------------------------------------------ ray generation (SURVEY 8f NEXT-1) */
 

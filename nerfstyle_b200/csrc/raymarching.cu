@@ -99,25 +99,7 @@ NRF_EXPORT int nrf_sph_from_ray(const float* rays_o, const float* rays_d, float 
     return nrf_check_launch();
 }
 
-// raymarching.cu:56-81
-__device__ __forceinline__ uint32_t expand_bits(uint32_t v) {
-    v = (v * 0x00010001u) & 0xFF0000FFu;
-    v = (v * 0x00000101u) & 0x0F00F00Fu;
-    v = (v * 0x00000011u) & 0xC30C30C3u;
-    v = (v * 0x00000005u) & 0x49249249u;
-    return v;
-}
-__device__ __forceinline__ uint32_t morton3D_dev(uint32_t x, uint32_t y, uint32_t z) {
-    return expand_bits(x) | (expand_bits(y) << 1) | (expand_bits(z) << 2);
-}
-__device__ __forceinline__ uint32_t morton3D_invert_dev(uint32_t x) {
-    x = x & 0x49249249u;
-    x = (x | (x >> 2)) & 0xc30c30c3u;
-    x = (x | (x >> 4)) & 0x0f00f00fu;
-    x = (x | (x >> 8)) & 0xff0000ffu;
-    x = (x | (x >> 16)) & 0x0000ffffu;
-    return x;
-}
+// expand_bits / morton3D_dev / morton3D_invert_dev (raymarching.cu:56-81) live in common.cuh
 
 // raymarching.cu:313-325
 __global__ void k_morton3D(const int32_t* __restrict__ coords, uint32_t N, int32_t* __restrict__ indices) {

@@ -148,7 +148,7 @@ class Renderer(nn.Module):
 
     def __init__(self, model, bound, raymarch_channels=3, grid_size=128, update_iter=16, update_thres=256,
                  density_thresh=10., density_decay=0.95, density_scale=1., min_near=0.2, t_thresh=1e-4, max_steps=1024,
-                 grid_bsize=None):
+                 grid_bsize=None, fused_occupancy=True):
         super().__init__()
         self.model = model
         self.bound = bound
@@ -157,6 +157,10 @@ class Renderer(nn.Module):
         self.density_thresh, self.density_decay, self.density_scale = density_thresh, density_decay, density_scale
         self.min_near, self.t_thresh, self.max_steps, self.grid_bsize = min_near, t_thresh, max_steps, grid_bsize
         self.update_occ = True
+        # fused_occupancy: update_state runs as device passes with no host read-back (csrc/occupancy.cu); False = the
+        # reference's op sequence (update_state_reference)
+        self.fused_occupancy = fused_occupancy
+        self._occ = None
         self.cascade = 1 + ceil(log2(bound))
         self.register_buffer('aabb', torch.tensor([-bound, -bound, -bound, bound, bound, bound], dtype=torch.float32),
                              persistent=False)
@@ -171,6 +175,30 @@ class Renderer(nn.Module):
     @property
     def device(self):
         return self.aabb.device
+
+    # mean_density / mean_count (renderer.py:187,194) are host numbers in the reference, read back inside update_state.
+    # The fused update leaves them on the device; they are fetched (one sync) only when somebody asks.
+    @property
+    def mean_density(self):
+        v = self._mean_density
+        if torch.is_tensor(v):
+            v = self._mean_density = v.item()
+        return v
+
+    @mean_density.setter
+    def mean_density(self, v):
+        self._mean_density = v
+
+    @property
+    def mean_count(self):
+        v = self._mean_count
+        if isinstance(v, tuple):
+            v = self._mean_count = int(v[0].item() / v[1])
+        return v
+
+    @mean_count.setter
+    def mean_count(self, v):
+        self._mean_count = v
 
     def state_dict(self, *args, **kwargs):
         """renderer.py:78-91 (same keys; intr / precrop_frac belong to the caller's camera set-up)."""
@@ -201,9 +229,87 @@ class Renderer(nn.Module):
         sigmas = self.model(cas_xyzs).reshape(-1).detach() * self.density_scale
         return sigmas
 
-    @torch.no_grad()
     def update_state(self):
-        """renderer.py:138-194"""
+        """renderer.py:138-194."""
+        if self.fused_occupancy and self.density_grid.is_cuda:
+            return self.update_state_fused()
+        return self.update_state_reference()
+
+    def _occ_buffers(self):
+        L = raymarching.L
+        if self._occ is None or self._occ['dev'] != self.device:
+            sh = []
+            for cas in range(self.cascade):                      # renderer.py:124-127
+                bound = min(2 ** cas, self.bound)
+                half_grid_size = bound / self.grid_size
+                sh += [bound - half_grid_size, half_grid_size]
+            self._occ = {'dev': self.device,
+                         'scale_hgs': torch.tensor(sh, dtype=torch.float32, device=self.device),
+                         'state': torch.zeros(2, dtype=torch.float32, device=self.device),
+                         'scratch': torch.empty(int(L.lib().nrf_occ_scratch_bytes()), dtype=torch.uint8, device=self.device)}
+        return self._occ
+
+    @torch.no_grad()
+    def update_state_fused(self, noise=None, rnd_cells=None, pick=None):
+        """renderer.py:138-194 as device passes: the sample points of every cascade come out of one kernel in Morton order
+        (so the density query's output IS tmp_grid -- no meshgrid / cat / morton / index_put), ONE density query covers all
+        cascades, the decay / max update, the mean and the packbits threshold stay on the device (the reference reads the
+        mean density, the occupied-cell lists and the mean sample count back to the host every update).  The random inputs
+        (torch.rand_like :129, torch.randint :160,:164) can be passed in for testing."""
+        L = raymarching.L
+        lib, dev = L.lib(), self.device
+        H, C = self.grid_size, self.cascade
+        H3 = H ** 3
+        ob = self._occ_buffers()
+        grid = self.density_grid
+        assert grid.is_contiguous() and grid.dtype == torch.float32
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            if self.local_step < self.update_thres:
+                if noise is None:
+                    noise = torch.rand(C, H3, 3, device=dev)
+                pts = torch.empty(C, H3, 3, dtype=torch.float32, device=dev)
+                L.check(lib.nrf_occ_points_full(pts.data_ptr(), L.ptr(noise), H, C, ob['scale_hgs'].data_ptr(), st), 'occ_points_full')
+                values = self.model(pts.view(-1, 3)).reshape(-1).detach().float().contiguous()
+                tmp_scale = float(self.density_scale)
+            else:
+                N = H3 // 4
+                if rnd_cells is None:
+                    rnd_cells = torch.randint(0, H, (C, N, 3), device=dev, dtype=torch.int32)
+                if pick is None:
+                    pick = torch.rand(C, N, device=dev)
+                if noise is None:
+                    noise = torch.rand(C, 2 * N, 3, device=dev)
+                flags = torch.empty(C, H3, dtype=torch.int32, device=dev)
+                occ_list = torch.empty(C, H3, dtype=torch.int32, device=dev)
+                occ_count = torch.empty(C, dtype=torch.int32, device=dev)
+                L.check(lib.nrf_occ_flags(grid.data_ptr(), H, C, flags.data_ptr(), st), 'occ_flags')
+                scratch = L.scratch(dev, lib.nrf_march_scratch_bytes(H3))
+                for cas in range(C):                 # the device-side torch.nonzero(density_grid[cas] > 0) of :163
+                    L.check(lib.nrf_compact_alive(flags[cas].data_ptr(), H3, occ_list[cas].data_ptr(),
+                                                  occ_count[cas:cas + 1].data_ptr(), scratch.data_ptr(), st), 'compact_alive')
+                pts = torch.empty(C, 2 * N, 3, dtype=torch.float32, device=dev)
+                indices = torch.empty(C, 2 * N, dtype=torch.int32, device=dev)
+                L.check(lib.nrf_occ_points_sparse(pts.data_ptr(), indices.data_ptr(), L.ptr(noise), rnd_cells.contiguous().data_ptr(),
+                                                  pick.contiguous().data_ptr(), occ_list.data_ptr(), occ_count.data_ptr(), N, H, C,
+                                                  ob['scale_hgs'].data_ptr(), st), 'occ_points_sparse')
+                sig = self.model(pts.view(-1, 3)).reshape(-1).detach().float().contiguous()
+                values = torch.full((C, H3), -1.0, dtype=torch.float32, device=dev)
+                L.check(lib.nrf_occ_scatter_max(values.data_ptr(), indices.data_ptr(), sig.data_ptr(), float(self.density_scale),
+                                                2 * N, H, C, st), 'occ_scatter_max')
+                tmp_scale = 1.0
+                self._occ_last = (indices, pts)
+            L.check(lib.nrf_occ_update(grid.data_ptr(), values.data_ptr(), tmp_scale, float(self.density_decay), C * H3,
+                                       float(self.density_thresh), ob['state'].data_ptr(), ob['scratch'].data_ptr(), st), 'occ_update')
+            L.check(lib.nrf_packbits_dev(grid.data_ptr(), C * H3 // 8, ob['state'].data_ptr() + 4, self.density_bitfield.data_ptr(), st),
+                    'packbits_dev')
+        self._mean_density = ob['state'][0].clone()                       # fetched lazily (property)
+        total_step = min(STEP_CTR_SIZE, self.update_iter)
+        self._mean_count = (self.step_counter[:total_step, 0].sum(), total_step)
+
+    @torch.no_grad()
+    def update_state_reference(self):
+        """renderer.py:138-194, op for op."""
         tmp_grid = -torch.ones_like(self.density_grid)
         if self.local_step < self.update_thres:
             bsize = self.grid_bsize if self.grid_bsize is not None else self.grid_size
@@ -250,7 +356,8 @@ class Renderer(nn.Module):
             counter = torch.zeros(2).to(self.step_counter)
         xyzs, dirs, deltas, rays_info = raymarching.march_rays_train(
             rays_o, rays_d, None, self.bound, self.density_bitfield, self.cascade, self.grid_size, nears, fars, counter,
-            self.mean_count, True, 128, True, 0., self.max_steps, False)
+            self._mean_count if isinstance(self._mean_count, int) else -1,       # unused under force_all_rays=True (:219-222)
+            True, 128, True, 0., self.max_steps, False)
         rgbs, sigmas = self.model(xyzs, dirs=dirs, **kwargs)
         sigmas = sigmas * self.density_scale
         weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays_info, self.t_thresh, False)

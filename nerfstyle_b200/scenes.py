@@ -49,6 +49,18 @@ def generate_rays(pose, intr, device, indices=None):
     """Pixel-centre rays of one view.  pose [4,4]; indices: optional LongTensor of flat pixel ids (row-major over
     h x w).  Returns unit-norm rays_d [K,3] and rays_o [K,3] on `device` (float32)."""
     w, h = int(intr['w']), int(intr['h'])
+    if torch.device(device).type == 'cuda':
+        # the product path: one nrf_generate_rays launch (nerfstyle_b200.nerf_lib), same arithmetic as the lines below
+        from .nerf_lib import Intrinsics, NerfLib
+        lib = NerfLib()
+        lib.device = device
+        it = Intrinsics(h, w, intr['fx'], intr['fy'], intr['cx'], intr['cy'])
+        if indices is None:
+            rb, _ = lib.generate_rays(pose, it, camera_flip=int(intr.get('flip_camera', 0)))
+        else:
+            rb, _ = lib.generate_rays(pose, it, bsize=int(indices.numel()), indices=indices,
+                                      camera_flip=int(intr.get('flip_camera', 0)))
+        return rb.origins, rb.dirs
     pose = torch.as_tensor(pose, dtype=torch.float32, device=device)
     if indices is None:
         indices = torch.arange(w * h, device=device)

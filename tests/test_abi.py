@@ -39,6 +39,14 @@ def test_error_reporting_without_gpu(cuda_lib):
     assert cuda_lib.nrf_near_far_from_aabb(None, None, None, 0, 0.2, None, None, None) == 0
     assert cuda_lib.nrf_mlp_forward(None, 0, None, 0, 32, 1, 1, 64, 1, 0, None, 1, None) == 0
     assert cuda_lib.nrf_march_scratch_bytes(8192) >= 8192 // 64 * 4
+    # entry points added for SURVEY 8f NEXT-1 / the paired tables: same rules
+    assert cuda_lib.nrf_generate_rays(None, 1.0, 1.0, 0.5, 0.5, 0, 0, 4, 16, None, 0, None, 0, 0, None, None, None, None) == -1
+    assert cuda_lib.nrf_generate_rays(None, 1.0, 1.0, 0.5, 0.5, 0, 0, 4, 0, None, 0, None, 0, 0, None, None, None, None) == 0
+    assert cuda_lib.nrf_grid_encode_forward_pair(None, None, None, None, None, 8, 16, 0.5, 16, 0, 1, 0, 1, None, None, None, None) == -1
+    assert cuda_lib.nrf_grid_encode_backward_pair(None, None, None, None, None, 0, 16, 0.5, 16, 0, 1, 0, 1, None, None) == 0
+    assert cuda_lib.nrf_adam_step_pair(None, None, None, None, None, None, None, None, None, None, 4, None, 0.01, 0.0, 0.9, 0.999,
+                                       1e-15, 0.05, None) == -1
+    assert cuda_lib.nrf_adam_step_ex(None, None, None, None, None, None, 0, None, 0.01, 0.0, 0.9, 0.999, 1e-15, 0.05, 1, 1, None) == 0
 
 
 def test_product_never_imports_oracle():

@@ -295,3 +295,86 @@ def test_paired_tables_match_unpaired(cuda_lib, dev):
         da, db = (a['after'][n] - a['before'][n])[mask], (b['after'][n] - b['before'][n])[mask]
         torch.testing.assert_close(da, db, rtol=1e-3, atol=1e-6)
         assert mask.sum() > 0
+
+
+def _occ_renderers(dev, **kw):
+    """Two renderers sharing one model (so both query the same field): fused and reference occupancy update."""
+    from nerfstyle_b200 import model as M
+    torch.manual_seed(0)
+    m = M.StyleTCNerf([-2., -2., -2.], [2., 2., 2.], class_dim=8).to(dev)
+    with torch.no_grad():
+        for e in (m.x_density_embedder, m.x_color_embedder):
+            e.embeddings.uniform_(-0.5, 0.5, generator=torch.Generator(device=dev).manual_seed(5))
+    a = M.Renderer(m, 2.0, raymarch_channels=11, fused_occupancy=True, **kw).to(dev)
+    b = M.Renderer(m, 2.0, raymarch_channels=11, fused_occupancy=False, **kw).to(dev)
+    return m, a, b
+
+
+def test_update_state_fused_full_phase_equals_reference_ops(cuda_lib, dev, monkeypatch):
+    """Renderer.update_state as device passes (nrf_occ_points_full / nrf_occ_update / nrf_packbits_dev) against the reference's
+    op sequence (renderer.py:138-194) on the same jitter: the density grid is bit-identical, the mean within 1e-6, the bitfield
+    identical up to cells that sit on the threshold."""
+    from nerfstyle_b200 import raymarching
+    m, a, b = _occ_renderers(dev)
+    H, C = a.grid_size, a.cascade
+    H3 = H ** 3
+    g = torch.Generator(device=dev).manual_seed(11)
+    for rnd in range(2):                                        # second round exercises the decay / max against a non-zero grid
+        noise = torch.rand(C, H3, 3, device=dev, generator=g)   # Morton order
+        # the reference draws its jitter in meshgrid (x, y, z) order: row j = (x * H + y) * H + z  <->  Morton cell i
+        ar = torch.arange(H, dtype=torch.int32, device=dev)
+        xx, yy, zz = torch.meshgrid(ar, ar, ar, indexing='ij')
+        mort = raymarching.morton3D(torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], dim=-1)).long()
+        queue = [noise[c][mort] for c in range(C)]
+        monkeypatch.setattr(torch, 'rand_like', lambda t, _q=queue: _q.pop(0).to(t.dtype))
+        with torch.autocast('cuda', dtype=torch.float16):
+            b.update_state()
+        monkeypatch.undo()
+        assert not queue
+        with torch.autocast('cuda', dtype=torch.float16):
+            a.update_state_fused(noise=noise)
+        assert torch.equal(a.density_grid, b.density_grid)
+        assert float(a.density_grid.max()) > 0
+        assert abs(a.mean_density - b.mean_density) <= 1e-6 * abs(b.mean_density)
+        diff = int((a.density_bitfield != b.density_bitfield).sum())
+        assert diff <= 2, diff
+        assert int(a.density_bitfield.count_nonzero()) > 1000
+        assert a.mean_count == b.mean_count
+        a.local_step = b.local_step = 16                        # still the full phase (< update_thres)
+
+
+def test_update_state_fused_sparse_phase_semantics(cuda_lib, dev):
+    """Later-phase update (renderer.py:157-181) on the device: random cells + random OCCUPIED cells, tmp_grid scatter, decay/max.
+    Checked by recomputation from the points the update used: untouched cells keep their value, sampled cells become
+    max(old * decay, sigma of a sample in that cell); the occupied picks are occupied; the random cells are morton3D(rnd)."""
+    from nerfstyle_b200 import raymarching
+    m, a, b = _occ_renderers(dev)
+    H, C = a.grid_size, a.cascade
+    H3 = H ** 3
+    N = H3 // 4
+    with torch.autocast('cuda', dtype=torch.float16):
+        a.update_state_fused()                                  # populate the grid (full phase)
+    a.local_step = a.update_thres + 5
+    old = a.density_grid.clone()
+    g = torch.Generator(device=dev).manual_seed(3)
+    rnd_cells = torch.randint(0, H, (C, N, 3), device=dev, dtype=torch.int32, generator=g)
+    pick = torch.rand(C, N, device=dev, generator=g)
+    noise = torch.rand(C, 2 * N, 3, device=dev, generator=g)
+    with torch.autocast('cuda', dtype=torch.float16):
+        a.update_state_fused(noise=noise, rnd_cells=rnd_cells, pick=pick)
+        indices, pts = a._occ_last
+        sig = (m(pts.view(-1, 3)).reshape(C, 2 * N).float() * a.density_scale)
+    for c in range(C):
+        assert torch.equal(indices[c, :N], raymarching.morton3D(rnd_cells[c]))
+        occ = indices[c, N:].long()
+        assert bool((old[c][occ] > 0).all())
+        # expected: scatter-amax of the samples, then the reference's masked decay / max
+        tmp = torch.full((H3,), -1.0, device=dev).scatter_reduce(0, indices[c].long(), sig[c], reduce='amax', include_self=True)
+        exp = torch.where((old[c] >= 0) & (tmp >= 0), torch.maximum(old[c] * a.density_decay, tmp), old[c])
+        assert torch.equal(a.density_grid[c], exp)
+        assert int((tmp >= 0).sum()) > N // 2 and int((tmp < 0).sum()) > 0
+    # the points lie inside their cells' cascade-scaled, jittered boxes
+    assert float(pts.abs().max()) <= a.bound
+    thr = min(a.mean_density, a.density_thresh)
+    ref_bits = raymarching.packbits(a.density_grid, thr)
+    assert int((ref_bits != a.density_bitfield).sum()) <= 2
