@@ -3,6 +3,7 @@
     python tools/bench_configs.py render  [--w 1008 --h 756 --frames 3]        # config 3 (torchrun for N>1: tiles shard)
     python tools/bench_configs.py nnfm                                         # config 4: matching kernel vs torch composition
     python tools/bench_configs.py sweep                                        # config 5: rays/step sweep (torchrun for N>1)
+    python tools/bench_configs.py style                                        # config 4: one whole stylization step (trainers/style.py:162-207)
 Each prints one JSON line.
 """
 import argparse
@@ -126,6 +127,100 @@ def nnfm_bench(args):
     print(json.dumps({'config': 'nnfm_matching', 'N1': N1, 'N2': N2, 'K': K, **res}))
 
 
+def style(args):
+    """One stylization training step the way StyleTrainer.run_iter does it (trainers/style.py:162-207), on this repo's ops:
+    (1) full-frame render WITHOUT gradients (render_train on all 504x378 rays), (2) VGG-16 relu3 features of the render, the
+    target and the style image, content MSE + segment-wise nearest-neighbour matching loss (loss.py:187-214, nrf_nnfm_forward),
+    backward to d loss / d pixel, (3) the frame again in 200x200 patches WITH gradients (nerf_lib.generate_rays(patch=...)),
+    each patch's render backpropagated with its slice of the cached pixel gradients, (4) GradScaler + Adam step on the colour
+    hash table only (StyleTrainer.OPTIM_KEYS).  VGG-16 is torchvision's (weights=None: no network here) running on cuDNN --
+    library code, outside the hot path; everything else is this repo's kernels."""
+    import itertools
+    import torchvision
+    from nerfstyle_b200 import nnfm as NN
+    from nerfstyle_b200.nerf_lib import Box2D, Intrinsics, NerfLib
+    from nerfstyle_b200.optim import FusedAdamEMA
+    world, rank, dev = setup()
+    torch.manual_seed(0)
+    W, H, K = 504, 378, B.N_CLASSES
+    m = M.StyleTCNerf([-2., -2., -2.], [2., 2., 2.], class_dim=K).to(dev)
+    r = M.Renderer(m, 2.0, raymarch_channels=3 + K).to(dev)
+    with torch.autocast('cuda', dtype=torch.float16):
+        r.update_state()
+    r.update_occ = False
+    intr = Intrinsics(H, W, scenes.ROOM['fx'], scenes.ROOM['fy'], scenes.ROOM['cx'], scenes.ROOM['cy'])
+    pose = torch.from_numpy(scenes.synthetic_poses(2, 0)[0]).to(dev)
+    nl = NerfLib()
+    nl.device = dev
+    flip = scenes.ROOM['flip_camera']
+    all_idx = torch.arange(W * H, device=dev)
+    tgt_rgb, tgt_cls = scenes.synthetic_target(all_idx, dict(scenes.ROOM))
+    target_chw = tgt_rgb.t().reshape(3, H, W).contiguous()
+    vgg = torchvision.models.vgg16(weights=None).features[:16].to(dev).eval()
+    for p_ in vgg.parameters():
+        p_.requires_grad_(False)
+
+    def fx(img_chw):                       # networks/fx.py: 'relu3' = the three relu3_x maps concatenated (768 channels)
+        x, outs = img_chw[None], []
+        for i, layer in enumerate(vgg):
+            x = layer(x)
+            if i in (11, 13, 15):
+                outs.append(x)
+        return torch.cat(outs, dim=1)[0]
+    style_img = torch.rand(3, 504, 504, device=dev)
+    with torch.no_grad(), torch.autocast('cuda', dtype=torch.float16):
+        style_feat = fx(style_img)
+        target_feat = fx(target_chw)
+    hs, ws = style_feat.shape[1:]
+    clusters = (torch.arange(ws, device=dev) * K // ws)[None, :].expand(hs, ws).contiguous()
+    matching = list(range(K))
+    opt = FusedAdamEMA([m.x_color_embedder.embeddings], lr=0.01, eps=1e-15, lr_decay_steps=30000, ema_decay=None, enable_amp=True)
+    ps = 200
+    content_lambda, style_lambda = 1.0, 1.0
+    def step():
+        opt.zero_grad()
+        for p_ in m.parameters():
+            p_.grad = None
+        with torch.no_grad(), torch.autocast('cuda', dtype=torch.float16):
+            rays, _ = nl.generate_rays(pose, intr, camera_flip=flip)
+            image, depth, classes = r.render_train(rays.origins, rays.dirs)
+        rgb_map = image.detach().clone().requires_grad_(True)
+        with torch.autocast('cuda', dtype=torch.float16):
+            rgb_chw = rgb_map.t().reshape(3, H, W)
+            feat = fx(rgb_chw)
+            preds = torch.argmax(classes.t().reshape(K, H, W), dim=0)
+            nh, nw = feat.shape[1:]                # labels_downscale (loss.py:23-28)
+            preds_small = preds[torch.linspace(0, H - 1, nh, device=dev).long()[:, None], torch.linspace(0, W - 1, nw, device=dev).long()]
+            content = torch.nn.functional.mse_loss(feat.float(), target_feat.float()) * content_lambda
+            sty = NN.semantic_nnfm_loss(feat, style_feat, preds_small, clusters, matching) * style_lambda
+            total = content + sty
+        opt.scale_loss(total).backward()
+        grad_map = rgb_map.grad.reshape(H, W, 3)
+        for x0, y0 in itertools.product(range(0, W, ps), range(0, H, ps)):
+            patch = Box2D(x=x0, y=y0, w=ps, h=ps)
+            with torch.autocast('cuda', dtype=torch.float16):
+                prays, _ = nl.generate_rays(pose, intr, patch=patch, camera_flip=flip)
+                pimg, _, _ = r.render_train(prays.origins, prays.dirs)
+            pg = grad_map[patch.hrange(), patch.wrange()].reshape(-1, 3)
+            pimg.backward(pg)
+        opt.step()
+        return total.detach()
+    step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.frames):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.frames
+    print(json.dumps({'config': 'stylization_step', 'w': W, 'h': H, 'rays_per_pass': W * H, 'patches': 6, 'patch_size': ps,
+                      'image_feats': list(target_feat.shape), 'style_feats': list(style_feat.shape), 'ms_per_step': round(ms, 2),
+                      'rays_per_s_both_passes': round(2 * W * H / ms * 1e3, 1), 'steps': args.frames, 'loss': float(loss),
+                      'optimised': 'x_color_embedder.embeddings', 'peak_mem_gb': round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2),
+                      'vgg': 'torchvision vgg16(weights=None).features[:16], cuDNN (library, outside the hot path)'}))
+
+
 def sweep(args):
     world, rank, dev = setup()
     out = []
@@ -165,7 +260,7 @@ def sweep(args):
 
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
-    ap.add_argument('what', choices=['render', 'nnfm', 'sweep'])
+    ap.add_argument('what', choices=['render', 'nnfm', 'sweep', 'style'])
     ap.add_argument('--w', type=int, default=1008)
     ap.add_argument('--h', type=int, default=756)
     ap.add_argument('--frames', type=int, default=3)
@@ -174,4 +269,4 @@ if __name__ == '__main__':
     ap.add_argument('--sync-every', type=int, default=4)
     ap.add_argument('--loop', default='graph', choices=['graph', 'host'])
     a = ap.parse_args()
-    {'render': render, 'nnfm': nnfm_bench, 'sweep': sweep}[a.what](a)
+    {'render': render, 'nnfm': nnfm_bench, 'sweep': sweep, 'style': style}[a.what](a)
