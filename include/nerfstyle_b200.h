@@ -169,7 +169,8 @@ int nrf_grid_encode_backward(const void* grad, const float* inputs, const void* 
  * x_color_embedder, networks/style_nerf.py:29-30,121-134, are such a pair).  D=3, C=2, point-major [B, L*2] outputs /
  * gradients, no input gradients.  Results are those of two nrf_grid_encode_forward / _backward calls.
  * xform (device float[7] = {min[3], size[3], bound}, or NULL): the points are first mapped by ((x - min) / size + bound) /
- * (2 bound) in f32, operation for operation what common.py:288 and grid.py:174 do in four elementwise kernels. */
+ * (2 bound) in f32, operation for operation what common.py:288 and grid.py:174 do in four elementwise kernels. 
+ * A table that takes no gradient passes NULL for both its grad and its grad_embeddings (its share of the scatter is skipped). */
 int nrf_grid_encode_forward_dual(const float* inputs, const void* embeddings0, const void* embeddings1,
                                  const int32_t* offsets, void* outputs0, void* outputs1, uint32_t B, uint32_t L, float S,
                                  uint32_t H, uint32_t gridtype, int align_corners, uint32_t style, int dtype,

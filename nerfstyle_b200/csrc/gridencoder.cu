@@ -431,7 +431,9 @@ k_grid_bwd_d3c2(const T* __restrict__ grad0, const T* __restrict__ grad1, const 
     for (int e = 0; e < NE; e++) {
         const T* grad = e == 0 ? grad0 : grad1;
         uint32_t* sge = sg[e];
-        if (point_major) {
+        if (grad == nullptr) {                             // this table takes no gradient (frozen): all-zero rows, skipped below
+            for (int c = threadIdx.x; c < GRID_BLOCK * ROW; c += GRID_BLOCK) sge[c] = 0u;
+        } else if (point_major) {
             constexpr int WORDS = LPT * WPL;               // words per point in this level group
             const bool vec = (WORDS % 4 == 0) && ((L * WPL) % 4 == 0) && ((l0 * WPL) % 4 == 0) && (nlev == (uint32_t)LPT) &&
                              (((uintptr_t)grad & 15) == 0);
@@ -771,7 +773,9 @@ NRF_EXPORT int nrf_grid_encode_backward_dual(const void* grad0, const void* grad
                                              uint32_t gridtype, int align_corners, uint32_t style, int dtype, int grad_table_dtype,
                                              const float* xform, void* stream) {
     if (B == 0) return NRF_OK;
-    if (!grad0 || !grad1 || !inputs || !offsets || !grad_embeddings0 || !grad_embeddings1) return NRF_E_INVALID;
+    // a table that takes no gradient (frozen) passes NULL for BOTH its output gradient and its table gradient
+    if ((grad0 == nullptr) != (grad_embeddings0 == nullptr) || (grad1 == nullptr) != (grad_embeddings1 == nullptr)) return NRF_E_INVALID;
+    if ((!grad0 && !grad1) || !inputs || !offsets) return NRF_E_INVALID;
     if (L == 0 || L > GRID_MAX_LEVELS) return NRF_E_UNSUPPORTED;
     if ((((uintptr_t)grad_embeddings0) & 7) || (((uintptr_t)grad_embeddings1) & 7)) return NRF_E_INVALID;
     cudaStream_t s = (cudaStream_t)stream;

@@ -161,6 +161,9 @@ class _grid_encode_dual(Function):
         inputs, offsets, xform = ctx.saved_tensors
         B, Lv, S, H, gridtype, align_corners, style, dtype, shape = ctx.meta
         dev = inputs.device
+        need = [bool(ctx.needs_input_grad[1]), bool(ctx.needs_input_grad[2])]
+        if not any(need):
+            return None, None, None, None, None, None, None, None, None, None
         gs = []
         for g in (g0, g1):
             if g is None:
@@ -168,7 +171,7 @@ class _grid_encode_dual(Function):
             g = g.contiguous()
             gs.append(g if g.dtype == dtype else g.to(dtype))
         L.Stats.units = B
-        if ctx.sink is not None:
+        if ctx.sink is not None and all(need):
             # the optimizer owns ONE interleaved f32 gradient buffer for both tables and reads it directly: the tables'
             # .grad stays None (FusedAdamEMA.grad_of); repeated backwards before a step accumulate in the buffer
             gp = ctx.sink.grad_pair_buffer()
@@ -178,13 +181,15 @@ class _grid_encode_dual(Function):
                                                               L.dtype_code(dtype), L.ptr(xform), L.stream_of(inputs)),
                         'grid_encode_backward_pair')
             return None, None, None, None, None, None, None, None, None, None
-        ge0 = torch.zeros(shape, dtype=torch.float32, device=dev)
-        ge1 = torch.zeros(shape, dtype=torch.float32, device=dev)
+        # a frozen table (requires_grad False, e.g. the density table of the stylization stage when the caller freezes it)
+        # passes NULL: no zero fill, no reductions for it
+        ge0 = torch.zeros(shape, dtype=torch.float32, device=dev) if need[0] else None
+        ge1 = torch.zeros(shape, dtype=torch.float32, device=dev) if need[1] else None
         with torch.cuda.device(dev):
-            L.check(L.lib().nrf_grid_encode_backward_dual(L.ptr(gs[0]), L.ptr(gs[1]), L.ptr(inputs), L.ptr(offsets), L.ptr(ge0),
-                                                          L.ptr(ge1), B, Lv, S, H, int(gridtype), int(bool(align_corners)),
-                                                          int(style), L.dtype_code(dtype), L.DTYPE_F32, L.ptr(xform),
-                                                          L.stream_of(inputs)),
+            L.check(L.lib().nrf_grid_encode_backward_dual(L.ptr(gs[0]) if need[0] else None, L.ptr(gs[1]) if need[1] else None,
+                                                          L.ptr(inputs), L.ptr(offsets), L.ptr(ge0), L.ptr(ge1), B, Lv, S, H,
+                                                          int(gridtype), int(bool(align_corners)), int(style), L.dtype_code(dtype),
+                                                          L.DTYPE_F32, L.ptr(xform), L.stream_of(inputs)),
                     'grid_encode_backward_dual')
         return None, ge0, ge1, None, None, None, None, None, None, None
 

@@ -203,6 +203,37 @@ def test_dual_equals_two_single_passes(cuda_lib, dev, amp):
             assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
 
 
+@pytest.mark.parametrize('frozen', [0, 1])
+def test_dual_backward_with_a_frozen_table(cuda_lib, dev, frozen):
+    """A table with requires_grad False (the stylization stage optimises the colour table only) takes no share of the dual
+    scatter: its .grad stays None, the other table's gradient is unchanged."""
+    from nerfstyle_b200.gridencoder import grid_encode_dual
+    ea, eb = _default_encoder(dev, 1), _default_encoder(dev, 2)
+    x = _points(7001, 3, dev, -1.0, 1.0)
+    grads = []
+    for freeze in (False, True):
+        for e in (ea, eb):
+            e.embeddings.grad = None
+            e.embeddings.requires_grad_(True)
+        if freeze:
+            (ea, eb)[frozen].embeddings.requires_grad_(False)
+        with torch.autocast('cuda', dtype=torch.float16):
+            oa, ob = grid_encode_dual(x, ea, eb)
+        ga = torch.randn(oa.shape, generator=torch.Generator().manual_seed(6)).to(dev).to(oa.dtype)
+        gb = torch.randn(ob.shape, generator=torch.Generator().manual_seed(7)).to(dev).to(ob.dtype)
+        outs, gs = ([oa, ob], [ga, gb]) if not freeze else ([(oa, ob)[1 - frozen]], [(ga, gb)[1 - frozen]])
+        torch.autograd.backward(outs, gs)
+        grads.append([None if e.embeddings.grad is None else e.embeddings.grad.clone() for e in (ea, eb)])
+    assert grads[1][frozen] is None and grads[0][frozen] is not None
+    a, b = grads[1][1 - frozen], grads[0][1 - frozen]
+    assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) and float(b.abs().max()) > 0
+    for e in (ea, eb):
+        e.embeddings.requires_grad_(True)
+    # the C ABI insists that a frozen table drops BOTH its pointers, and that at least one table is live
+    assert cuda_lib.nrf_grid_encode_backward_dual(None, 8, 8, 8, 8, 8, 4, 16, 0.5, 16, 0, 1, 0, 1, 0, None, None) == -1
+    assert cuda_lib.nrf_grid_encode_backward_dual(None, None, 8, 8, None, None, 4, 16, 0.5, 16, 0, 1, 0, 1, 0, None, None) == -1
+
+
 def test_dual_input_transform_is_bit_exact(cuda_lib, dev):
     """xform folds BBox.normalize and the encoder's input map into the kernel: same f32 operations -> same bits."""
     from nerfstyle_b200.gridencoder import grid_encode_dual

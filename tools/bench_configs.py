@@ -174,6 +174,9 @@ def style(args):
     hs, ws = style_feat.shape[1:]
     clusters = (torch.arange(ws, device=dev) * K // ws)[None, :].expand(hs, ws).contiguous()
     matching = list(range(K))
+    if args.freeze:      # the reference leaves requires_grad on (its optimizer just ignores the other gradients); freezing skips them
+        for n_, p_ in m.named_parameters():
+            p_.requires_grad_(n_ == 'x_color_embedder.embeddings')
     opt = FusedAdamEMA([m.x_color_embedder.embeddings], lr=0.01, eps=1e-15, lr_decay_steps=30000, ema_decay=None, enable_amp=True)
     ps = 200
     content_lambda, style_lambda = 1.0, 1.0
@@ -217,7 +220,7 @@ def style(args):
     print(json.dumps({'config': 'stylization_step', 'w': W, 'h': H, 'rays_per_pass': W * H, 'patches': 6, 'patch_size': ps,
                       'image_feats': list(target_feat.shape), 'style_feats': list(style_feat.shape), 'ms_per_step': round(ms, 2),
                       'rays_per_s_both_passes': round(2 * W * H / ms * 1e3, 1), 'steps': args.frames, 'loss': float(loss),
-                      'optimised': 'x_color_embedder.embeddings', 'peak_mem_gb': round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2),
+                      'optimised': 'x_color_embedder.embeddings', 'others_frozen': bool(args.freeze), 'peak_mem_gb': round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2),
                       'vgg': 'torchvision vgg16(weights=None).features[:16], cuDNN (library, outside the hot path)'}))
 
 
@@ -268,5 +271,6 @@ if __name__ == '__main__':
     ap.add_argument('--density-scale', type=float, default=1.0)
     ap.add_argument('--sync-every', type=int, default=4)
     ap.add_argument('--loop', default='graph', choices=['graph', 'host'])
+    ap.add_argument('--freeze', action='store_true', help='style: requires_grad False on everything but the colour table')
     a = ap.parse_args()
     {'render': render, 'nnfm': nnfm_bench, 'sweep': sweep, 'style': style}[a.what](a)
