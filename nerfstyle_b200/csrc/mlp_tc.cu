@@ -593,11 +593,14 @@ k_mlp_bwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ pa
             if (!first) { tc05::mbar_wait(&bar_wdone, phase_w); phase_w ^= 1; }      // operand tiles are free again
             PROF_MARK(1);      // previous tile's weight-gradient MMAs done
             stage_x_tile<CPR>(xr, smem + L.X, CH, coal, warp, lane, tid);
+            PROF_MARK(13);     // x rows staged (first use of the prefetched registers: exposes any load latency left)
             if (linear_out) {
                 *reinterpret_cast<uint4*>(dzrow) = make_uint4(dyc[0], dyc[1], dyc[2], dyc[3]);
                 *reinterpret_cast<uint4*>(dzrow + CH) = make_uint4(dyc[4], dyc[5], dyc[6], dyc[7]);
             }
+            PROF_MARK(14);     // dZ rows staged
             publish(&bar_ready);
+            PROF_MARK(15);     // proxy fence + arrive
             {   // prefetch the next tile's rows
                 const uint32_t nt = tile + gridDim.x;
                 const size_t nrow = (size_t)nt * 128 + tid;

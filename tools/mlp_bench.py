@@ -77,7 +77,7 @@ def main():
             torch.cuda.synchronize()
             lib.nrf_mlp_set_profile(None)
             ntile = -(-B // 128) / (148 * min(ctas, 4 if nh == 1 else 2))
-            print('   prof ctas/sm=%d cycles/tile: %s' % (ctas, ' '.join('%d:%.0f' % (i, v / ntile) for i, v in enumerate(prof.tolist()[:13]))))
+            print('   prof ctas/sm=%d cycles/tile: %s' % (ctas, ' '.join('%d:%.0f' % (i, v / ntile) for i, v in enumerate(prof.tolist()[:16]))))
         lib.nrf_mlp_set_tuning(5, 4)
 
 
