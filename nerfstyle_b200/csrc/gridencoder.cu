@@ -203,6 +203,15 @@ k_grid_fwd_d3c2(const float* __restrict__ inputs, const T* __restrict__ table0, 
         if (point_major) {
             V2* o = reinterpret_cast<V2*>(outputs) + (size_t)b * L + l0;
             constexpr int PER16 = 16 / (int)sizeof(V2);
+            if constexpr (sizeof(T) == 2 && LPT == 8) {
+                // 8 levels of f16 pairs = one 32-byte sector: a single 256-bit store (STG.E.256, sm_100)
+                if ((L % 8) == 0 && l0 + LPT <= L && ((uintptr_t)outputs & 31) == 0) {
+                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o), "r"(h2u(res[e][0])), "r"(h2u(res[e][1])),
+                                 "r"(h2u(res[e][2])), "r"(h2u(res[e][3])), "r"(h2u(res[e][4])), "r"(h2u(res[e][5])), "r"(h2u(res[e][6])),
+                                 "r"(h2u(res[e][7])) : "memory");
+                    continue;
+                }
+            }
             if (LPT % PER16 == 0 && (L % PER16) == 0 && l0 + LPT <= L && ((uintptr_t)outputs & 15) == 0) {
 #pragma unroll
                 for (int j = 0; j < LPT; j += PER16) {

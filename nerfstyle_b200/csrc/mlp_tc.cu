@@ -95,12 +95,22 @@ template <int CPR>
 __device__ __forceinline__ void load_x_tile(uint4 (&xr)[CPR], const void* __restrict__ x, int x_dt, size_t tile_row0, bool tile_ok, uint32_t B,
                                             uint32_t n_in, bool x_vec, bool coal, int warp, int lane, int tid) {
     if (coal) {
+        // 32-byte pieces (one sector, LDG.E.256): piece i * 32 + lane of the warp's 32 rows x CPR/2 pieces -- a warp request
+        // reads 1 KB of consecutive global memory
+        constexpr int PPR = CPR / 2;
 #pragma unroll
-        for (int i = 0; i < CPR; i++) {
-            const int idx = i * 32 + lane, r = idx / CPR, c = idx - r * CPR;
+        for (int i = 0; i < PPR; i++) {
+            const int idx = i * 32 + lane, r = idx / PPR, c2 = idx - r * PPR;
             const size_t row = tile_row0 + warp * 32 + r;
-            xr[i] = (tile_ok && row < B) ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(x) + row * n_in) + c)
-                                         : make_uint4(0u, 0u, 0u, 0u);
+            if (tile_ok && row < B) {
+                const __half* p = reinterpret_cast<const __half*>(x) + row * n_in + 16 * c2;
+                asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=r"(xr[2 * i].x), "=r"(xr[2 * i].y), "=r"(xr[2 * i].z), "=r"(xr[2 * i].w),
+                               "=r"(xr[2 * i + 1].x), "=r"(xr[2 * i + 1].y), "=r"(xr[2 * i + 1].z), "=r"(xr[2 * i + 1].w) : "l"(p));
+            } else {
+                xr[2 * i] = make_uint4(0u, 0u, 0u, 0u);
+                xr[2 * i + 1] = make_uint4(0u, 0u, 0u, 0u);
+            }
         }
     } else {
         const size_t row = tile_row0 + tid;
@@ -111,10 +121,12 @@ __device__ __forceinline__ void load_x_tile(uint4 (&xr)[CPR], const void* __rest
 template <int CPR>
 __device__ __forceinline__ void stage_x_tile(const uint4 (&xr)[CPR], uint8_t* sX, uint32_t CH, bool coal, int warp, int lane, int tid) {
     if (coal) {
+        constexpr int PPR = CPR / 2;
 #pragma unroll
-        for (int i = 0; i < CPR; i++) {
-            const int idx = i * 32 + lane, r = idx / CPR, c = idx - r * CPR;
-            *reinterpret_cast<uint4*>(sX + c * CH + (warp * 32 + r) * 16) = xr[i];
+        for (int i = 0; i < PPR; i++) {
+            const int idx = i * 32 + lane, r = idx / PPR, c2 = idx - r * PPR;
+            *reinterpret_cast<uint4*>(sX + (2 * c2) * CH + (warp * 32 + r) * 16) = xr[2 * i];
+            *reinterpret_cast<uint4*>(sX + (2 * c2 + 1) * CH + (warp * 32 + r) * 16) = xr[2 * i + 1];
         }
     } else {
 #pragma unroll
@@ -183,6 +195,11 @@ __device__ __forceinline__ void dy_load_raw(const void* __restrict__ dy, int dy_
     if (dy_dt == NRF_DTYPE_F16) {
         const __half* p = reinterpret_cast<const __half*>(dy) + row * ld;
         if (vec_ok) {                                  // n_out in {8, 16}
+            if (n_out > 8 && ld % 16 == 0 && (reinterpret_cast<uintptr_t>(dy) & 31) == 0) {      // one 256-bit load (LDG.E.256)
+                asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=r"(raw[0]), "=r"(raw[1]), "=r"(raw[2]), "=r"(raw[3]), "=r"(raw[4]), "=r"(raw[5]), "=r"(raw[6]), "=r"(raw[7]) : "l"(p));
+                return;
+            }
             const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
             raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w;
             if (n_out > 8) { const uint4 b = __ldg(reinterpret_cast<const uint4*>(p) + 1); raw[4] = b.x; raw[5] = b.y; raw[6] = b.z; raw[7] = b.w; }
@@ -394,9 +411,10 @@ k_mlp_fwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ pa
         // the network's output precision is f16 (tcnn); an f32 `y` holds that f16 value widened, except for TRUNC_EXP
         // whose exp is evaluated in f32 on the f16-rounded pre-activation (tcnn_nerf.py:55-62)
         const bool round_y = y_dt == NRF_DTYPE_F32 && out_act != NRF_ACT_TRUNC_EXP;
+        // (a 256-bit store of the 16 f16 outputs of color1_net was measured 60 % SLOWER for that launch and dropped)
         uint32_t phase = 0;
         uint8_t* hrow = smem + L.H1 + tid * 16;
-        const bool coal = x_vec && x_dt == NRF_DTYPE_F16 && n_in == (uint32_t)IN_PAD;
+        const bool coal = x_vec && x_dt == NRF_DTYPE_F16 && n_in == (uint32_t)IN_PAD && (reinterpret_cast<uintptr_t>(x) & 31) == 0;
         uint4 xr[CPR];
         load_x_tile<CPR>(xr, x, x_dt, (size_t)blockIdx.x * 128, true, B, n_in, x_vec, coal, warp, lane, tid);
         for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -565,9 +583,11 @@ k_mlp_bwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ pa
         const bool dx_vec = vec_ok_for(dx, n_in, n_in);
         const bool dy_vec = vec_ok_for(dy, n_out, ld_dy);
         const float inv_scale = 1.0f / loss_scale;
+        // plain (non-accumulating) f16 dx whose rows are whole 32-byte sectors
+        const bool dx_wide = dx_vec && !dx_accumulate && x_dt == NRF_DTYPE_F16 && (n_in % 16 == 0) && ((reinterpret_cast<uintptr_t>(dx) & 31) == 0);
         uint32_t phase = 0, phase_w = 0;
         bool first = true;
-        const bool coal = x_vec && x_dt == NRF_DTYPE_F16 && n_in == (uint32_t)IN_PAD;
+        const bool coal = x_vec && x_dt == NRF_DTYPE_F16 && n_in == (uint32_t)IN_PAD && (reinterpret_cast<uintptr_t>(x) & 31) == 0;
         uint8_t* const h1row = smem + L.H1 + tid * 16;
         uint8_t* const h2row = smem + L.H2 + tid * 16;
         uint8_t* const dzrow = smem + L.dZ + tid * 16;
@@ -660,7 +680,16 @@ k_mlp_bwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ pa
                     uint32_t v[16];
                     tc05::tmem_ld16(tacc_lane + 16 * g, v);
                     tc05::tmem_ld_wait();
-                    if (row_ok) {
+                    if (row_ok && dx_wide) {
+                        // 16 f16 gradients = one 32-byte sector: a single 256-bit store (STG.E.256, sm_100) per lane instead of
+                        // two half-sector 16-byte stores
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int q = 0; q < 8; q++) pk[q] = tpack(__uint_as_float(v[2 * q]) * inv_scale, __uint_as_float(v[2 * q + 1]) * inv_scale);
+                        __half* dst = reinterpret_cast<__half*>(dx) + row * n_in + 16 * g;
+                        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                                     "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+                    } else if (row_ok) {
 #pragma unroll
                         for (int c = 0; c < 2; c++) {
                             float f[8];
