@@ -91,12 +91,12 @@ __device__ __forceinline__ uint4 load_chunk(const void* __restrict__ base, int d
 // the warp's 32 rows x CPR chunks (piece i * 32 + lane: consecutive lanes read consecutive 16-byte pieces of global
 // memory -- 4 cache lines per request instead of 16 for the row-owner mapping; ncu showed the MLP kernels L1TEX-bound);
 // otherwise every thread reads its own row (f32 inputs, odd widths).
-template <int CPR>
+// WIDE: 32-byte pieces (one sector, LDG.E.256) -- a warp request reads 1 KB of consecutive global memory.  Measured: the
+// backward (4 CTAs/SM) gains from it, the forward (6 CTAs/SM) loses 5 %, so the forward keeps 16-byte pieces.
+template <int CPR, bool WIDE>
 __device__ __forceinline__ void load_x_tile(uint4 (&xr)[CPR], const void* __restrict__ x, int x_dt, size_t tile_row0, bool tile_ok, uint32_t B,
                                             uint32_t n_in, bool x_vec, bool coal, int warp, int lane, int tid) {
-    if (coal) {
-        // 32-byte pieces (one sector, LDG.E.256): piece i * 32 + lane of the warp's 32 rows x CPR/2 pieces -- a warp request
-        // reads 1 KB of consecutive global memory
+    if (coal && WIDE) {
         constexpr int PPR = CPR / 2;
 #pragma unroll
         for (int i = 0; i < PPR; i++) {
@@ -112,21 +112,35 @@ __device__ __forceinline__ void load_x_tile(uint4 (&xr)[CPR], const void* __rest
                 xr[2 * i + 1] = make_uint4(0u, 0u, 0u, 0u);
             }
         }
+    } else if (coal) {
+#pragma unroll
+        for (int i = 0; i < CPR; i++) {
+            const int idx = i * 32 + lane, r = idx / CPR, c = idx - r * CPR;
+            const size_t row = tile_row0 + warp * 32 + r;
+            xr[i] = (tile_ok && row < B) ? __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(x) + row * n_in) + c)
+                                         : make_uint4(0u, 0u, 0u, 0u);
+        }
     } else {
         const size_t row = tile_row0 + tid;
 #pragma unroll
         for (int c = 0; c < CPR; c++) xr[c] = load_chunk(x, x_dt, row, c, n_in, tile_ok && row < B, x_vec);
     }
 }
-template <int CPR>
+template <int CPR, bool WIDE>
 __device__ __forceinline__ void stage_x_tile(const uint4 (&xr)[CPR], uint8_t* sX, uint32_t CH, bool coal, int warp, int lane, int tid) {
-    if (coal) {
+    if (coal && WIDE) {
         constexpr int PPR = CPR / 2;
 #pragma unroll
         for (int i = 0; i < PPR; i++) {
             const int idx = i * 32 + lane, r = idx / PPR, c2 = idx - r * PPR;
             *reinterpret_cast<uint4*>(sX + (2 * c2) * CH + (warp * 32 + r) * 16) = xr[2 * i];
             *reinterpret_cast<uint4*>(sX + (2 * c2 + 1) * CH + (warp * 32 + r) * 16) = xr[2 * i + 1];
+        }
+    } else if (coal) {
+#pragma unroll
+        for (int i = 0; i < CPR; i++) {
+            const int idx = i * 32 + lane, r = idx / CPR, c = idx - r * CPR;
+            *reinterpret_cast<uint4*>(sX + c * CH + (warp * 32 + r) * 16) = xr[i];
         }
     } else {
 #pragma unroll
@@ -350,7 +364,7 @@ __host__ __device__ constexpr TcSmem bwd_smem() {
 
 // ------------------------------------------------------------------------------------------------ forward
 template <int IN_KT, int NH>
-__global__ void __launch_bounds__(TC_THREADS, 5)
+__global__ void __launch_bounds__(TC_THREADS, 6)      // 64 registers: six CTAs really are resident (68 silently made it five)
 k_mlp_fwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ params, uint32_t B, uint32_t n_in, uint32_t n_out,
              int hidden_act, int out_act, void* __restrict__ y, int y_dt, uint32_t ld_y, const int32_t* __restrict__ B_dev) {
     constexpr int IN_PAD = IN_KT * 16;
@@ -416,15 +430,15 @@ k_mlp_fwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ pa
         uint8_t* hrow = smem + L.H1 + tid * 16;
         const bool coal = x_vec && x_dt == NRF_DTYPE_F16 && n_in == (uint32_t)IN_PAD && (reinterpret_cast<uintptr_t>(x) & 31) == 0;
         uint4 xr[CPR];
-        load_x_tile<CPR>(xr, x, x_dt, (size_t)blockIdx.x * 128, true, B, n_in, x_vec, coal, warp, lane, tid);
+        load_x_tile<CPR, false>(xr, x, x_dt, (size_t)blockIdx.x * 128, true, B, n_in, x_vec, coal, warp, lane, tid);
         for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const size_t row = (size_t)tile * 128 + tid;
             const bool row_ok = row < B;
-            stage_x_tile<CPR>(xr, smem + L.X, CH, coal, warp, lane, tid);
+            stage_x_tile<CPR, false>(xr, smem + L.X, CH, coal, warp, lane, tid);
             publish(&bar_ready);
             {   // prefetch the next tile's rows (in flight until the top of the next iteration)
                 const uint32_t nt = tile + gridDim.x;
-                load_x_tile<CPR>(xr, x, x_dt, (size_t)nt * 128, nt < ntiles, B, n_in, x_vec, coal, warp, lane, tid);
+                load_x_tile<CPR, false>(xr, x, x_dt, (size_t)nt * 128, nt < ntiles, B, n_in, x_vec, coal, warp, lane, tid);
             }
 #pragma unroll
             for (int l = 0; l < NH; l++) {
@@ -584,7 +598,8 @@ k_mlp_bwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ pa
         const bool dy_vec = vec_ok_for(dy, n_out, ld_dy);
         const float inv_scale = 1.0f / loss_scale;
         // plain (non-accumulating) f16 dx whose rows are whole 32-byte sectors
-        const bool dx_wide = dx_vec && !dx_accumulate && x_dt == NRF_DTYPE_F16 && (n_in % 16 == 0) && ((reinterpret_cast<uintptr_t>(dx) & 31) == 0);
+        const bool dx_wide_ok = dx_vec && x_dt == NRF_DTYPE_F16 && (n_in % 16 == 0) && ((reinterpret_cast<uintptr_t>(dx) & 31) == 0);
+        const bool dx_wide = dx_wide_ok && !dx_accumulate, dx_wide_acc = dx_wide_ok && dx_accumulate;
         uint32_t phase = 0, phase_w = 0;
         bool first = true;
         const bool coal = x_vec && x_dt == NRF_DTYPE_F16 && n_in == (uint32_t)IN_PAD && (reinterpret_cast<uintptr_t>(x) & 31) == 0;
@@ -601,7 +616,7 @@ k_mlp_bwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ pa
         uint32_t dyraw[16];
         {
             const size_t row0 = (size_t)blockIdx.x * 128 + tid;
-            load_x_tile<CPR>(xr, x, x_dt, (size_t)blockIdx.x * 128, true, B, n_in, x_vec, coal, warp, lane, tid);
+            load_x_tile<CPR, true>(xr, x, x_dt, (size_t)blockIdx.x * 128, true, B, n_in, x_vec, coal, warp, lane, tid);
             dy_load_raw(dy, dy_dt, row0, n_out, ld_dy, row0 < B, dy_vec, dyraw);
         }
         for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -612,7 +627,7 @@ k_mlp_bwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ pa
             PROF_MARK(0);
             if (!first) { tc05::mbar_wait(&bar_wdone, phase_w); phase_w ^= 1; }      // operand tiles are free again
             PROF_MARK(1);      // previous tile's weight-gradient MMAs done
-            stage_x_tile<CPR>(xr, smem + L.X, CH, coal, warp, lane, tid);
+            stage_x_tile<CPR, true>(xr, smem + L.X, CH, coal, warp, lane, tid);
             PROF_MARK(13);     // x rows staged (first use of the prefetched registers: exposes any load latency left)
             if (linear_out) {
                 *reinterpret_cast<uint4*>(dzrow) = make_uint4(dyc[0], dyc[1], dyc[2], dyc[3]);
@@ -625,7 +640,7 @@ k_mlp_bwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ pa
                 const uint32_t nt = tile + gridDim.x;
                 const size_t nrow = (size_t)nt * 128 + tid;
                 const bool nok = nt < ntiles && nrow < B;
-                load_x_tile<CPR>(xr, x, x_dt, (size_t)nt * 128, nt < ntiles, B, n_in, x_vec, coal, warp, lane, tid);
+                load_x_tile<CPR, true>(xr, x, x_dt, (size_t)nt * 128, nt < ntiles, B, n_in, x_vec, coal, warp, lane, tid);
                 dy_load_raw(dy, dy_dt, nrow, n_out, ld_dy, nok, dy_vec, dyraw);
             }
             PROF_MARK(2);      // operands staged, prefetch issued
@@ -680,7 +695,22 @@ k_mlp_bwd_tc(const void* __restrict__ x, int x_dt, const __half* __restrict__ pa
                     uint32_t v[16];
                     tc05::tmem_ld16(tacc_lane + 16 * g, v);
                     tc05::tmem_ld_wait();
-                    if (row_ok && dx_wide) {
+                    if (row_ok && dx_wide_acc) {
+                        // accumulate into an existing f16 dx: the row belongs to this thread alone and the producer of the
+                        // existing values is an earlier kernel on the stream, so a 256-bit load + packed add + 256-bit store
+                        // replaces four 16-byte reductions
+                        __half* dst = reinterpret_cast<__half*>(dx) + row * n_in + 16 * g;
+                        uint32_t old[8];
+                        asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                     : "=r"(old[0]), "=r"(old[1]), "=r"(old[2]), "=r"(old[3]), "=r"(old[4]), "=r"(old[5]), "=r"(old[6]), "=r"(old[7])
+                                     : "l"(dst) : "memory");
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int q = 0; q < 8; q++)
+                            pk[q] = h2bits(__hadd2(bits2h(old[q]), bits2h(tpack(__uint_as_float(v[2 * q]) * inv_scale, __uint_as_float(v[2 * q + 1]) * inv_scale))));
+                        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                                     "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+                    } else if (row_ok && dx_wide) {
                         // 16 f16 gradients = one 32-byte sector: a single 256-bit store (STG.E.256, sm_100) per lane instead of
                         // two half-sector 16-byte stores
                         uint32_t pk[8];
