@@ -808,6 +808,9 @@ int launch_fwd(const void* x, int xdt, const void* params, uint32_t B, uint32_t 
     auto kern = k_mlp_fwd_tc<IN_KT, NH>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
     const uint32_t ntiles = ceil_div_u32(B, 128);
+    // NOTE per_sm must not exceed what is really resident (registers included: see the launch bounds), or the surplus CTAs
+    // run as a tail wave.  (cudaOccupancyMaxActiveBlocksPerMultiprocessor under-reports here -- it ignores the opt-in
+    // shared-memory carve-out -- and halved the grid when it was used as a clamp.)
     const uint32_t per_sm = (uint32_t)max(1, min(min(g_fwd_ctas_per_sm, (int)(220 * 1024 / (L.total + 1024))), 8));
     const uint32_t grid = (uint32_t)min((uint64_t)ntiles, (uint64_t)tc_sm_count() * per_sm);
     kern<<<grid, TC_THREADS, L.total, s>>>(x, xdt, (const __half*)params, B, n_in, n_out, hact, oact, y, ydt, ld_y, B_dev);
