@@ -331,6 +331,15 @@ int nrf_occ_update(float* grid, const float* values, float tmp_scale, float deca
                    float* state, void* scratch, void* stream);
 int nrf_packbits_dev(const float* grid, uint32_t N, const float* density_thresh_dev, uint8_t* bitfield, void* stream);
 
+/* ------------------------------------------------------------------ reconstruction loss head */
+
+/* The tail of Renderer.render_train (white background, renderer.py:229-232) + Trainer.calc_loss (trainers/base.py:251-304) and
+ * their gradients in one launch.  image [N, Cch] f32 = the composited (rgb, class logits), weights_sum [N], target_rgb [N,3],
+ * target_cls [N] i64 (NULL when Cch == 3).  out[3] = {mse + class_lambda * ce, mse, ce}; grad_image [N,Cch] and grad_ws [N] are
+ * d out[0] / d image and d out[0] / d weights_sum.  Deterministic (one block, fixed reduction order). */
+int nrf_recon_loss(const float* image, const float* weights_sum, const float* target_rgb, const int64_t* target_cls, uint32_t N,
+                   uint32_t Cch, float class_lambda, float* out, float* grad_image, float* grad_ws, void* stream);
+
 /* ------------------------------------------------------------------ ray generation (SURVEY 8f NEXT-1) */
 
 /* NerfLib.generate_rays (nerf_lib.py:69-142) + RayBatch.__post_init__ (common.py:139-147) for K rays in one launch.

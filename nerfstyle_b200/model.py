@@ -343,8 +343,9 @@ class Renderer(nn.Module):
         total_step = min(STEP_CTR_SIZE, self.update_iter)
         self.mean_count = int(self.step_counter[:total_step, 0].sum().item() / total_step)
 
-    def render_train(self, rays_o, rays_d, **kwargs):
-        """renderer.py:196-235"""
+    def render_train_raw(self, rays_o, rays_d, **kwargs):
+        """renderer.py:196-228: everything up to the compositing outputs.  Returns (weights_sum [N], depth [N] (relative to
+        the near plane, un-normalised), image [N, 3 + K] (rgb without background, class logits), nears, fars)."""
         if self.update_occ and (self.local_step % self.update_iter == 0):
             self.update_state()
         nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, self.aabb, self.min_near)
@@ -359,8 +360,14 @@ class Renderer(nn.Module):
             self._mean_count if isinstance(self._mean_count, int) else -1,       # unused under force_all_rays=True (:219-222)
             True, 128, True, 0., self.max_steps, False)
         rgbs, sigmas = self.model(xyzs, dirs=dirs, **kwargs)
-        sigmas = sigmas * self.density_scale
+        if self.density_scale != 1.0:             # x * 1.0 == x exactly: skip the 16 MB pass and its backward (renderer.py:225)
+            sigmas = sigmas * self.density_scale
         weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays_info, self.t_thresh, False)
+        return weights_sum, depth, image, nears, fars
+
+    def render_train(self, rays_o, rays_d, **kwargs):
+        """renderer.py:196-235"""
+        weights_sum, depth, image, nears, fars = self.render_train_raw(rays_o, rays_d, **kwargs)
         classes = image[:, 3:]
         image = image[:, :3]
         image = image + (1 - weights_sum).unsqueeze(-1)
@@ -401,7 +408,8 @@ class Renderer(nn.Module):
                 n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, None, self.bound, self.density_bitfield,
                 self.cascade, self.grid_size, nears, fars, 128, False, 0., self.max_steps, False)
             rgbs, sigmas = self.model(xyzs, dirs=dirs, **kwargs)
-            sigmas = sigmas * self.density_scale
+            if self.density_scale != 1.0:         # renderer.py:278
+                sigmas = sigmas * self.density_scale
             raymarching.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, False, weights_sum,
                                        depth, image, self.t_thresh)
             if sync_every <= 1:

@@ -8,15 +8,53 @@ group before the (identical) optimizer step on every rank.
 """
 import torch
 import torch.nn.functional as F
+from torch.autograd import Function
+
+
+class _ReconLoss(Function):
+    """White background (renderer.py:229-232) + MSE + class_lambda * cross-entropy (trainers/base.py:251-304) and their
+    gradients w.r.t. the compositing outputs in ONE launch (csrc/loss.cu) instead of ~25 elementwise / reduction / slicing
+    kernels and their backward twins.  Returns a [3] tensor: (total, mse, ce)."""
+
+    @staticmethod
+    def forward(ctx, weights_sum, image, target_rgb, target_cls, class_lambda):
+        from . import _lib as L
+        N, C = image.shape
+        image, weights_sum = image.float().contiguous(), weights_sum.float().contiguous()
+        target_rgb = target_rgb.float().contiguous()
+        target_cls = target_cls.to(torch.int64).contiguous() if C > 3 else None
+        out = torch.empty(3, dtype=torch.float32, device=image.device)
+        g_img = torch.empty_like(image)
+        g_ws = torch.empty_like(weights_sum)
+        with torch.cuda.device(image.device):
+            L.check(L.lib().nrf_recon_loss(image.data_ptr(), weights_sum.data_ptr(), target_rgb.data_ptr(), L.ptr(target_cls), N, C,
+                                           float(class_lambda), out.data_ptr(), g_img.data_ptr(), g_ws.data_ptr(),
+                                           L.stream_of(image)), 'recon_loss')
+        ctx.save_for_backward(g_ws, g_img)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g_ws, g_img = ctx.saved_tensors
+        s = g[0]                                   # only the total (out[0]) carries the training gradient
+        return g_ws * s, g_img * s, None, None, None
+
+
+def recon_loss(weights_sum, image, target_rgb, target_cls, class_lambda):
+    """(total, mse, ce) as 0-dim tensors; differentiable through `total` w.r.t. weights_sum and image."""
+    out = _ReconLoss.apply(weights_sum, image, target_rgb, target_cls, class_lambda)
+    return out[0], out[1].detach(), out[2].detach()
 
 
 class TrainStep:
     def __init__(self, renderer, lr=0.01, mlp_lr=None, lr_decay=30000, ema_decay=0.95, class_lambda=0.001, enable_amp=True,
-                 fused_adam=True, world_size=1, fused_optimizer=True, rank=None, shard_optimizer=True, pair_tables=True):
+                 fused_adam=True, world_size=1, fused_optimizer=True, rank=None, shard_optimizer=True, pair_tables=True,
+                 fused_loss=True):
         self.renderer = renderer
         self.model = renderer.model
         params = list(self.model.parameters())
         self.params = params
+        self.fused_loss = fused_loss
         self.enable_amp = enable_amp
         self.class_lambda = class_lambda
         self.world_size = world_size
@@ -75,8 +113,12 @@ class TrainStep:
         n_local = rays_o.shape[0]
         n_global = n_global or n_local * self.world_size
         with torch.autocast('cuda', dtype=torch.float16, enabled=self.enable_amp):
-            image, depth, classes = self.renderer.render_train(rays_o, rays_d)
-            loss, mse = self.loss_fn(image, classes, target_rgb, target_cls)
+            if self.fused_loss and rays_o.is_cuda:
+                weights_sum, _, image_raw, _, _ = self.renderer.render_train_raw(rays_o, rays_d)
+                loss, mse, _ = recon_loss(weights_sum, image_raw, target_rgb, target_cls, self.class_lambda)
+            else:
+                image, depth, classes = self.renderer.render_train(rays_o, rays_d)
+                loss, mse = self.loss_fn(image, classes, target_rgb, target_cls)
         if loss_host is not None:
             if self._side is None:
                 self._side = torch.cuda.Stream(device=rays_o.device)

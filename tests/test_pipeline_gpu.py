@@ -378,3 +378,55 @@ def test_update_state_fused_sparse_phase_semantics(cuda_lib, dev):
     thr = min(a.mean_density, a.density_thresh)
     ref_bits = raymarching.packbits(a.density_grid, thr)
     assert int((ref_bits != a.density_bitfield).sum()) <= 2
+
+
+@pytest.mark.parametrize('n_rays,k', [(8192, 8), (1000, 8), (37, 1), (4096, 0)])
+def test_fused_recon_loss_matches_torch_composition(cuda_lib, dev, n_rays, k):
+    """nrf_recon_loss == white background (renderer.py:229-232) + MSE + class_lambda * CrossEntropy (trainers/base.py:251-304)
+    composed from torch ops: loss terms within 1e-6 relative, gradients w.r.t. the compositing outputs within 1e-5 * max."""
+    from nerfstyle_b200.trainer import recon_loss
+    g = torch.Generator(device=dev).manual_seed(n_rays + k)
+    image = (torch.randn(n_rays, 3 + k, device=dev, generator=g) * 2).requires_grad_(True)
+    ws = torch.rand(n_rays, device=dev, generator=g).requires_grad_(True)
+    tgt = torch.rand(n_rays, 3, device=dev, generator=g)
+    cls = torch.randint(0, max(k, 1), (n_rays,), device=dev, generator=g)
+    lam = 0.001
+    total, mse, ce = recon_loss(ws, image, tgt, cls, lam)
+    (total * 1024.0).backward()                                  # an upstream scale, as under GradScaler
+    gi, gw = image.grad.clone(), ws.grad.clone()
+    image.grad = ws.grad = None
+    rgb = image[:, :3] + (1 - ws).unsqueeze(-1)
+    e_mse = torch.mean((rgb - tgt) ** 2)
+    e_ce = torch.nn.functional.cross_entropy(image[:, 3:], cls) if k > 0 else torch.zeros((), device=dev)
+    e_total = e_mse + e_ce * lam
+    (e_total * 1024.0).backward()
+    assert abs(float(mse) - float(e_mse)) <= 1e-6 * abs(float(e_mse))
+    assert abs(float(ce) - float(e_ce)) <= 2e-6 * abs(float(e_ce)) + 1e-12
+    assert abs(float(total) - float(e_total)) <= 1e-6 * abs(float(e_total))
+    assert float((gi - image.grad).abs().max()) <= 1e-5 * float(image.grad.abs().max())
+    assert float((gw - ws.grad).abs().max()) <= 1e-5 * float(ws.grad.abs().max())
+
+
+def test_trainstep_fused_loss_equals_unfused(cuda_lib, dev):
+    """TrainStep(fused_loss=True) and the op-by-op loss run the same trajectory."""
+    from nerfstyle_b200 import model as M, scenes
+    from nerfstyle_b200.trainer import TrainStep
+    intr = dict(scenes.ROOM)
+    pose = scenes.synthetic_poses(2, 0)[0]
+    losses = []
+    for fused in (True, False):
+        torch.manual_seed(0)
+        torch.cuda.manual_seed_all(0)
+        m = M.StyleTCNerf([-2., -2., -2.], [2., 2., 2.], class_dim=8).to(dev)
+        r = M.Renderer(m, 2.0, raymarch_channels=11).to(dev)
+        ts = TrainStep(r, enable_amp=True, fused_loss=fused)
+        gen = torch.Generator().manual_seed(0)
+        ls = []
+        for it in range(4):
+            idx = scenes.frame_indices(intr, 1024, gen).to(dev)
+            o, d = scenes.generate_rays(pose, intr, dev, idx)
+            tgt, seg = scenes.synthetic_target(idx, intr)
+            ls.append(float(ts.step(o, d, tgt, seg)))
+        losses.append(ls)
+    for a, b in zip(*losses):
+        assert abs(a - b) <= 2e-3 * abs(b), losses
