@@ -5,6 +5,10 @@ Sub-modules (each mirrors one reference interface):
   gridencoder   gridencoder/grid.py          (GridEncoder, grid_encode)
   tcnn          tinycudann.Network           (fused 64-wide MLP)
   nnfm          loss.py cosine_dists+amin    (nearest-neighbour feature matching)
+  nerf_lib      nerf_lib.py generate_rays    (camera rays on the device: NerfLib, Intrinsics, Box2D, RayBatch)
+  model         renderer.py / style_nerf.py  (host-side mirror: StyleTCNerf, Renderer incl. the fused occupancy update and
+                                              the device-driven inference loop)
+  trainer/optim trainers/base.py step        (TrainStep, fused loss head, FusedAdamEMA with paired tables)
   dropin        sys.modules aliases so the reference's renderer.py / networks/*.py import these unchanged
 
 All compute goes through libnerfstyle_b200.so (C ABI: include/nerfstyle_b200.h).  No CPU fallback.
