@@ -227,3 +227,26 @@ def test_spherical_harmonics_basis_is_orthonormal():
     Y = field.sh_encode((d + 1) / 2, 4)
     G = (Y * w[:, None]).T @ Y
     assert np.abs(G - np.eye(16)).max() < 1e-12
+
+
+def test_occupancy_oracle_known_answers(oracle):
+    """oracle/occupancy.py (renderer.py:120-194): closed-form checks of the sample points and the masked decay / max update."""
+    from oracle import occupancy as occ
+    H, C, bound = 8, 2, 2.0
+    consts = occ.cascade_constants(C, bound, H)
+    assert consts[0] == (np.float32(1.0 - 1.0 / 8), np.float32(1.0 / 8)) and consts[1] == (np.float32(2.0 - 2.0 / 8), np.float32(2.0 / 8))
+    mid = np.full((C, H ** 3, 3), 0.5, np.float32)                   # noise 0.5 -> no jitter: the scaled cell centre
+    pts = occ.points_full_morton(mid, C, bound, H)
+    # Morton index 0 is cell (0,0,0) -> centre -1; index 7 is cell (1,1,1); the last index is cell (H-1,)*3 -> centre +1
+    assert np.array_equal(pts[0, 0], np.full(3, -consts[0][0], np.float32))
+    assert np.array_equal(pts[1, H ** 3 - 1], np.full(3, consts[1][0], np.float32))
+    c1 = np.float32(2.0) * np.float32(1.0) * (np.float32(1.0) / np.float32(7.0)) - np.float32(1.0)
+    assert np.array_equal(pts[0, 7], np.full(3, c1 * consts[0][0], np.float32))
+    assert np.array_equal(pts[0, 1], np.array([c1 * consts[0][0], -consts[0][0], -consts[0][0]], np.float32))   # x is the lowest Morton bit
+    lo = occ.points_full_morton(np.zeros_like(mid), C, bound, H)
+    assert np.allclose(pts - lo, np.array([c[1] for c in consts], np.float32)[:, None, None])                    # jitter spans +- half a cell
+    grid = np.array([[0.0, 1.0, -1.0, 2.0]], np.float32)
+    tmp = np.array([[0.5, -1.0, 3.0, 1.0]], np.float32)
+    g, mean, bits = occ.grid_update(np.tile(grid, (1, 2)), np.tile(tmp, (1, 2)), 0.95, 10.0)
+    assert np.array_equal(g[0, :4], np.array([0.5, 1.0, -1.0, np.float32(2.0) * np.float32(0.95)], np.float32))
+    assert abs(mean - (0.5 + 1.0 + 0.0 + 1.9) / 4) < 1e-6 and np.asarray(bits).reshape(-1)[0] == 0b10101010

@@ -430,3 +430,35 @@ def test_trainstep_fused_loss_equals_unfused(cuda_lib, dev):
         losses.append(ls)
     for a, b in zip(*losses):
         assert abs(a - b) <= 2e-3 * abs(b), losses
+
+
+def test_occupancy_kernels_against_cpu_oracle(cuda_lib, oracle, dev):
+    """nrf_occ_points_full / nrf_occ_update / nrf_packbits_dev against the numpy restatement of renderer.py:120-194
+    (oracle/occupancy.py): sample points and updated grid bit-exact, mean within 1e-6, bitfield identical away from the
+    threshold.  Small grid (H = 32) so the CPU side takes a fraction of a second."""
+    from oracle import occupancy as occ
+    from nerfstyle_b200 import _lib as L
+    lib = L.lib()
+    H, C, bound = 32, 2, 2.0
+    H3 = H ** 3
+    g = torch.Generator(device=dev).manual_seed(21)
+    noise = torch.rand(C, H3, 3, device=dev, generator=g)
+    sh = torch.tensor([v for pair in occ.cascade_constants(C, bound, H) for v in pair], dtype=torch.float32, device=dev)
+    pts = torch.empty(C, H3, 3, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib.nrf_occ_points_full(pts.data_ptr(), noise.data_ptr(), H, C, sh.data_ptr(), st) == 0
+    e_pts = occ.points_full_morton(noise.cpu().numpy(), C, bound, H)
+    assert np.array_equal(pts.cpu().numpy().view(np.uint32), e_pts.view(np.uint32))
+    # update: a grid with invalid (-1) cells, sigmas with a spread of magnitudes
+    grid = torch.rand(C, H3, device=dev, generator=g) * 4
+    grid[torch.rand(C, H3, device=dev, generator=g) < 0.1] = -1.0
+    sig = torch.rand(C * H3, device=dev, generator=g) ** 4 * 30
+    e_grid, e_mean, e_bits = occ.grid_update(grid.cpu().numpy(), (sig * 1.5).reshape(C, H3).cpu().numpy(), 0.95, 10.0)
+    state = torch.zeros(2, device=dev)
+    scratch = torch.empty(int(lib.nrf_occ_scratch_bytes()), dtype=torch.uint8, device=dev)
+    bits = torch.empty(C * H3 // 8, dtype=torch.uint8, device=dev)
+    assert lib.nrf_occ_update(grid.data_ptr(), sig.data_ptr(), 1.5, 0.95, C * H3, 10.0, state.data_ptr(), scratch.data_ptr(), st) == 0
+    assert lib.nrf_packbits_dev(grid.data_ptr(), C * H3 // 8, state.data_ptr() + 4, bits.data_ptr(), st) == 0
+    assert np.array_equal(grid.cpu().numpy().view(np.uint32), e_grid.view(np.uint32))
+    assert abs(float(state[0]) - e_mean) <= 1e-6 * e_mean and abs(float(state[1]) - min(e_mean, 10.0)) <= 1e-6 * e_mean
+    assert int((bits.cpu().numpy() != np.asarray(e_bits).reshape(-1)).sum()) <= 1
