@@ -138,3 +138,45 @@ def test_reference_modules_import_unchanged_on_dropin():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_fused_optimizer_pairing_rules_on_cpu(cuda_lib):
+    """FusedAdamEMA's host logic without a GPU: which tensors are paired, how the interleaved buffers are laid out, the
+    gradient-sink protocol (grad_pair_buffer / grad_of / zero_grad) and the shard plan."""
+    from nerfstyle_b200.optim import FusedAdamEMA
+    torch.manual_seed(0)
+    T = 1 << 19                                      # 2 T elements >= half_copy_min_numel
+    a, b = torch.nn.Parameter(torch.randn(T, 2)), torch.nn.Parameter(torch.randn(T, 2))
+    w = torch.nn.Parameter(torch.randn(3072))
+    opt = FusedAdamEMA([a, w, b], enable_amp=True)
+    assert opt.pair_idx == (0, 2)
+    assert opt.half_pair.shape == (T, 2, 2) and opt.half_pair.dtype == torch.float16 and opt.half_pair.is_contiguous()
+    assert torch.equal(a._nrf_half_copy, a.detach().half()) and torch.equal(b._nrf_half_copy, b.detach().half())
+    assert a._nrf_half_pair[0] is b._nrf_half_pair[0] and (a._nrf_half_pair[1], b._nrf_half_pair[1]) == (0, 1)
+    assert a._nrf_half_copy.data_ptr() == opt.half_pair.data_ptr() and b._nrf_half_copy.data_ptr() == opt.half_pair.data_ptr() + 4
+    assert w._nrf_half_copy.is_contiguous()           # small tensors keep their own fp16 copy
+    # writing the parameters by other means + refresh keeps the interleaved copy current
+    with torch.no_grad():
+        b.mul_(0.5)
+    opt.refresh_half_copies()
+    assert torch.equal(opt.half_pair[:, 1], b.detach().half())
+    # gradient sink: the buffer is created zeroed, stays across backwards of one step, is cleared after zero_grad()
+    assert opt.grad_of(a) is None
+    gp = opt.grad_pair_buffer()
+    assert gp.shape == (T, 2, 2) and gp.dtype == torch.float32 and float(gp.abs().max()) == 0.0 and opt.grad_pair_valid
+    gp[:, 1] += 1.0
+    assert opt.grad_pair_buffer() is gp and float(gp[:, 1].min()) == 1.0          # accumulation, no re-zeroing
+    assert torch.equal(opt.grad_of(b), gp[:, 1]) and float(opt.grad_of(a).abs().max()) == 0.0
+    opt.zero_grad()
+    assert opt.grad_of(a) is None and not opt.grad_pair_valid
+    assert float(opt.grad_pair_buffer().abs().max()) == 0.0
+    # no pairing without AMP, with pair_tables off, or when the shapes differ / three tables share a shape
+    assert FusedAdamEMA([a, b], enable_amp=False).pair_idx is None
+    assert FusedAdamEMA([a, b], pair_tables=False).pair_idx is None
+    c = torch.nn.Parameter(torch.randn(T + 8, 2))
+    assert FusedAdamEMA([a, c]).pair_idx is None
+    assert FusedAdamEMA([a, b, torch.nn.Parameter(torch.randn(T, 2))]).pair_idx is None
+    # shard plan: both tables of a pair get the same (even) element range; state lives only for the shard
+    sh = FusedAdamEMA([a, w, b], world_size=4, rank=3)
+    assert sh.shard[0] == sh.shard[2] == (3 * (2 * T // 4), 2 * T) and sh.shard[1] is None and sh.pair_idx == (0, 2)
+    assert sh.exp_avg[0].numel() == 2 * T // 4 and sh.exp_avg[1].numel() == 3072
