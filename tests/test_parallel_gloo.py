@@ -125,3 +125,47 @@ def test_sharded_exchange_primitives():
     assert ret['flag'] == 1
     torch.testing.assert_close(ret['small'][0], torch.full((3,), 3.0))
     torch.testing.assert_close(ret['small'][1], torch.full((2, 2), 30.0))
+
+
+def _pair_worker(rank, world, port, ret):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from nerfstyle_b200 import parallel
+    T = 12                                                  # rows per table
+    # interleaved gradient buffer [row][table][2]: table e of rank r holds (r+1) * (100 e + 2 row + feature)
+    row = torch.arange(T, dtype=torch.float32)[:, None, None]
+    e = torch.arange(2, dtype=torch.float32)[None, :, None]
+    f = torch.arange(2, dtype=torch.float32)[None, None, :]
+    gp = (100 * e + 2 * row + f) * (rank + 1)
+    per = 2 * T // world                                    # parameter elements per rank and table (FusedAdamEMA.shard)
+    lo = rank * per
+    shard = torch.empty(gp.numel() // world)
+    parallel.reduce_scatter_sum(gp.reshape(-1).clone(), shard, world, rank)
+    # the shard of the interleaved buffer is exactly this rank's ROW range of both tables: rows [lo/2, (lo+per)/2)
+    want = (gp * 3 / (rank + 1))[lo // 2:(lo + per) // 2]   # sum over ranks 1 + 2 = 3
+    ok = bool(torch.equal(shard.view(-1, 2, 2), want))
+    # "update" the fp16 pair buffer on the own rows only, then gather: elements [2 lo, 2 (lo + per)) of the flat buffer
+    half_pair = torch.zeros(T, 2, 2, dtype=torch.float16)
+    half_pair[lo // 2:(lo + per) // 2] = (shard.view(-1, 2, 2) / 3).half()
+    flat = half_pair.view(-1)
+    parallel.all_gather_shards(flat, flat[2 * lo:2 * (lo + per)], world)
+    if rank == 0:
+        ret['ok'] = ok
+        ret['half_pair'] = half_pair.clone()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_paired_table_exchange_index_arithmetic():
+    """The data-parallel step with paired tables: ONE reduce-scatter of the interleaved gradient buffer hands every rank the
+    same ROW range of both tables, ONE in-place all-gather of the interleaved fp16 buffer rebuilds both (optim.py)."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_pair_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert ret['ok']
+    row = torch.arange(12, dtype=torch.float32)[:, None, None]
+    e = torch.arange(2, dtype=torch.float32)[None, :, None]
+    f = torch.arange(2, dtype=torch.float32)[None, None, :]
+    torch.testing.assert_close(ret['half_pair'].float(), 100 * e + 2 * row + f)
