@@ -121,6 +121,13 @@ int nrf_composite_rays_train_backward(const float* grad_weights_sum, const float
                                       const float* weights_sum, const float* image, uint32_t M, uint32_t N,
                                       uint32_t C, float T_thresh, float* grad_sigmas, float* grad_rgbs,
                                       void* stream);
+/* write_zeros != 0: the gradients need no zero fill by the caller -- every sample slot that belongs to a ray is written
+ * (gradient or zero); padding rows that belong to no ray stay the caller's.  C <= 32. */
+int nrf_composite_rays_train_backward_ex(const float* grad_weights_sum, const float* grad_image, const float* sigmas,
+                                      const float* rgbs, const float* deltas, const int32_t* rays, int is_ndc,
+                                      const float* weights_sum, const float* image, uint32_t M, uint32_t N,
+                                      uint32_t C, float T_thresh, float* grad_sigmas, float* grad_rgbs,
+                                      int write_zeros, void* stream);
 
 /* raymarching.cu:1005-1120.  xyzs/dirs [Mpad,3], deltas [Mpad,4]; rows [n_alive*n_step, Mpad) and the
  * unused slots of exited rays are zero-filled by the kernel when zero_fill != 0 (the reference relies on a

@@ -37,6 +37,8 @@ SIGNATURES = {
     'nrf_composite_rays_train_forward': (_i32, [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _f32, _i32, _vp, _vp, _vp, _vp]),
     'nrf_composite_rays_train_backward': (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _u32, _u32, _u32, _f32,
                                                  _vp, _vp, _vp]),
+    'nrf_composite_rays_train_backward_ex': (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _u32, _u32, _u32, _f32,
+                                                    _vp, _vp, _i32, _vp]),
     'nrf_march_rays': (_i32, [_u32, _u32, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _u32, _i32, _u32, _u32, _vp, _vp, _vp,
                               _vp, _vp, _vp, _vp, _u32, _i32, _vp]),
     'nrf_composite_rays': (_i32, [_u32, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _u32, _i32, _vp, _vp, _vp, _vp]),
@@ -106,7 +108,7 @@ _lib = None
 KERNELS_PER_CALL = {
     'nrf_near_far_from_aabb': 1, 'nrf_sph_from_ray': 1, 'nrf_morton3D': 1, 'nrf_morton3D_invert': 1, 'nrf_packbits': 1,
     'nrf_march_rays_train_count': 4, 'nrf_march_rays_train_write': 1, 'nrf_march_rays_train': 4,
-    'nrf_composite_rays_train_forward': 1, 'nrf_composite_rays_train_backward': 1, 'nrf_march_rays': 1,
+    'nrf_composite_rays_train_forward': 1, 'nrf_composite_rays_train_backward': 1, 'nrf_composite_rays_train_backward_ex': 1, 'nrf_march_rays': 1,
     'nrf_composite_rays': 1, 'nrf_compact_alive': 3, 'nrf_grid_encode_forward': 1, 'nrf_grid_encode_backward': 1, 'nrf_grid_encode_forward_dual': 1,
     'nrf_grid_encode_backward_dual': 1, 'nrf_grid_encode_forward_pair': 1, 'nrf_grid_encode_backward_pair': 1,
     'nrf_grid_initialize': 1, 'nrf_mlp_forward': 1, 'nrf_mlp_backward': 1, 'nrf_sh_encode_forward': 1, 'nrf_march_rays_dev': 1,

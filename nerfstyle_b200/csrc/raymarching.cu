@@ -718,12 +718,24 @@ __global__ void __launch_bounds__(COMP_WARPS * 32)
 k_composite_train_bwd(const float* __restrict__ grad_ws, const float* __restrict__ grad_image, const float* __restrict__ sigmas,
                       const float* __restrict__ rgbs, const float* __restrict__ deltas, const int32_t* __restrict__ rays, bool is_ndc,
                       const float* __restrict__ weights_sum, const float* __restrict__ image, uint32_t M, uint32_t N, uint32_t C,
-                      float T_thresh, float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs) {
+                      float T_thresh, float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs, bool write_zeros) {
     const uint32_t n = blockIdx.x * COMP_WARPS + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (n >= N) return;
     const uint32_t index = (uint32_t)rays[3 * (size_t)n], offset = (uint32_t)rays[3 * (size_t)n + 1], num_steps = (uint32_t)rays[3 * (size_t)n + 2];
-    if (num_steps == 0 || offset + num_steps >= M) return;
+    // write_zeros: the caller did NOT zero-fill the gradients (the reference does, raymarching.py:339-340); every sample of this
+    // ray that receives no gradient -- the terminating one, those behind it, a dropped ray's -- is written as zero here
+    auto zero_rows = [&](uint32_t first, uint32_t last) {     // samples [first, last) of this ray, clipped to the buffer
+        for (uint32_t i = first + lane; i < last && offset + i < M; i += 32) {
+            grad_sigmas[offset + i] = 0.0f;
+            float* gr = grad_rgbs + (size_t)(offset + i) * C;
+            for (uint32_t c = 0; c < C; c++) gr[c] = 0.0f;
+        }
+    };
+    if (num_steps == 0 || offset + num_steps >= M) {
+        if (write_zeros && num_steps != 0) zero_rows(0, num_steps);
+        return;
+    }
     float g[CMAX];
     float G_total = 0.0f;     // sum_c g_c * image_c
 #pragma unroll
@@ -765,8 +777,16 @@ k_composite_train_bwd(const float* __restrict__ grad_ws, const float* __restrict
 #pragma unroll
             for (int c = 0; c < CMAX; c++) if (c < (int)C) gr[c] = g[c] * w;
             grad_sigmas[offset + i] = d0 * (__fmaf_rn(T_after, gdot, -(G_total - pre)) + ws_term);
+        } else if (write_zeros && valid) {
+            float* gr = grad_rgbs + (size_t)(offset + i) * C;
+#pragma unroll
+            for (int c = 0; c < CMAX; c++) if (c < (int)C) gr[c] = 0.0f;
+            grad_sigmas[offset + i] = 0.0f;
         }
-        if (term) break;
+        if (term) {
+            if (write_zeros) zero_rows(base + 32, num_steps);
+            break;
+        }
         T_run = __shfl_sync(NRF_FULL_MASK, T_after, 31);
         pre_run = __shfl_sync(NRF_FULL_MASK, pre, 31);
     }
@@ -805,19 +825,39 @@ __global__ void k_composite_train_bwd_serial(const float* __restrict__ grad_ws, 
     }
 }
 
+NRF_EXPORT int nrf_composite_rays_train_backward_ex(const float* grad_weights_sum, const float* grad_image, const float* sigmas,
+                                                    const float* rgbs, const float* deltas, const int32_t* rays, int is_ndc,
+                                                    const float* weights_sum, const float* image, uint32_t M, uint32_t N,
+                                                    uint32_t C, float T_thresh, float* grad_sigmas, float* grad_rgbs,
+                                                    int write_zeros, void* stream);
+
 NRF_EXPORT int nrf_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image, const float* sigmas,
                                                  const float* rgbs, const float* deltas, const int32_t* rays, int is_ndc,
                                                  const float* weights_sum, const float* image, uint32_t M, uint32_t N,
                                                  uint32_t C, float T_thresh, float* grad_sigmas, float* grad_rgbs,
                                                  void* stream) {
+    return nrf_composite_rays_train_backward_ex(grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays, is_ndc, weights_sum, image,
+                                                M, N, C, T_thresh, grad_sigmas, grad_rgbs, 0, stream);
+}
+
+// write_zeros != 0: grad_sigmas / grad_rgbs need not be zero-filled by the caller -- every sample slot that belongs to a ray
+// is written (gradient or zero); slots that belong to NO ray (padding rows) remain the caller's business.  The warp-per-ray
+// kernels only (C <= 32).
+NRF_EXPORT int nrf_composite_rays_train_backward_ex(const float* grad_weights_sum, const float* grad_image, const float* sigmas,
+                                                    const float* rgbs, const float* deltas, const int32_t* rays, int is_ndc,
+                                                    const float* weights_sum, const float* image, uint32_t M, uint32_t N,
+                                                    uint32_t C, float T_thresh, float* grad_sigmas, float* grad_rgbs,
+                                                    int write_zeros, void* stream) {
     if (N == 0) return NRF_OK;
+    if (write_zeros && C > 32) return NRF_E_UNSUPPORTED;
+    const bool wz = write_zeros != 0;
     if (!grad_weights_sum || !grad_image || !sigmas || !rgbs || !deltas || !rays || !weights_sum || !image || !grad_sigmas || !grad_rgbs)
         return NRF_E_INVALID;
     if ((((uintptr_t)deltas) & 15) != 0) return NRF_E_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t nb = ceil_div_u32(N, COMP_WARPS);
     const bool ndc = is_ndc != 0;
-#define LAUNCH_BWD(CM) k_composite_train_bwd<CM><<<nb, COMP_WARPS * 32, 0, s>>>(grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays, ndc, weights_sum, image, M, N, C, T_thresh, grad_sigmas, grad_rgbs)
+#define LAUNCH_BWD(CM) k_composite_train_bwd<CM><<<nb, COMP_WARPS * 32, 0, s>>>(grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays, ndc, weights_sum, image, M, N, C, T_thresh, grad_sigmas, grad_rgbs, wz)
     if (C <= 4) LAUNCH_BWD(4);
     else if (C <= 8) LAUNCH_BWD(8);
     else if (C <= 16) LAUNCH_BWD(16);

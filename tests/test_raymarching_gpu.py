@@ -315,3 +315,34 @@ def test_plain_c_host_of_the_abi(cuda_lib, dev):
                                '-Wl,-rpath,' + os.path.join(root, 'nerfstyle_b200'), '-lm'])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and 'C HOST OK' in out.stdout, out.stdout + out.stderr
+
+
+def test_composite_backward_without_zero_fill_equals_reference_path(cuda_lib, dev):
+    """Rays produced by this package's march_rays_train partition the sample rows exactly, so composite_rays_train's backward
+    skips the reference's two zero fills (raymarching.py:339-340) and lets the kernel write the zeros of terminated / dropped
+    samples itself.  Same gradients, bit for bit, with early termination active and the allocator's free blocks poisoned."""
+    from nerfstyle_b200 import raymarching
+    o, d = _rays(3000, 4, dev)
+    bits, _ = _bitfield('analytic', dev)
+    aabb = torch.tensor([-2., -2, -2, 2, 2, 2], device=dev)
+    nears, fars = raymarching.near_far_from_aabb(o, d, aabb, 0.2)
+    counter = torch.zeros(2, dtype=torch.int32, device=dev)
+    xyzs, dirs, deltas, rays = raymarching.march_rays_train(o, d, None, 2.0, bits, 2, 128, nears, fars, counter, -1, False, 128, True,
+                                                            0., 1024, False)
+    assert getattr(rays, '_nrf_dense_rows', None) == int(counter[0]) and xyzs.shape[0] > int(counter[0])
+    M = xyzs.shape[0]
+    g = torch.Generator(device=dev).manual_seed(9)
+    sig0 = torch.rand(M, device=dev, generator=g) * 40          # dense medium: most rays terminate early
+    rgb0 = torch.rand(M, 11, device=dev, generator=g)
+    gw, gi = torch.randn(3000, device=dev, generator=g), torch.randn(3000, 11, device=dev, generator=g)
+    res = []
+    for dense in (True, False):
+        r = rays if dense else rays.clone()                      # the clone carries no tag -> zero-filled reference path
+        sig, rgb = sig0.clone().requires_grad_(True), rgb0.clone().requires_grad_(True)
+        ws, depth, image = raymarching.composite_rays_train(sig, rgb, deltas, r, 1e-4, False)
+        poison = torch.full((M * 12 + 4096,), float('nan'), device=dev)
+        del poison                                               # freed NaN blocks are what torch.empty will hand back
+        torch.autograd.backward([ws, image], [gw, gi])
+        res.append((sig.grad.clone(), rgb.grad.clone()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    assert bool(torch.isfinite(res[0][1]).all()) and float((res[0][0] == 0).float().mean()) > 0.3    # many terminated samples
