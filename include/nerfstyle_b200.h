@@ -343,9 +343,11 @@ int nrf_packbits_dev(const float* grid, uint32_t N, const float* density_thresh_
 /* The tail of Renderer.render_train (white background, renderer.py:229-232) + Trainer.calc_loss (trainers/base.py:251-304) and
  * their gradients in one launch.  image [N, Cch] f32 = the composited (rgb, class logits), weights_sum [N], target_rgb [N,3],
  * target_cls [N] i64 (NULL when Cch == 3).  out[3] = {mse + class_lambda * ce, mse, ce}; grad_image [N,Cch] and grad_ws [N] are
- * d out[0] / d image and d out[0] / d weights_sum.  Deterministic (one block, fixed reduction order). */
+ * d out[0] / d image and d out[0] / d weights_sum.  Deterministic (fixed reduction order).  scratch:
+ * nrf_recon_loss_scratch_bytes(N) bytes, 8-byte aligned, zero before its first use (each call leaves it zeroed again). */
+uint64_t nrf_recon_loss_scratch_bytes(uint32_t N);
 int nrf_recon_loss(const float* image, const float* weights_sum, const float* target_rgb, const int64_t* target_cls, uint32_t N,
-                   uint32_t Cch, float class_lambda, float* out, float* grad_image, float* grad_ws, void* stream);
+                   uint32_t Cch, float class_lambda, float* out, float* grad_image, float* grad_ws, void* scratch, void* stream);
 
 /* ------------------------------------------------------------------ ray generation (SURVEY 8f NEXT-1) */
 

@@ -84,7 +84,8 @@ SIGNATURES = {
     'nrf_occ_scratch_bytes': (_u64, []),
     'nrf_occ_update': (_i32, [_vp, _vp, _f32, _f32, _u64, _f32, _vp, _vp, _vp]),
     'nrf_packbits_dev': (_i32, [_vp, _u32, _vp, _vp, _vp]),
-    'nrf_recon_loss': (_i32, [_vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp, _vp]),
+    'nrf_recon_loss_scratch_bytes': (_u64, [_u32]),
+    'nrf_recon_loss': (_i32, [_vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp, _vp, _vp]),
     'nrf_generate_rays': (_i32, [_vp, _f32, _f32, _f32, _f32, _u32, _u32, _u32, _u32, _vp, _i32, _vp, _u32, _u32, _vp, _vp,
                                  _vp, _vp]),
 }

@@ -16,6 +16,8 @@ class _ReconLoss(Function):
     gradients w.r.t. the compositing outputs in ONE launch (csrc/loss.cu) instead of ~25 elementwise / reduction / slicing
     kernels and their backward twins.  Returns a [3] tensor: (total, mse, ce)."""
 
+    _scratch = {}
+
     @staticmethod
     def forward(ctx, weights_sum, image, target_rgb, target_cls, class_lambda):
         from . import _lib as L
@@ -26,10 +28,15 @@ class _ReconLoss(Function):
         out = torch.empty(3, dtype=torch.float32, device=image.device)
         g_img = torch.empty_like(image)
         g_ws = torch.empty_like(weights_sum)
+        lib = L.lib()
+        key = (image.device, int(lib.nrf_recon_loss_scratch_bytes(N)))
+        scratch = _ReconLoss._scratch.get(key)
+        if scratch is None:          # zero once: every call leaves the arrival counter at zero again
+            scratch = _ReconLoss._scratch[key] = torch.zeros(key[1] // 8 + 1, dtype=torch.float64, device=image.device)
         with torch.cuda.device(image.device):
-            L.check(L.lib().nrf_recon_loss(image.data_ptr(), weights_sum.data_ptr(), target_rgb.data_ptr(), L.ptr(target_cls), N, C,
-                                           float(class_lambda), out.data_ptr(), g_img.data_ptr(), g_ws.data_ptr(),
-                                           L.stream_of(image)), 'recon_loss')
+            L.check(lib.nrf_recon_loss(image.data_ptr(), weights_sum.data_ptr(), target_rgb.data_ptr(), L.ptr(target_cls), N, C,
+                                       float(class_lambda), out.data_ptr(), g_img.data_ptr(), g_ws.data_ptr(),
+                                       scratch.data_ptr(), L.stream_of(image)), 'recon_loss')
         ctx.save_for_backward(g_ws, g_img)
         return out
 
