@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tools'))
 import microbench as mb  # noqa: E402
-from nerfstyle_b200 import _lib, model as M  # noqa: E402
+from nerfstyle_b200 import model as M  # noqa: E402
 
 dev, lib = mb.dev, mb.lib
 xyzs, dirs, deltas, rays = mb.bench_march()
