@@ -491,7 +491,7 @@ def _cpu_step_fn(n_rays):
         loss.backward()
         opt.step()
         state['it'] += 1
-        return float(loss), int(out['counter'][0])
+        return float(loss.detach()), int(out['counter'][0])
     return step
 
 
