@@ -60,3 +60,93 @@ def semantic_nnfm_loss(image_feat, style_feat, preds_small=None, clusters=None, 
     sim = (a_hat * b_hat[jj]).sum(dim=1)
     dist = torch.where(valid, 1.0 - sim, torch.full_like(sim, float('inf')))
     return dist.mean()
+
+
+def labels_downscale(labels, new_dim):
+    """loss.py:23-28: the class map at the feature-map resolution (rows / columns linspace(0, H-1, NH) truncated)."""
+    H, W = labels.shape
+    NH, NW = new_dim
+    r_indices = torch.linspace(0, H - 1, NH).long().to(labels.device)
+    c_indices = torch.linspace(0, W - 1, NW).long().to(labels.device)
+    return labels[r_indices[:, None], c_indices]
+
+
+class NNFMStyleLoss(torch.nn.Module):
+    """loss.py:93-112 on the fused kernel: mean over image positions of the nearest style feature's cosine distance."""
+
+    def __init__(self, keys):
+        super().__init__()
+        self.keys = keys
+
+    def forward(self, feats1, feats2):
+        loss = 0
+        for k in self.keys:
+            loss = loss + semantic_nnfm_loss(feats1[k].squeeze(0), feats2[k].squeeze(0))
+        return loss
+
+
+class SemanticStyleLoss(torch.nn.Module):
+    """loss.py:115-214 with the same constructor / init_feats / forward interface; the N1 x N2 distance matrix, its
+    per-class `inf` masking loop and the row minimum are one tensor-core kernel (nn_match).  `clusters` may be given as
+    a tensor instead of a `.npz` path."""
+
+    def __init__(self, keys, clusters_path=None, matching=None, clusters=None):
+        super().__init__()
+        self.keys = keys
+        self.ready = False
+        self.clusters = None
+        self.matching = None
+        self.use_matching = False
+        if clusters_path is not None or clusters is not None:
+            import numpy as np
+            self.use_matching = True
+            seg = np.load(str(clusters_path))['seg_map'] if clusters is None else np.asarray(torch.as_tensor(clusters).cpu())
+            ids = np.unique(seg)
+            if ids[0] < 0:
+                ids = ids[1:]
+            self.n_clusters = len(ids) if matching is None else max(len(ids), int(max(matching)) + 1)
+            self.clusters = torch.as_tensor(seg)
+            self.matching = matching
+
+    @torch.no_grad()
+    def init_feats(self, all_style_feats, num_classes):
+        style_feats = all_style_feats[self.keys[0]].squeeze(0)
+        self.style_feats = style_feats
+        if self.use_matching:
+            import torch.nn.functional as F
+            self.clusters = F.interpolate(self.clusters.to(style_feats.device)[None, None].float(), style_feats.shape[1:])
+            self.clusters = self.clusters[0, 0].to(torch.long)
+            self.num_classes = num_classes
+        self.ready = True
+
+    def update_matching(self, image_feats, preds):
+        """loss.py:172-185 (host-side Hungarian assignment on K x K means; not a hot path)."""
+        import numpy as np
+        from scipy.optimize import linear_sum_assignment
+
+        def centroid(mask):
+            H, W = mask.shape
+            N = torch.sum(mask)
+            r = torch.sum(torch.sum(mask, dim=1) * torch.arange(H, device=mask.device)) / N / H
+            c = torch.sum(torch.sum(mask, dim=0) * torch.arange(W, device=mask.device)) / N / W
+            return torch.stack((r, c))
+        preds_small = labels_downscale(preds, image_feats.shape[-2:])
+        im_mean = torch.stack([torch.mean(image_feats[:, preds_small == i], dim=1) for i in range(self.num_classes)])
+        im_cent = torch.stack([centroid(preds == i) for i in range(self.num_classes)])
+        st_mean = torch.stack([torch.mean(self.style_feats[:, self.clusters == i], dim=1) for i in range(self.n_clusters)])
+        st_cent = torch.stack([centroid(self.clusters == i) for i in range(self.n_clusters)])
+        feat_d = 1.0 - _normalize_rows(im_mean.float()) @ _normalize_rows(st_mean.float()).T
+        cost = feat_d + torch.linalg.norm(im_cent[:, None] - st_cent[None], dim=-1)
+        self.matching = linear_sum_assignment(np.nan_to_num(cost.detach().cpu().numpy()))[1]
+
+    def forward(self, feats1, _, preds, iter=0):
+        assert self.ready
+        image_feat = feats1[self.keys[0]].squeeze(0)
+        if not self.use_matching:
+            return semantic_nnfm_loss(image_feat, self.style_feats)
+        if self.matching is None:
+            self.update_matching(image_feat.detach(), preds)
+        preds_small = labels_downscale(preds, image_feat.shape[-2:])
+        # classes outside [0, num_classes) have no mask entry in the reference: label them -1 (= unmasked in the kernel)
+        ps = torch.where((preds_small >= 0) & (preds_small < self.num_classes), preds_small, torch.full_like(preds_small, -1))
+        return semantic_nnfm_loss(image_feat, self.style_feats, ps, self.clusters, [int(m) for m in self.matching])
