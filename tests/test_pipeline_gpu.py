@@ -50,6 +50,7 @@ def test_train_step_matches_oracle(cuda_lib, oracle, dev, amp, fused_heads):
     # floats
     img, eimg = image.detach().float().cpu().numpy(), out['rgb'].detach().numpy()
     mse = float(np.mean((img - eimg) ** 2))
+    print('MEASURED pipeline image', amp, fused_heads, np.abs(img - eimg).max(), 'classes', np.abs(classes.detach().float().cpu().numpy() - out['classes'].detach().numpy()).max(), 'loss rel', abs(float(loss) - float(eloss)) / abs(float(eloss)))
     assert np.abs(img - eimg).max() < (2e-3 if amp else 5e-4), np.abs(img - eimg).max()
     psnr_delta = abs(10 * math.log10(max(np.mean((img - target.numpy()) ** 2), 1e-12)) -
                      10 * math.log10(max(np.mean((eimg - target.numpy()) ** 2), 1e-12)))
@@ -63,6 +64,7 @@ def test_train_step_matches_oracle(cuda_lib, oracle, dev, amp, fused_heads):
         denom = np.abs(eg).max()
         assert denom > 0, name
         tol = 2e-2
+        print('MEASURED pipeline', amp, fused_heads, name, np.abs(gp - eg).max() / denom)
         assert np.abs(gp - eg).max() <= tol * denom, (name, np.abs(gp - eg).max() / denom)
 
 
