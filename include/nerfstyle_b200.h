@@ -238,6 +238,17 @@ int nrf_mlp_backward_ex(const void* x, int x_dtype, const void* params_f16, cons
                         uint32_t width, int hidden_act, int out_act, float loss_scale, void* dx, int dx_dtype,
                         int dx_accumulate, float* dparams, void* stream);
 
+/* fp32 PARITY MODE of the same network (SURVEY.md 8c "fp32 (parity mode)"): fp32 weights (same tcnn layout), fp32
+ * activations and fp32 FMA accumulation, nothing rounded to f16 and therefore no loss_scale.  x is f32 or f16 (dx follows
+ * it), y / dy are f32; ld_y / ld_dy / dx_accumulate / NRF_ACT_TRUNC_EXP as in the _ex forms.  Not a performance path: it
+ * exists so that gradients of the whole path can be checked against an fp32 CPU evaluation at rel 1e-4. */
+int nrf_mlp_forward_f32(const void* x, int x_dtype, const float* params_f32, uint32_t B, uint32_t n_in, uint32_t n_out,
+                        uint32_t n_hidden, uint32_t width, int hidden_act, int out_act, float* y, uint32_t ld_y,
+                        void* stream);
+int nrf_mlp_backward_f32(const void* x, int x_dtype, const float* params_f32, const float* dy, uint32_t ld_dy, uint32_t B,
+                         uint32_t n_in, uint32_t n_out, uint32_t n_hidden, uint32_t width, int hidden_act, int out_act,
+                         void* dx, int dx_accumulate, float* dparams, void* stream);
+
 /* ------------------------------------------------------------------ device-driven inference loop (SURVEY 8f NEXT-2) */
 
 /* The inference loop of renderer.py:237-293 with its per-iteration host logic moved to the device.  ctl = device int32[8]

@@ -20,7 +20,7 @@ NRF_EXPORT const char* nrf_error_string(int code) {
     }
 }
 NRF_EXPORT int nrf_last_cuda_error(void) { return g_nrf_last_cuda_error; }
-NRF_EXPORT int nrf_version(void) { return 3; }   // 3: paired tables, ray generation, occupancy update, loss head, _ex forms
+NRF_EXPORT int nrf_version(void) { return 4; }   // 4: fp32 parity-mode MLP (nrf_mlp_*_f32); 3: paired tables, ray generation, occupancy update, loss head, _ex forms
 NRF_EXPORT int nrf_device_info(int* sm_count, int* cc_major, int* cc_minor, int* l2_bytes) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);

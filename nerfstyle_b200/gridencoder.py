@@ -11,8 +11,17 @@ from torch.autograd import Function
 from torch.amp import custom_bwd, custom_fwd
 
 from . import _lib as L
+from . import optim as _optim
 
 _gridtype_to_id = {'hash': 0, 'tiled': 1}
+
+
+def _require_complete_master(embeddings):
+    """An fp32 read of a table whose optimizer shards it across ranks would see stale rows outside this rank's shard."""
+    opt = _optim.optimizer_of(embeddings)
+    if opt is not None and not opt.master_complete:
+        raise RuntimeError('nerfstyle_b200.gridencoder: fp32 read of a hash table whose fp32 master copy is sharded across ranks '
+                           '(only the fp16 copy is kept whole); call optimizer.gather_master() first or run under autocast')
 
 
 class _grid_encode(Function):
@@ -37,8 +46,10 @@ class _grid_encode(Function):
         H = int(base_resolution)
         # grid.py:42-43: half-precision tables under autocast when C is even
         if torch.is_autocast_enabled('cuda') and C % 2 == 0:
-            shadow = getattr(embeddings, '_nrf_half_copy', None)      # kept current by nerfstyle_b200.optim.FusedAdamEMA
+            shadow = _optim.current_half_copy(embeddings)            # kept current by nerfstyle_b200.optim.FusedAdamEMA
             embeddings = shadow if shadow is not None else embeddings.to(torch.half)
+        else:
+            _require_complete_master(embeddings)
         embeddings = embeddings.contiguous()
         offsets = offsets.contiguous()
         dt = L.dtype_code(embeddings.dtype)
@@ -114,11 +125,11 @@ class _grid_encode_dual(Function):
         # interleaved fp16 copies kept by the fused optimizer (optim.FusedAdamEMA, pair_tables): one gather serves both tables
         pair = None
         if torch.is_autocast_enabled('cuda'):
-            pa, pb = getattr(emb0, '_nrf_half_pair', None), getattr(emb1, '_nrf_half_pair', None)
+            pa, pb = _optim.current_half_pair(emb0), _optim.current_half_pair(emb1)
             if pa is not None and pb is not None and pa[0] is pb[0] and (pa[1], pb[1]) == (0, 1):
                 pair = pa[0]
         ctx.sink = None
-        sa, sb = getattr(emb0, '_nrf_grad_sink', None), getattr(emb1, '_nrf_grad_sink', None)
+        sa, sb = _optim.live_grad_sink(emb0), _optim.live_grad_sink(emb1)
         if pair is not None and sa is not None and sb is not None and sa[0] is sb[0] and (sa[1], sb[1]) == (0, 1):
             ctx.sink = sa[0]
         L.Stats.units = B
@@ -137,8 +148,10 @@ class _grid_encode_dual(Function):
         embs = []
         for e in (emb0, emb1):
             if torch.is_autocast_enabled('cuda'):
-                shadow = getattr(e, '_nrf_half_copy', None)
+                shadow = _optim.current_half_copy(e)
                 e = shadow if shadow is not None else e.to(torch.half)
+            else:
+                _require_complete_master(e)
             embs.append(e.contiguous())
         if embs[0].dtype != embs[1].dtype:
             raise RuntimeError('grid_encode_dual: tables must share a dtype')

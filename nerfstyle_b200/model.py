@@ -23,6 +23,7 @@ from torch.amp import custom_bwd, custom_fwd
 from . import raymarching
 from . import tcnn
 from .gridencoder import GridEncoder, grid_encode_dual, same_geometry
+from .optim import current_half_copy
 
 STEP_CTR_SIZE = 16
 
@@ -71,8 +72,9 @@ class StyleTCNerf(nn.Module):
         # MLP kernels (tcnn.density_head / tcnn.color_heads); False runs the reference's exact op sequence
         self.fused_heads = fused_heads
         self._dual = None
-        self.register_buffer('bbox_min', torch.as_tensor(bbox_min, dtype=torch.float32))
-        self.register_buffer('bbox_size', torch.as_tensor(bbox_max, dtype=torch.float32) - self.bbox_min)
+        # not persistent: the reference's bounding box is a plain BBox attribute, so its state_dict has no such keys
+        self.register_buffer('bbox_min', torch.as_tensor(bbox_min, dtype=torch.float32), persistent=False)
+        self.register_buffer('bbox_size', torch.as_tensor(bbox_max, dtype=torch.float32) - self.bbox_min, persistent=False)
         self.class_dim = class_dim
         self.use_dir = False
         max_bound = float(torch.max(self.bbox_size).item())
@@ -87,6 +89,18 @@ class StyleTCNerf(nn.Module):
     @property
     def device(self):
         return self.bbox_min.device
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._dual = None                  # .to() / .cuda() moved the buffers: the cached kernel-side transform is rebuilt
+        return out
+
+    def state_dict(self, *args, **kwargs):
+        """A sharded fused optimizer keeps the fp32 master tables current only inside each rank's shard: gather them first
+        (a collective when world_size > 1 -- every rank must call state_dict())."""
+        from .optim import sync_for_checkpoint
+        sync_for_checkpoint(self)
+        return super().state_dict(*args, **kwargs)
 
     def _forward(self, pts, dirs=None):
         if self.fused_heads and pts.is_cuda and dirs is not None:
@@ -430,12 +444,12 @@ class Renderer(nn.Module):
     def _graph_state(self, N):
         """Static buffers + the captured two-iteration CUDA graph for frames of N rays (built on first use)."""
         st = getattr(self, '_gs', None)
-        if st is not None and st['N'] == N and st['dev'] == self.device:
+        if st is not None and st['N'] == N and st['dev'] == self.device and st['xform_ptr'] == self.model._xform.data_ptr():
             return st
         dev, Cch = self.device, self.raymarch_channels
         cap = (N + 127) // 128 * 128                       # rows per iteration never exceed N (n_alive * n_step <= N)
         f32, i32 = torch.float32, torch.int32
-        st = {'N': N, 'dev': dev, 'cap': cap, 'graph': None,
+        st = {'N': N, 'dev': dev, 'cap': cap, 'graph': None, 'xform_ptr': self.model._xform.data_ptr(),
               'rays_o': torch.empty(N, 3, dtype=f32, device=dev), 'rays_d': torch.empty(N, 3, dtype=f32, device=dev),
               'nears': torch.empty(N, dtype=f32, device=dev), 'fars': torch.empty(N, dtype=f32, device=dev),
               'rays_t': torch.empty(N, 1, dtype=f32, device=dev),
@@ -520,7 +534,8 @@ class Renderer(nn.Module):
         st['alive'][0].copy_(torch.arange(N, dtype=torch.int32, device=self.device))
         st['ctl'].copy_(torch.tensor([N, 1, N, 0, N, self.max_steps, 0, 0], dtype=torch.int32))
         for i, e in enumerate((m.x_density_embedder, m.x_color_embedder)):       # fp16 tables / weights for this frame
-            st['pair'][:, i].copy_(getattr(e.embeddings, '_nrf_half_copy', e.embeddings.detach()))
+            shadow = current_half_copy(e.embeddings)
+            st['pair'][:, i].copy_(shadow if shadow is not None else e.embeddings.detach())
         for n in st['w']:
             st['w'][n].copy_(getattr(m, n).params.detach())
         if st['graph'] is None:

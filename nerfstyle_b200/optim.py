@@ -3,25 +3,92 @@ tensor on the device (csrc/optim.cu), mirroring trainers/base.py:216-229,420-426
 
 It also maintains the fp16 copy of each hash table, which `GridEncoder` picks up under autocast instead of re-casting
 the 48 MB fp32 table on every forward (gridencoder/grid.py:42-43 does `embeddings.to(torch.half)` per call).
+
+Ownership protocol.  The optimizer hangs four attributes on each parameter it owns -- `_nrf_optimizer` (weak reference
+to the owner), `_nrf_half_copy` (+ `_nrf_half_version`: the parameter's version counter when the copy was last made),
+`_nrf_half_pair`, `_nrf_grad_sink` -- and removes them again in `detach()`; constructing a new FusedAdamEMA over a
+parameter detaches the previous owner.  Readers go through `current_half_copy()`, which re-casts a copy whose
+parameter has been written since (load_state_dict, `param.copy_`, anything that bumps the version counter); writes
+through `param.data` are invisible to PyTorch itself and need an explicit `refresh_half_copies()` -- `ema_scope()`
+does that for the one such write this module performs.
 """
+import contextlib
 import struct
+import weakref
 
 import torch
 
 from . import _lib as L
+
+_ATTRS = ('_nrf_optimizer', '_nrf_half_copy', '_nrf_half_version', '_nrf_half_pair', '_nrf_grad_sink')
+
+
+def optimizer_of(p):
+    """The live FusedAdamEMA that owns parameter `p`, or None."""
+    ref = getattr(p, '_nrf_optimizer', None)
+    opt = ref() if ref is not None else None
+    return opt if (opt is not None and opt.alive) else None
+
+
+def current_half_copy(p):
+    """The fp16 shadow copy of `p` kept by its optimizer (None when there is none), re-cast first if `p` has been
+    written since the copy was made."""
+    h = getattr(p, '_nrf_half_copy', None)
+    if h is None:
+        return None
+    opt = optimizer_of(p)
+    if opt is None:                       # orphaned attributes (the owner was garbage-collected without detach())
+        for a in _ATTRS:
+            if hasattr(p, a):
+                delattr(p, a)
+        return None
+    if p._version != p._nrf_half_version:
+        opt.refresh_half_copies(only=p, external_write=True)
+    return h
+
+
+def current_half_pair(p):
+    """(interleaved fp16 buffer, slot) of a paired table, fresh; or None."""
+    if current_half_copy(p) is None:
+        return None
+    return getattr(p, '_nrf_half_pair', None)
+
+
+def live_grad_sink(p):
+    s = getattr(p, '_nrf_grad_sink', None)
+    if s is None or not s[0].alive:
+        return None
+    return s
+
+
+def sync_for_checkpoint(module):
+    """Before reading parameters for a checkpoint: a sharded optimizer keeps the fp32 master tables current only inside
+    each rank's shard, so gather them (a COLLECTIVE -- every rank must take the checkpoint path)."""
+    seen = set()
+    for p in module.parameters():
+        opt = optimizer_of(p)
+        if opt is not None and id(opt) not in seen:
+            seen.add(id(opt))
+            if not opt.master_complete:
+                opt.gather_master()
 
 
 class FusedAdamEMA:
     def __init__(self, params, lr=0.01, betas=(0.9, 0.999), eps=1e-15, lr_decay_steps=30000, ema_decay=0.95,
                  init_scale=65536.0, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000, enable_amp=True,
                  half_copy_min_numel=1 << 20, world_size=1, rank=0, shard_big=True, pair_tables=True):
-        """world_size > 1 makes step() own the gradient exchange of the data-parallel step:
+        """lr: one float, or one per parameter (the reference's second parameter group, trainers/base.py:210-212).
+
+        world_size > 1 makes step() own the gradient exchange of the data-parallel step:
         * small tensors (the MLPs): one flattened all-reduce, replicated update;
         * big tensors (the hash tables), under AMP: REDUCE-SCATTER of the gradient, Adam / EMA on this rank's 1/world
           shard only (optimizer state is allocated for the shard), then ALL-GATHER of the fp16 table copy -- the only
           form the next forward reads.  That moves 3/4 of an all-reduce's bytes and divides the optimizer pass by world.
-          The fp32 master table is then current only inside each rank's shard (gather_master() rebuilds it, e.g. for a
-          checkpoint); without AMP the tables are read in fp32 and the big tensors fall back to all-reduce.
+          The fp32 master table is then current only inside each rank's shard (`master_complete` is False until
+          gather_master() rebuilds it; state_dict() of the host-mirror modules does that); without AMP the tables are
+          read in fp32 and the big tensors fall back to all-reduce.
+        Which tensors are sharded / paired / exchanged depends only on (shape, requires_grad, world_size), never on the
+        rank or on which gradients happen to exist, so every rank issues the same collectives.
 
         pair_tables (under AMP): when two big tensors share one [T, 2] shape (the model's two hash tables),
         their fp16 copies live in ONE interleaved buffer [T][table][2] and their gradients are accumulated by the
@@ -30,16 +97,28 @@ class FusedAdamEMA:
         vector gather / one 16-byte reduction in the hash-grid kernels (nrf_grid_encode_forward_pair / _backward_pair)."""
         self.params = [p for p in params]
         dev = self.params[0].device
+        for p in self.params:                       # a previous fused optimizer over these parameters lets go of them
+            prev = optimizer_of(p)
+            if prev is not None:
+                prev.detach()
+        self.alive = True
         self.world_size, self.rank = int(world_size), int(rank)
-        self.lr, self.betas, self.eps, self.lr_decay_steps = lr, betas, eps, float(lr_decay_steps)
+        self.lrs = [float(v) for v in lr] if isinstance(lr, (list, tuple)) else [float(lr)] * len(self.params)
+        if len(self.lrs) != len(self.params):
+            raise ValueError('FusedAdamEMA: one learning rate per parameter expected')
+        self.lr = self.lrs[0]
+        self.betas, self.eps, self.lr_decay_steps = betas, eps, float(lr_decay_steps)
         self.ema_decay = ema_decay
         self.growth_factor, self.backoff_factor, self.growth_interval = growth_factor, backoff_factor, growth_interval
         self.enable_amp = enable_amp
-        # shard plan: (lo, hi) element range of this rank for every sharded tensor, None for replicated ones
+        self.master_complete = True
+        # shard plan: (lo, hi) element range of this rank for every sharded tensor, None for replicated ones.  Shards are
+        # an even number of elements so that a [T, 2] row never straddles two ranks.
         self.shard = []
         for p in self.params:
             n = p.numel()
-            if self.world_size > 1 and shard_big and enable_amp and n >= half_copy_min_numel and n % self.world_size == 0:
+            if (self.world_size > 1 and shard_big and enable_amp and n >= half_copy_min_numel and n % self.world_size == 0
+                    and (n // self.world_size) % 2 == 0):
                 per = n // self.world_size
                 self.shard.append((self.rank * per, (self.rank + 1) * per))
             else:
@@ -60,7 +139,7 @@ class FusedAdamEMA:
             twins = [g for g in groups.values() if len(g) == 2]
             if len(twins) == 1:
                 big = twins[0]
-                if all(self.shard[i] is None or self.shard[i][0] % 2 == 0 for i in big) and self.shard[big[0]] == self.shard[big[1]]:
+                if (self.shard[big[0]] is None) == (self.shard[big[1]] is None) and self.lrs[big[0]] == self.lrs[big[1]]:
                     self.pair_idx = tuple(big)
         self.grad_pair = None           # [T, 2, 2] f32, allocated by the first paired backward
         self.grad_pair_valid = False    # holds this step's gradients (zero_grad() invalidates; the next backward clears it)
@@ -80,14 +159,17 @@ class FusedAdamEMA:
         # fp16 shadow copies of the big tables, registered on the parameter for GridEncoder to find
         self.half = []
         self.half_pair = None
+        me = weakref.ref(self)
         if self.pair_idx is not None:
             a, b = (self.params[i] for i in self.pair_idx)
             self.half_pair = torch.stack([a.detach().to(torch.float16), b.detach().to(torch.float16)], dim=1).contiguous()
         for i, p in enumerate(self.params):
+            p._nrf_optimizer = me
             if self.pair_idx is not None and i in self.pair_idx:
                 e = self.pair_idx.index(i)
                 h = self.half_pair[:, e]                 # strided view: the interleaved buffer is the only fp16 copy
                 p._nrf_half_copy = h
+                p._nrf_half_version = p._version
                 p._nrf_half_pair = (self.half_pair, e)
                 p._nrf_grad_sink = (self, e)
                 self.half.append(h)
@@ -97,16 +179,52 @@ class FusedAdamEMA:
             if (enable_amp and p.numel() >= half_copy_min_numel) or p.numel() < half_copy_min_numel:
                 h = p.detach().to(torch.float16)
                 p._nrf_half_copy = h
+                p._nrf_half_version = p._version
                 self.half.append(h)
             else:
                 self.half.append(None)
 
+    # ------------------------------------------------------------------------------------------------ ownership
+    def detach(self):
+        """Let go of the parameters: remove every attribute this optimizer hung on them (fp16 shadows, pair buffer,
+        gradient sink).  The forward then casts the tables itself and the backward produces ordinary `.grad`s again --
+        e.g. before handing the model to another optimizer (the reference's _reset_optim between training stages)."""
+        for p in self.params:
+            ref = getattr(p, '_nrf_optimizer', None)
+            if ref is not None and ref() is self:
+                for a in _ATTRS:
+                    if hasattr(p, a):
+                        delattr(p, a)
+        self.alive = False
+
+    close = detach
+
+    def _require_alive(self):
+        if not self.alive:
+            raise RuntimeError('FusedAdamEMA: this optimizer was detached from its parameters (a newer one owns them)')
+
+    def is_sharded(self):
+        return any(sh is not None for sh in self.shard)
+
     @torch.no_grad()
-    def refresh_half_copies(self):
-        """Call after writing the parameters by any other means (loading a checkpoint, swapping in the EMA weights)."""
+    def refresh_half_copies(self, only=None, external_write=False):
+        """Re-cast the fp16 shadows from the fp32 parameters: after writing the parameters by any means PyTorch's version
+        counter does not see (`param.data` writes, e.g. torch_ema's copy_to / restore).  Version-visible writes
+        (load_state_dict, param.copy_) are picked up automatically by the next forward.  With a sharded optimizer the
+        fp32 master is complete only after gather_master() -- unless the write being reported replaced the whole tensor
+        (external_write=True, what the automatic path passes)."""
+        self._require_alive()
+        if self.is_sharded() and not self.master_complete and not external_write:
+            self.gather_master()
         for p, h in zip(self.params, self.half):
-            if h is not None:
+            if h is not None and (only is None or p is only):
                 h.copy_(p.detach())
+                p._nrf_half_version = p._version
+        if external_write and self.is_sharded():
+            # a whole-tensor write from outside (checkpoint load) makes the master complete again; the optimizer shards
+            # of EMA keep their own history
+            if only is None or all(p._version == p._nrf_half_version for p, h in zip(self.params, self.half) if h is not None):
+                self.master_complete = True
 
     def scale_loss(self, loss):
         return loss * self.scale if self.enable_amp else loss
@@ -118,6 +236,7 @@ class FusedAdamEMA:
 
     def grad_pair_buffer(self):
         """The interleaved gradient buffer the paired scatter accumulates into (called by the dual encoder's backward)."""
+        self._require_alive()
         a = self.params[self.pair_idx[0]]
         if self.grad_pair is None:
             self.grad_pair = torch.zeros(a.shape[0], 2, 2, dtype=torch.float32, device=a.device)
@@ -135,18 +254,62 @@ class FusedAdamEMA:
             return self.grad_pair[:, sink[1]]
         return None
 
+    # ------------------------------------------------------------------------------------------------ sharded state
     @torch.no_grad()
     def gather_master(self):
-        """Rebuild the full fp32 master copy of every sharded tensor on every rank (checkpointing)."""
+        """Rebuild the full fp32 master copy of every sharded tensor on every rank (checkpointing; a COLLECTIVE)."""
         from . import parallel
         for p, sh in zip(self.params, self.shard):
             if sh is not None:
                 flat = p.data.view(-1)
                 parallel.all_gather_shards(flat, flat[sh[0]:sh[1]].clone(), self.world_size)
+        self.master_complete = True
 
+    @torch.no_grad()
+    def full_ema(self):
+        """The EMA weights as full tensors shaped like the parameters (sharded ones are all-gathered: a COLLECTIVE)."""
+        from . import parallel
+        if self.ema is None:
+            return None
+        out = []
+        for p, e, sh in zip(self.params, self.ema, self.shard):
+            if sh is None:
+                out.append(e)
+            else:
+                full = torch.empty_like(p).view(-1)
+                parallel.all_gather_shards(full, e.contiguous(), self.world_size)
+                out.append(full.view_as(p))
+        return out
+
+    @contextlib.contextmanager
+    def ema_scope(self):
+        """torch_ema's `average_parameters()`: inside the scope the model evaluates with the EMA weights (the reference
+        tests / renders under EMA, trainers/base.py:361-377), fp16 shadows included; the training weights come back on
+        exit.  With a sharded optimizer entering and leaving are collectives."""
+        self._require_alive()
+        if self.ema is None:
+            yield
+            return
+        with torch.no_grad():
+            if self.is_sharded() and not self.master_complete:
+                self.gather_master()
+            backup = [p.detach().clone() for p in self.params]
+            for p, e in zip(self.params, self.full_ema()):
+                p.data.copy_(e)
+            self.refresh_half_copies()
+        try:
+            yield
+        finally:
+            with torch.no_grad():
+                for p, b in zip(self.params, backup):
+                    p.data.copy_(b)
+                self.refresh_half_copies()
+
+    # ------------------------------------------------------------------------------------------------ the step
     @torch.no_grad()
     def step(self):
         from . import parallel
+        self._require_alive()
         lib = L.lib()
         dev = self.params[0].device
         self.num_updates += 1
@@ -164,11 +327,21 @@ class FusedAdamEMA:
                     g = g.float().contiguous()
                 grads.append(g)
             # gradients of the paired tables arrive in the interleaved buffer unless someone produced .grad the usual way
-            pair_grads = self.pair_idx is not None and self.grad_pair_valid and all(grads[i] is None for i in self.pair_idx)
-            pair_src = None                    # (tensor holding this rank's interleaved gradient rows)
-            if pair_grads:
-                pair_src = self.grad_pair
+            pair_trainable = self.pair_idx is not None and all(self.params[i].requires_grad for i in self.pair_idx)
+            pair_has_grad = self.pair_idx is not None and any(grads[i] is not None for i in self.pair_idx)
+            if pair_has_grad and self.grad_pair_valid:
+                raise RuntimeError('FusedAdamEMA.step: a paired table has BOTH an ordinary .grad and gradients in the interleaved '
+                                   'pair buffer (two backward paths were mixed in one step); call zero_grad() between them')
+            pair_grads = pair_trainable and not pair_has_grad
+            if pair_grads and not self.grad_pair_valid and (self.world_size > 1 or self.grad_pair is not None):
+                self.grad_pair_buffer()          # this rank produced no table gradient (empty batch): exchange zeros
+            pair_grads = pair_grads and self.grad_pair_valid
+            pair_src = self.grad_pair if pair_grads else None      # tensor holding this rank's interleaved gradient rows
             if self.world_size > 1:
+                # every rank must issue the same collectives: a trainable tensor without a gradient contributes zeros
+                for i, p in enumerate(self.params):
+                    if grads[i] is None and p.requires_grad and not (pair_grads and i in self.pair_idx):
+                        grads[i] = torch.zeros(p.shape, dtype=torch.float32, device=dev)
                 # ---- gradient exchange: reduce-scatter the sharded tensors, one flattened all-reduce for the rest
                 for i, sh in enumerate(self.shard):
                     if sh is not None and grads[i] is not None:
@@ -190,7 +363,7 @@ class FusedAdamEMA:
                     L.check(lib.nrf_grads_check(g.data_ptr(), g.numel(), self.state.data_ptr(), st), 'grads_check')
             if pair_grads:
                 L.check(lib.nrf_grads_check(pair_src.data_ptr(), pair_src.numel(), self.state.data_ptr(), st), 'grads_check')
-            if self.world_size > 1 and any(sh is not None for sh in self.shard):
+            if self.world_size > 1 and self.is_sharded():
                 # an inf seen in ANY rank's shard skips the step everywhere (the replicated GradScaler decision)
                 parallel.allreduce_max_int(self.state[4:8].view(torch.int32), self.world_size)
             gathered_pair = False
@@ -204,7 +377,7 @@ class FusedAdamEMA:
                     self.exp_avg[ia].data_ptr(), self.exp_avg[ib].data_ptr(), self.exp_avg_sq[ia].data_ptr(),
                     self.exp_avg_sq[ib].data_ptr(), L.ptr(self.ema[ia]) if self.ema is not None else None,
                     L.ptr(self.ema[ib]) if self.ema is not None else None, self.half_pair.data_ptr() + (lo // 2) * 8, n // 2,
-                    self.state.data_ptr(), self.lr, self.lr_decay_steps, self.betas[0], self.betas[1], self.eps, omd, st),
+                    self.state.data_ptr(), self.lrs[ia], self.lr_decay_steps, self.betas[0], self.betas[1], self.eps, omd, st),
                     'adam_step_pair')
             for i, p in enumerate(self.params):
                 paired = self.pair_idx is not None and i in self.pair_idx
@@ -220,13 +393,14 @@ class FusedAdamEMA:
                     h_ptr = (self.half[i].data_ptr() + 2 * lo) if self.half[i] is not None else None
                 L.check(lib.nrf_adam_step_ex(p_ptr, g_ptr, self.exp_avg[i].data_ptr(), self.exp_avg_sq[i].data_ptr(),
                                              L.ptr(self.ema[i]) if self.ema is not None else None, h_ptr, n,
-                                             self.state.data_ptr(), self.lr, self.lr_decay_steps, self.betas[0], self.betas[1],
+                                             self.state.data_ptr(), self.lrs[i], self.lr_decay_steps, self.betas[0], self.betas[1],
                                              self.eps, omd, g_stride, h_stride, st), 'adam_step')
             if self.world_size > 1:
                 # ---- the next forward reads only the fp16 table copies: gather their shards (in place)
                 for i, sh in enumerate(self.shard):
                     if sh is None or (grads[i] is None and not (pair_grads and i in self.pair_idx)):
                         continue
+                    self.master_complete = False
                     if self.pair_idx is not None and i in self.pair_idx:
                         if not gathered_pair:          # param elements [lo, hi) <-> interleaved halfs [2 lo, 2 hi)
                             hflat = self.half_pair.view(-1)

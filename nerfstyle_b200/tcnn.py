@@ -41,6 +41,17 @@ class _mlp_function(Function):
         x = x.contiguous()
         params_h = half_params(params, owner)
         B = x.shape[0]
+        if params_h.dtype == torch.float32:                  # parity mode
+            y = torch.empty(B, n_out, dtype=torch.float32, device=x.device)
+            with torch.cuda.device(x.device):
+                L.check(L.lib().nrf_mlp_forward_f32(L.ptr(x), L.dtype_code(x.dtype), L.ptr(params_h), B, n_in, n_out, n_hidden,
+                                                    width, hidden_act, out_act, L.ptr(y), n_out, L.stream_of(x)),
+                        'mlp_forward_f32')
+            ctx.save_for_backward(x, params_h)
+            ctx.cfg = cfg
+            ctx.need_dx = ctx.needs_input_grad[0]
+            ctx.need_dp = ctx.needs_input_grad[1]
+            return y
         y = torch.empty(B, n_out, dtype=torch.float16, device=x.device)
         with torch.cuda.device(x.device):
             L.check(L.lib().nrf_mlp_forward(L.ptr(x), L.dtype_code(x.dtype), L.ptr(params_h), B, n_in, n_out, n_hidden,
@@ -62,13 +73,42 @@ class _mlp_function(Function):
         B = x.shape[0]
         dx = torch.empty_like(x) if ctx.need_dx else None
         dparams = torch.zeros(params_h.shape, dtype=torch.float32, device=x.device) if ctx.need_dp else None
-        if ctx.need_dx or ctx.need_dp:
+        if (ctx.need_dx or ctx.need_dp) and params_h.dtype == torch.float32:          # parity mode
+            dy = dy.float().contiguous()
+            with torch.cuda.device(x.device):
+                L.check(L.lib().nrf_mlp_backward_f32(L.ptr(x), L.dtype_code(x.dtype), L.ptr(params_h), L.ptr(dy), n_out, B, n_in,
+                                                     n_out, n_hidden, width, hidden_act, out_act, L.ptr(dx), 0, L.ptr(dparams),
+                                                     L.stream_of(x)), 'mlp_backward_f32')
+        elif ctx.need_dx or ctx.need_dp:
             with torch.cuda.device(x.device):
                 L.check(L.lib().nrf_mlp_backward(L.ptr(x), L.dtype_code(x.dtype), L.ptr(params_h), L.ptr(dy),
                                                  L.dtype_code(dy.dtype), B, n_in, n_out, n_hidden, width, hidden_act,
                                                  out_act, float(loss_scale), L.ptr(dx), L.dtype_code(x.dtype),
                                                  L.ptr(dparams), L.stream_of(x)), 'mlp_backward')
         return dx, dparams, None, None
+
+
+_parity = False
+
+
+def set_parity_mode(on):
+    """fp32 PARITY MODE: every Network evaluates with fp32 weights / activations / accumulation on the SIMT
+    kernels of csrc/mlp_f32.cu and returns fp32; nothing is rounded to fp16.  For parity checks, not for speed."""
+    global _parity
+    _parity = bool(on)
+
+
+class parity_mode:
+    """`with tcnn.parity_mode(): ...` -- scoped set_parity_mode(True)."""
+
+    def __enter__(self):
+        self._prev = _parity
+        set_parity_mode(True)
+        return self
+
+    def __exit__(self, *exc):
+        set_parity_mode(self._prev)
+        return False
 
 
 _cache_epoch = 0          # > 0 and odd while a cache_half_params() scope is open
@@ -97,7 +137,10 @@ def half_params(params, owner=None):
     """fp16 copy of a flat parameter vector for the kernels.  FusedAdamEMA keeps one current on the parameter
     (`_nrf_half_copy`, written by the optimizer kernel); inside a cache_half_params() scope the cast is cached on
     `owner`; otherwise it is made afresh."""
-    h = getattr(params, '_nrf_half_copy', None)
+    if _parity:
+        return params.detach().float().contiguous()          # parity mode: the kernels read the fp32 master weights
+    from .optim import current_half_copy
+    h = current_half_copy(params)          # re-cast automatically when the parameter was written since (checkpoint load)
     if h is not None:
         return h
     if owner is None or _cache_epoch % 2 == 0:
@@ -111,6 +154,11 @@ def half_params(params, owner=None):
 
 def _fwd_ex(net, x, params_h, y, col, n_out, out_act):
     """y[:, col:col+n_out] = net(x) through the extended C entry point (y may be wider than n_out; f16 or f32)."""
+    if params_h.dtype == torch.float32:                      # parity mode (y must be f32)
+        L.check(L.lib().nrf_mlp_forward_f32(L.ptr(x), L.dtype_code(x.dtype), L.ptr(params_h), x.shape[0], net.n_input_dims, n_out,
+                                            net.n_hidden_layers, net.n_neurons, net.hidden_act, out_act,
+                                            y.data_ptr() + col * y.element_size(), y.shape[1], L.stream_of(x)), 'mlp_forward_f32')
+        return
     L.check(L.lib().nrf_mlp_forward_ex(L.ptr(x), L.dtype_code(x.dtype), L.ptr(params_h), x.shape[0], net.n_input_dims, n_out,
                                        net.n_hidden_layers, net.n_neurons, net.hidden_act, out_act,
                                        y.data_ptr() + col * y.element_size(), L.dtype_code(y.dtype), y.shape[1],
@@ -118,6 +166,14 @@ def _fwd_ex(net, x, params_h, y, col, n_out, out_act):
 
 
 def _bwd_ex(net, x, params_h, dy, col, n_out, out_act, dx, dx_accumulate, dparams):
+    if params_h.dtype == torch.float32:                      # parity mode (dy must be f32)
+        if dy.dtype != torch.float32:
+            raise RuntimeError('nerfstyle_b200.tcnn: parity mode needs f32 output gradients')
+        L.check(L.lib().nrf_mlp_backward_f32(L.ptr(x), L.dtype_code(x.dtype), L.ptr(params_h), dy.data_ptr() + col * 4, dy.shape[1],
+                                             x.shape[0], net.n_input_dims, n_out, net.n_hidden_layers, net.n_neurons,
+                                             net.hidden_act, out_act, L.ptr(dx), int(dx_accumulate), L.ptr(dparams),
+                                             L.stream_of(x)), 'mlp_backward_f32')
+        return
     L.check(L.lib().nrf_mlp_backward_ex(L.ptr(x), L.dtype_code(x.dtype), L.ptr(params_h),
                                         dy.data_ptr() + col * dy.element_size(), L.dtype_code(dy.dtype), dy.shape[1],
                                         x.shape[0], net.n_input_dims, n_out, net.n_hidden_layers, net.n_neurons,
@@ -147,7 +203,7 @@ class _density_head(Function):
         enc, params_h = ctx.saved_tensors
         net = ctx.net
         g = g.contiguous()
-        if g.dtype not in (torch.float16, torch.float32):
+        if g.dtype not in (torch.float16, torch.float32) or params_h.dtype == torch.float32:
             g = g.float()
         dx = torch.empty_like(enc) if ctx.need[0] else None
         dp = torch.zeros(params_h.shape, dtype=torch.float32, device=enc.device) if ctx.need[1] else None
@@ -169,7 +225,7 @@ class _color_heads(Function):
         B = enc.shape[0]
         K = class_net.n_output_dims
         hp = [half_params(p, n) for p, n in ((p_class, class_net), (p_c1, color1_net), (p_c2, color2_net))]
-        c1 = torch.empty(B, color1_net.n_output_dims, dtype=torch.float16, device=enc.device)
+        c1 = torch.empty(B, color1_net.n_output_dims, dtype=torch.float32 if _parity else torch.float16, device=enc.device)
         rgbs = torch.empty(B, 3 + K, dtype=torch.float32, device=enc.device)
         with torch.cuda.device(enc.device):
             _fwd_ex(color1_net, enc, hp[1], c1, 0, color1_net.n_output_dims, color1_net.out_act)
@@ -186,7 +242,7 @@ class _color_heads(Function):
         class_net, color1_net, color2_net = ctx.nets
         K = class_net.n_output_dims
         g = g.contiguous()
-        if g.dtype not in (torch.float16, torch.float32):
+        if g.dtype not in (torch.float16, torch.float32) or h_c2.dtype == torch.float32:
             g = g.float()
         dev = enc.device
         z = lambda h, need: torch.zeros(h.shape, dtype=torch.float32, device=dev) if need else None

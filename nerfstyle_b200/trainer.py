@@ -76,12 +76,23 @@ class TrainStep:
                 import torch.distributed as dist
                 rank = dist.get_rank() if (world_size > 1 and dist.is_initialized()) else 0
             # with world_size > 1 the optimizer owns the gradient exchange (reduce-scatter / sharded Adam / all-gather)
-            self.fused = FusedAdamEMA(params, lr=lr, eps=1e-15, lr_decay_steps=lr_decay, ema_decay=ema_decay,
+            # mlp_lr: the reference's optional second parameter group (trainers/base.py:199-212, keywords2 -> lr 0.005)
+            lrs = [mlp_lr if (mlp_lr is not None and 'net' in n) else lr for n, _ in self.model.named_parameters()]
+            self.fused = FusedAdamEMA(params, lr=lrs, eps=1e-15, lr_decay_steps=lr_decay, ema_decay=ema_decay,
                                       enable_amp=enable_amp, world_size=world_size, rank=rank, shard_big=shard_optimizer,
                                       pair_tables=pair_tables)
             self.ema = self.fused.ema
             return
-        self.optim = torch.optim.Adam([{'params': params}], lr=lr, betas=(0.9, 0.999), eps=1e-15, fused=fused_adam)
+        from .optim import optimizer_of
+        for p in params:                    # a fused optimizer from an earlier stage lets go of the parameters first
+            prev = optimizer_of(p)
+            if prev is not None:
+                prev.detach()
+        groups = [{'params': params}]
+        if mlp_lr is not None:
+            named = list(self.model.named_parameters())
+            groups = [{'params': [p for n, p in named if 'net' not in n]}, {'params': [p for n, p in named if 'net' in n], 'lr': mlp_lr}]
+        self.optim = torch.optim.Adam(groups, lr=lr, betas=(0.9, 0.999), eps=1e-15, fused=fused_adam)
         self.scheduler = torch.optim.lr_scheduler.LambdaLR(
             self.optim, (lambda it: 0.1 ** (it / lr_decay)) if lr_decay > 0 else (lambda it: 1.0))
         self.scaler = torch.amp.GradScaler('cuda', enabled=enable_amp)
@@ -155,7 +166,9 @@ class TrainStep:
             self.scheduler.step()
         if self.ema is not None:
             with torch.no_grad():
-                torch._foreach_mul_(self.ema, self.ema_decay)
-                torch._foreach_add_(self.ema, [p.detach() for p in self.params], alpha=1.0 - self.ema_decay)
+                n = self.iter_ctr + 1
+                decay = min(self.ema_decay, (1 + n) / (10 + n))          # torch_ema (use_num_updates=True), as the fused path
+                torch._foreach_mul_(self.ema, decay)
+                torch._foreach_add_(self.ema, [p.detach() for p in self.params], alpha=1.0 - decay)
         self.iter_ctr += 1
         return loss.detach()

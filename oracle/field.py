@@ -147,10 +147,12 @@ class OracleField:
     """StyleTCNerf(use_dir=False) on CPU: two hash grids + density / class / color1 / color2 MLPs."""
 
     def __init__(self, bound=2.0, n_classes=8, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19,
-                 max_res_coeff=1024, half=False, seed=0, table_std=1e-4):
+                 max_res_coeff=1024, half=False, seed=0, table_std=1e-4, mlp_half=True):
         self.bound = float(bound)
         self.K = n_classes
         self.half = half
+        # mlp_half=False: the fp32 "parity mode" definition of the MLP (SURVEY.md 8c) -- no fp16 rounding anywhere
+        self.mlp_half = mlp_half
         # BBox(-bound, bound): size = 2*bound (style_nerf.py:28, tcnn_nerf.py:20-22)
         self.bbox_min = torch.full((3,), -self.bound)
         self.bbox_size = torch.full((3,), 2 * self.bound)
@@ -187,6 +189,8 @@ class OracleField:
         ni, no, nh, oact = self.nets[name]
         # color2_net always consumes an fp16 tensor (color1's output); the others consume the encoder output, which is
         # fp16 only under autocast
+        if not self.mlp_half:
+            return mlp_forward(x, self.params[name + '.params'], ni, no, nh, 'relu', oact, half=False, x_half=self.half and name != 'color2_net')
         return mlp_forward(x, self.params[name + '.params'], ni, no, nh, 'relu', oact, half=True,
                            x_half=(self.half or name == 'color2_net'))
 

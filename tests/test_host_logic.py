@@ -153,3 +153,57 @@ def test_fused_optimizer_pairing_rules_on_cpu(cuda_lib):
     sh = FusedAdamEMA([a, w, b], world_size=4, rank=3)
     assert sh.shard[0] == sh.shard[2] == (3 * (2 * T // 4), 2 * T) and sh.shard[1] is None and sh.pair_idx == (0, 2)
     assert sh.exp_avg[0].numel() == 2 * T // 4 and sh.exp_avg[1].numel() == 3072
+
+
+def test_fused_optimizer_ownership_and_freshness_on_cpu(cuda_lib):
+    """the fp16 shadows / pair buffer / gradient sink must not outlive their optimizer, and a shadow must never be
+    read stale after the parameter was written (checkpoint load with the optimizer already built)."""
+    from nerfstyle_b200 import optim
+    from nerfstyle_b200.optim import FusedAdamEMA
+    torch.manual_seed(1)
+    T = 1 << 19
+    a, b = torch.nn.Parameter(torch.randn(T, 2)), torch.nn.Parameter(torch.randn(T, 2))
+    w = torch.nn.Parameter(torch.randn(3072))
+    o1 = FusedAdamEMA([a, w, b])
+    assert optim.optimizer_of(a) is o1 and optim.live_grad_sink(a)[0] is o1
+    # a version-visible write (what load_state_dict does) is picked up by the next reader, pair buffer included
+    with torch.no_grad():
+        a.copy_(torch.full_like(a, 0.25))
+        w.mul_(2.0)
+    assert a._version != a._nrf_half_version
+    h = optim.current_half_copy(a)
+    assert float(h.min()) == float(h.max()) == 0.25 and a._version == a._nrf_half_version
+    assert torch.equal(o1.half_pair[:, 0], a.detach().half()) and torch.equal(o1.half_pair[:, 1], b.detach().half())
+    assert torch.equal(optim.current_half_copy(w), w.detach().half())
+    # a write through .data is invisible to the version counter: explicit refresh (ema_scope does this itself)
+    a.data.fill_(0.5)
+    assert float(optim.current_half_copy(a).max()) == 0.25
+    o1.refresh_half_copies()
+    assert float(optim.current_half_copy(a).min()) == 0.5
+    # ema_scope swaps the EMA weights in (fp16 shadows included) and the training weights back
+    o1.ema[0].fill_(-1.0)
+    with o1.ema_scope():
+        assert float(a.max()) == -1.0 and float(optim.current_half_copy(a).max()) == -1.0
+    assert float(a.min()) == 0.5 and float(optim.current_half_copy(a).min()) == 0.5
+    # a second optimizer over the same parameters takes them over; the first one refuses to run
+    o2 = FusedAdamEMA([a, w, b], pair_tables=False)
+    assert not o1.alive and optim.optimizer_of(a) is o2
+    assert not hasattr(a, '_nrf_grad_sink') and not hasattr(a, '_nrf_half_pair') and optim.live_grad_sink(a) is None
+    with pytest.raises(RuntimeError):
+        o1.grad_pair_buffer()
+    with pytest.raises(RuntimeError):
+        o1.step()
+    o2.detach()
+    for p in (a, b, w):
+        assert not any(hasattr(p, k) for k in optim._ATTRS)
+    assert optim.current_half_copy(a) is None
+    # the shard plan and the pairing decision depend on (shape, world) only -- identical on every rank
+    plans = [FusedAdamEMA([a, w, b], world_size=8, rank=r) for r in (0, 3, 7)]
+    assert len({(p.pair_idx, tuple(s is not None for s in p.shard)) for p in plans}) == 1
+    odd = [torch.nn.Parameter(torch.randn((1 << 19) + 4, 2)) for _ in range(2)]          # numel / 16 is odd -> not sharded anywhere
+    odd_plans = [FusedAdamEMA(odd, world_size=16, rank=r) for r in (0, 1)]
+    assert all(p.shard == [None, None] and p.pair_idx == (0, 1) for p in odd_plans)
+    # per-parameter learning rates (the reference's second parameter group)
+    o3 = FusedAdamEMA([a, w, b], lr=[0.01, 0.005, 0.01])
+    assert o3.lrs == [0.01, 0.005, 0.01] and o3.pair_idx == (0, 2)
+    assert FusedAdamEMA([a, w, b], lr=[0.01, 0.005, 0.02]).pair_idx is None         # paired tables share one fused pass
