@@ -631,9 +631,15 @@ k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict_
             const uint32_t i = base + lane;
             const bool valid = i < num_steps;
             float sigma = 0.0f, d0 = 0.0f, d1 = 0.0f;
+            float rgb[CMAX];
             if (valid) {
+                // every load of the block is issued before the scans below (one memory round trip per 32 samples; the
+                // rgb row used to be fetched only after the weights were known -- a second, dependent round trip)
                 const float4 dl = __ldg(reinterpret_cast<const float4*>(deltas) + offset + i);
                 sigma = __ldg(sigmas + offset + i);
+                const float* r = rgbs + (size_t)(offset + i) * C;
+#pragma unroll
+                for (int c = 0; c < CMAX; c++) rgb[c] = (c < (int)C) ? __ldg(r + c) : 0.0f;
                 d0 = is_ndc ? dl.z : dl.x;
                 d1 = is_ndc ? dl.w : dl.y;
             }
@@ -649,9 +655,8 @@ k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict_
             d = __fmaf_rn(w, t_run + tsum, d);
             ws += w;
             if (w != 0.0f) {
-                const float* r = rgbs + (size_t)(offset + i) * C;
 #pragma unroll
-                for (int c = 0; c < CMAX; c++) if (c < (int)C) acc[c] = __fmaf_rn(w, __ldg(r + c), acc[c]);
+                for (int c = 0; c < CMAX; c++) if (c < (int)C) acc[c] = __fmaf_rn(w, rgb[c], acc[c]);
             }
             if (term) break;
             T_run = __shfl_sync(NRF_FULL_MASK, T_after, 31);
