@@ -255,9 +255,16 @@ def run_ours(args):
     _lib.Stats.reset()
     _lib.Stats.timed = set(all_ops)
     nb = min(8, W + K)
+    if ts.fused is not None:
+        ts.fused.time_comm, ts.fused.comm_events = world > 1, []
     for s in range(nb):
         ts.step(*unpack(devb[s]))
     torch.cuda.synchronize()
+    comm = {}
+    if ts.fused is not None and world > 1:
+        for name, a, b in ts.fused.comm_events:
+            comm[name] = comm.get(name, 0.0) + a.elapsed_time(b) / nb
+        ts.fused.time_comm = False
     breakdown = {}
     for name, a, b, units in _lib.Stats.events:
         d = breakdown.setdefault(name, {'ms': 0.0, 'calls': 0})
@@ -347,6 +354,15 @@ def run_ours(args):
         'final_loss': lv,
         'cuda_mallocs_in_timed_region': int(seg1 - seg0),
     }
+    if world > 1:
+        # NCCL time per step (CUDA events around every collective on the stream it is issued on, instrumented pass):
+        # the all-gather of the fp16 tables runs on a side stream under the next step's ray marching; what the compute
+        # stream still waits for it is `wait_gather`.  overlap_frac = hidden / total collective time.
+        total = sum(v for k, v in comm.items() if k != 'wait_gather')
+        hidden = max(0.0, comm.get('all_gather', 0.0) - comm.get('wait_gather', 0.0))
+        line['comm_ms'] = {k: round(v, 4) for k, v in comm.items()}
+        line['comm_ms']['total'] = round(total, 4)
+        line['overlap_frac'] = round(hidden / total, 3) if total > 0 else None
     if world == 1 and not args.skip_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline(args.cpu_sample_rays)
     if world == 1 and not args.skip_extras:

@@ -44,6 +44,7 @@ def current_half_copy(p):
         return None
     if p._version != p._nrf_half_version:
         opt.refresh_half_copies(only=p, external_write=True)
+    opt.wait_pending_gather()             # the all-gather of the previous step may still be running on the side stream
     return h
 
 
@@ -144,6 +145,14 @@ class FusedAdamEMA:
         self.grad_pair = None           # [T, 2, 2] f32, allocated by the first paired backward
         self.grad_pair_valid = False    # holds this step's gradients (zero_grad() invalidates; the next backward clears it)
         self.grad_shard_pair = None
+        # overlap_gather: the all-gather of the fp16 table copies runs on a side stream and the NEXT step's first table
+        # read waits for it (current_half_copy) -- ray generation, near/far and the occupancy march of that step, which
+        # do not touch the tables, overlap the exchange
+        self.overlap_gather = True
+        self.time_comm = False
+        self.comm_events = []
+        self._comm_stream = None
+        self._gather_done = None
         self.exp_avg = [state_like(p, sh) for p, sh in zip(self.params, self.shard)]
         self.exp_avg_sq = [state_like(p, sh) for p, sh in zip(self.params, self.shard)]
         self.ema = [state_like(p, sh, 'copy') for p, sh in zip(self.params, self.shard)] if ema_decay is not None else None
@@ -199,6 +208,26 @@ class FusedAdamEMA:
 
     close = detach
 
+    def wait_pending_gather(self):
+        """Make the current stream wait for an all-gather still in flight on the side stream (no host sync)."""
+        ev = self._gather_done
+        if ev is not None:
+            with self._timed('wait_gather'):
+                torch.cuda.current_stream(self.params[0].device).wait_event(ev)
+            self._gather_done = None
+
+    @contextlib.contextmanager
+    def _timed(self, name):
+        """bench.py only (time_comm = True): CUDA events around a collective / a wait on the stream it is issued on."""
+        if not self.time_comm or self.params[0].device.type != 'cuda':
+            yield
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        yield
+        e1.record()
+        self.comm_events.append((name, e0, e1))
+
     def _require_alive(self):
         if not self.alive:
             raise RuntimeError('FusedAdamEMA: this optimizer was detached from its parameters (a newer one owns them)')
@@ -214,6 +243,7 @@ class FusedAdamEMA:
         fp32 master is complete only after gather_master() -- unless the write being reported replaced the whole tensor
         (external_write=True, what the automatic path passes)."""
         self._require_alive()
+        self.wait_pending_gather()
         if self.is_sharded() and not self.master_complete and not external_write:
             self.gather_master()
         for p, h in zip(self.params, self.half):
@@ -305,11 +335,45 @@ class FusedAdamEMA:
                     p.data.copy_(b)
                 self.refresh_half_copies()
 
+    def _gather_half_copies(self, dev, has_grad, pair_grads):
+        """All-gather of the fp16 copies of the sharded tensors that were just updated.  With overlap_gather it is issued
+        on a side stream (after this step's Adam kernels) and `_gather_done` is recorded for the next table read."""
+        from . import parallel
+        todo = [i for i, sh in enumerate(self.shard)
+                if sh is not None and (has_grad[i] or (pair_grads and i in self.pair_idx))]
+        if not todo:
+            return
+        self.master_complete = False
+        side = None
+        if self.overlap_gather and dev.type == 'cuda':
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream(device=dev)
+            side = self._comm_stream
+            side.wait_stream(torch.cuda.current_stream(dev))
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            gathered_pair = False
+            for i in todo:
+                sh = self.shard[i]
+                if self.pair_idx is not None and i in self.pair_idx:
+                    if not gathered_pair:          # param elements [lo, hi) <-> interleaved halfs [2 lo, 2 hi)
+                        hflat = self.half_pair.view(-1)
+                        with self._timed('all_gather'):
+                            parallel.all_gather_shards(hflat, hflat[2 * sh[0]:2 * sh[1]], self.world_size)
+                        gathered_pair = True
+                    continue
+                hflat = self.half[i].view(-1)
+                with self._timed('all_gather'):
+                    parallel.all_gather_shards(hflat, hflat[sh[0]:sh[1]], self.world_size)
+            if side is not None:
+                self._gather_done = torch.cuda.Event()
+                self._gather_done.record(side)
+
     # ------------------------------------------------------------------------------------------------ the step
     @torch.no_grad()
     def step(self):
         from . import parallel
         self._require_alive()
+        self.wait_pending_gather()          # (a step without a forward in between: tests)
         lib = L.lib()
         dev = self.params[0].device
         self.num_updates += 1
@@ -345,7 +409,8 @@ class FusedAdamEMA:
                 # ---- gradient exchange: reduce-scatter the sharded tensors, one flattened all-reduce for the rest
                 for i, sh in enumerate(self.shard):
                     if sh is not None and grads[i] is not None:
-                        parallel.reduce_scatter_sum(grads[i].view(-1), self.grad_shard[i], self.world_size, self.rank)
+                        with self._timed('reduce_scatter'):
+                            parallel.reduce_scatter_sum(grads[i].view(-1), self.grad_shard[i], self.world_size, self.rank)
                         grads[i] = self.grad_shard[i]
                 if pair_grads:
                     if self.shard[self.pair_idx[0]] is not None:
@@ -353,11 +418,14 @@ class FusedAdamEMA:
                         flat = self.grad_pair.view(-1)
                         if self.grad_shard_pair is None:
                             self.grad_shard_pair = torch.empty(flat.numel() // self.world_size, dtype=torch.float32, device=dev)
-                        parallel.reduce_scatter_sum(flat, self.grad_shard_pair, self.world_size, self.rank)
+                        with self._timed('reduce_scatter'):
+                            parallel.reduce_scatter_sum(flat, self.grad_shard_pair, self.world_size, self.rank)
                         pair_src = self.grad_shard_pair
                     else:
-                        parallel.allreduce_tensors([self.grad_pair], self.world_size)
-                parallel.allreduce_tensors([g for g, sh in zip(grads, self.shard) if sh is None and g is not None], self.world_size)
+                        with self._timed('all_reduce'):
+                            parallel.allreduce_tensors([self.grad_pair], self.world_size)
+                with self._timed('all_reduce_small'):
+                    parallel.allreduce_tensors([g for g, sh in zip(grads, self.shard) if sh is None and g is not None], self.world_size)
             for g in grads:
                 if g is not None:
                     L.check(lib.nrf_grads_check(g.data_ptr(), g.numel(), self.state.data_ptr(), st), 'grads_check')
@@ -365,8 +433,8 @@ class FusedAdamEMA:
                 L.check(lib.nrf_grads_check(pair_src.data_ptr(), pair_src.numel(), self.state.data_ptr(), st), 'grads_check')
             if self.world_size > 1 and self.is_sharded():
                 # an inf seen in ANY rank's shard skips the step everywhere (the replicated GradScaler decision)
-                parallel.allreduce_max_int(self.state[4:8].view(torch.int32), self.world_size)
-            gathered_pair = False
+                with self._timed('all_reduce_small'):
+                    parallel.allreduce_max_int(self.state[4:8].view(torch.int32), self.world_size)
             if pair_grads:
                 # both tables in one pass over the interleaved gradient rows (16-byte loads) and fp16 rows (8-byte stores)
                 ia, ib = self.pair_idx
@@ -397,17 +465,6 @@ class FusedAdamEMA:
                                              self.eps, omd, g_stride, h_stride, st), 'adam_step')
             if self.world_size > 1:
                 # ---- the next forward reads only the fp16 table copies: gather their shards (in place)
-                for i, sh in enumerate(self.shard):
-                    if sh is None or (grads[i] is None and not (pair_grads and i in self.pair_idx)):
-                        continue
-                    self.master_complete = False
-                    if self.pair_idx is not None and i in self.pair_idx:
-                        if not gathered_pair:          # param elements [lo, hi) <-> interleaved halfs [2 lo, 2 hi)
-                            hflat = self.half_pair.view(-1)
-                            parallel.all_gather_shards(hflat, hflat[2 * sh[0]:2 * sh[1]], self.world_size)
-                            gathered_pair = True
-                        continue
-                    hflat = self.half[i].view(-1)
-                    parallel.all_gather_shards(hflat, hflat[sh[0]:sh[1]], self.world_size)
+                self._gather_half_copies(dev, [g is not None for g in grads], pair_grads)
             L.check(lib.nrf_scaler_update(self.state.data_ptr(), self.growth_factor, self.backoff_factor,
                                           int(self.growth_interval) if self.enable_amp else (1 << 30), st), 'scaler_update')
