@@ -261,6 +261,10 @@ def run_ours(args):
         ts.step(*unpack(devb[s]))
     torch.cuda.synchronize()
     comm = {}
+
+    class ts_p2p:
+        value = ts.fused is not None and ts.fused._p2p is not None
+        multicast = bool(value and ts.fused._p2p['grad_mc'])
     if ts.fused is not None and world > 1:
         for name, a, b in ts.fused.comm_events:
             comm[name] = comm.get(name, 0.0) + a.elapsed_time(b) / nb
@@ -343,8 +347,11 @@ def run_ours(args):
                    'occupancy': 'H128 C2 update every 16 steps', 'amp': amp, 'optimizer': 'Adam(fused)+EMA',
                    'l2_policy': 'no flush: per-step working set (~%d MB of samples/activations + 96 MB tables) exceeds the 126 MB L2'
                                 % (samples_last * 700 // (1 << 20)),
-                   'parallelism': 'dp%d (rays sharded; table grads reduce-scattered, Adam on 1/N table shards, fp16 tables all-gathered; '
-                                  'MLP grads all-reduced -- NCCL over NVLink)' % world},
+                   'parallelism': ('dp%d (rays sharded; exchange fused into the optimizer kernel over NVLink peer memory: multimem.ld_reduce of '
+                                   'the table-gradient shard, Adam on 1/N rows, multimem.st of the fp16 rows to every rank)' % world)
+                                  if getattr(ts_p2p, 'value', False) else
+                                  ('dp%d (rays sharded; table grads reduce-scattered, Adam on 1/N table shards, fp16 tables all-gathered; '
+                                   'MLP grads all-reduced -- NCCL over NVLink)' % world)},
         'e2e': {'value': round(n_global * K / e2e_s, 1), 'unit': 'rays/s', 'h2d_bytes_per_step': int(host[0].numel() * 4),
                 'd2h_bytes_per_step': 4 + 8, 'ms_per_step': round(e2e_s * 1e3 / K, 4)},
         'gpu_launches': int(launches),
@@ -355,14 +362,18 @@ def run_ours(args):
         'cuda_mallocs_in_timed_region': int(seg1 - seg0),
     }
     if world > 1:
-        # NCCL time per step (CUDA events around every collective on the stream it is issued on, instrumented pass):
-        # the all-gather of the fp16 tables runs on a side stream under the next step's ray marching; what the compute
-        # stream still waits for it is `wait_gather`.  overlap_frac = hidden / total collective time.
+        # exchange time per step (CUDA events around every collective / peer-memory kernel on the stream it is issued on,
+        # instrumented pass).  Peer-memory path (default): `barrier` (all ranks' gradients complete), `p2p_small` (MLP
+        # gradients + found-inf flag), `p2p_adam_pair` (reduce-scatter + Adam + all-gather of the tables in ONE kernel,
+        # so this entry also contains the optimizer arithmetic), `barrier_tail` (on a side stream under the next step's
+        # ray marching; what the compute stream still waits for it is `wait_gather`).  NCCL path: reduce_scatter /
+        # all_reduce_small / all_gather.  overlap_frac = hidden / total.
         total = sum(v for k, v in comm.items() if k != 'wait_gather')
-        hidden = max(0.0, comm.get('all_gather', 0.0) - comm.get('wait_gather', 0.0))
+        hidden = max(0.0, comm.get('all_gather', 0.0) + comm.get('barrier_tail', 0.0) - comm.get('wait_gather', 0.0))
         line['comm_ms'] = {k: round(v, 4) for k, v in comm.items()}
         line['comm_ms']['total'] = round(total, 4)
         line['overlap_frac'] = round(hidden / total, 3) if total > 0 else None
+        line['exchange'] = {'peer_memory': bool(ts_p2p.value), 'nvls_multicast': bool(ts_p2p.multicast)}
     if world == 1 and not args.skip_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline(args.cpu_sample_rays)
     if world == 1 and not args.skip_extras:

@@ -321,6 +321,22 @@ int nrf_adam_step_pair(float* param0, float* param1, const float* grad_pair, flo
                        float ema_one_minus_decay, void* stream);
 int nrf_scaler_update(void* state, float growth, float backoff, int growth_interval, void* stream);
 
+/* The data-parallel exchange fused into the optimizer kernels over NVLink / NVSwitch peer memory (SURVEY.md 8e, 5.8;
+ * csrc/optim_p2p.cu): replaces ncclReduceScatter -> Adam on the shard -> ncclAllGather (+ two small all-reduces) of the
+ * N > 1 train step.  The *_ptrs_dev arguments are device arrays of `world` 64-bit addresses: buffer r of a symmetric
+ * allocation as mapped into this process; *_mc are the NVLS multicast addresses of the same allocations (NULL: peer
+ * loads / stores in rank order).  The caller brackets the calls with symmetric-memory barriers.
+ *   nrf_small_allreduce_p2p: out[i] = sum_r peer[r][i], i < n; peer[r][n] != 0 on any rank sets state.found_inf.
+ *   nrf_adam_step_pair_p2p : rows [row_lo, row_lo + rows) of the interleaved pair buffers: reduce the gradient rows of all
+ *                            ranks (multimem.ld_reduce), Adam / EMA as nrf_adam_step_pair, write the fp16 rows to all ranks
+ *                            (multimem.st); param / moment / ema pointers address the shard (element 0 = row row_lo). */
+int nrf_small_allreduce_p2p(const uint64_t* peer_ptrs_dev, uint32_t world, uint32_t n, float* out, void* state, void* stream);
+int nrf_adam_step_pair_p2p(float* param0, float* param1, const uint64_t* grad_ptrs_dev, const float* grad_mc,
+                           const uint64_t* half_ptrs_dev, void* half_mc, uint32_t world, uint64_t row_lo, float* exp_avg0,
+                           float* exp_avg1, float* exp_avg_sq0, float* exp_avg_sq1, float* ema0, float* ema1, uint64_t rows,
+                           const void* state, float lr0, float lr_decay_steps, float beta1, float beta2, float eps,
+                           float ema_one_minus_decay, void* stream);
+
 /* ------------------------------------------------------------------ occupancy-grid update (SURVEY 8f NEXT-2) */
 
 /* Renderer.update_state (renderer.py:120-194) around the density query, as device passes with no host read-back.

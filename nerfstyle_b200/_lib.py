@@ -79,6 +79,9 @@ SIGNATURES = {
     'nrf_adam_step_pair': (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _vp, _f32, _f32, _f32, _f32, _f32, _f32,
                                   _vp]),
     'nrf_scaler_update': (_i32, [_vp, _f32, _f32, _i32, _vp]),
+    'nrf_small_allreduce_p2p': (_i32, [_vp, _u32, _u32, _vp, _vp, _vp]),
+    'nrf_adam_step_pair_p2p': (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _vp, _f32, _f32,
+                                      _f32, _f32, _f32, _f32, _vp]),
     'nrf_occ_points_full': (_i32, [_vp, _vp, _u32, _u32, _vp, _vp]),
     'nrf_occ_points_sparse': (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp, _vp]),
     'nrf_occ_flags': (_i32, [_vp, _u32, _u32, _vp, _vp]),
@@ -116,7 +119,7 @@ KERNELS_PER_CALL = {
     'nrf_grid_encode_backward_dual': 1, 'nrf_grid_encode_forward_pair': 1, 'nrf_grid_encode_backward_pair': 1,
     'nrf_grid_initialize': 1, 'nrf_mlp_forward': 1, 'nrf_mlp_backward': 1, 'nrf_sh_encode_forward': 1, 'nrf_march_rays_dev': 1,
     'nrf_composite_rays_dev': 1, 'nrf_compact_alive_dev': 4, 'nrf_grid_encode_forward_dual_dev': 1, 'nrf_mlp_forward_dev': 1, 'nrf_mlp_forward_ex': 1, 'nrf_mlp_backward_ex': 1, 'nrf_mlp_forward_f32': 1, 'nrf_mlp_backward_f32': 1, 'nrf_nnfm_forward': 5,
-    'nrf_adam_step': 1, 'nrf_adam_step_ex': 1, 'nrf_adam_step_pair': 1, 'nrf_grads_check': 1, 'nrf_scaler_update': 1, 'nrf_generate_rays': 1,
+    'nrf_adam_step': 1, 'nrf_adam_step_ex': 1, 'nrf_adam_step_pair': 1, 'nrf_adam_step_pair_p2p': 1, 'nrf_small_allreduce_p2p': 1, 'nrf_grads_check': 1, 'nrf_scaler_update': 1, 'nrf_generate_rays': 1,
     'nrf_occ_points_full': 1, 'nrf_occ_points_sparse': 1, 'nrf_occ_flags': 1, 'nrf_occ_scatter_max': 1, 'nrf_occ_update': 2,
     'nrf_packbits_dev': 1, 'nrf_recon_loss': 1,
 }

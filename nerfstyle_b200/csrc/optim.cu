@@ -6,13 +6,7 @@
 // the scale did not shrink") is decided on the device from a small state block, so the step has no host sync.
 #include "common.cuh"
 
-struct OptState {        // lives in device memory, 8 x 4 bytes
-    float scale;         // current loss scale
-    int found_inf;       // set by k_grads_check for the current step
-    int growth_tracker;  // consecutive finite steps since the last scale change
-    int good_steps;      // optimizer steps actually taken (bias correction / LambdaLR epoch)
-    int pad[4];
-};
+#include "optim_state.cuh"
 
 __global__ void k_grads_check(const float* __restrict__ g, uint64_t n, OptState* st) {
     bool bad = false;

@@ -77,7 +77,7 @@ def sync_for_checkpoint(module):
 class FusedAdamEMA:
     def __init__(self, params, lr=0.01, betas=(0.9, 0.999), eps=1e-15, lr_decay_steps=30000, ema_decay=0.95,
                  init_scale=65536.0, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000, enable_amp=True,
-                 half_copy_min_numel=1 << 20, world_size=1, rank=0, shard_big=True, pair_tables=True):
+                 half_copy_min_numel=1 << 20, world_size=1, rank=0, shard_big=True, pair_tables=True, p2p=None):
         """lr: one float, or one per parameter (the reference's second parameter group, trainers/base.py:210-212).
 
         world_size > 1 makes step() own the gradient exchange of the data-parallel step:
@@ -95,7 +95,15 @@ class FusedAdamEMA:
         their fp16 copies live in ONE interleaved buffer [T][table][2] and their gradients are accumulated by the
         paired scatter kernel into ONE interleaved f32 buffer (`grad_pair`) that this optimizer reads directly -- the
         tables' `.grad` stays None (use grad_of(p) to look at a gradient).  A corner of both tables is then one
-        vector gather / one 16-byte reduction in the hash-grid kernels (nrf_grid_encode_forward_pair / _backward_pair)."""
+        vector gather / one 16-byte reduction in the hash-grid kernels (nrf_grid_encode_forward_pair / _backward_pair).
+
+        p2p (None = on when possible; env NRF_P2P=0 turns it off): with sharded paired tables on CUDA the whole exchange is
+        fused into the optimizer kernels over NVLink / NVSwitch peer memory (csrc/optim_p2p.cu) -- the interleaved gradient
+        and fp16 buffers become torch symmetric-memory allocations, each rank reduces its row shard straight out of every
+        rank's gradient buffer (multimem.ld_reduce through the NVLS multicast mapping when the fabric has one), runs Adam /
+        EMA on it and stores the fp16 rows into every rank's table copy (multimem.st); the MLP gradients and the found-inf
+        flag go through a third symmetric buffer.  No NCCL call remains in the step; two symmetric-memory barriers bracket the
+        kernel.  Anything else (no pairing, gloo, no symmetric memory) keeps the NCCL path."""
         self.params = [p for p in params]
         dev = self.params[0].device
         for p in self.params:                       # a previous fused optimizer over these parameters lets go of them
@@ -192,6 +200,136 @@ class FusedAdamEMA:
                 self.half.append(h)
             else:
                 self.half.append(None)
+        self._p2p, self._p2p_error = None, None
+        if (p2p is None or p2p) and self.world_size > 1 and self.pair_idx is not None and self.shard[self.pair_idx[0]] is not None:
+            if self._setup_p2p(dev):            # the interleaved buffers moved: re-register the views on the parameters
+                for e, i in enumerate(self.pair_idx):
+                    p = self.params[i]
+                    h = self.half_pair[:, e]
+                    p._nrf_half_copy, p._nrf_half_pair = h, (self.half_pair, e)
+                    self.half[i] = h
+            elif p2p:
+                raise RuntimeError('FusedAdamEMA(p2p=True): symmetric memory unavailable (%s)' % self._p2p_error)
+
+    # ------------------------------------------------------------------------------------------------ peer memory
+    def _setup_p2p(self, dev):
+        """Re-home the interleaved gradient / fp16 buffers in symmetric memory and rendezvous (a COLLECTIVE: every rank
+        constructs its optimizer at the same point).  Returns False (leaving everything as it was) when unavailable."""
+        import os
+        import torch.distributed as dist
+        if os.environ.get('NRF_P2P', '1') == '0' or dev.type != 'cuda' or not dist.is_initialized() or dist.get_backend() != 'nccl':
+            return False
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = dist.group.WORLD
+            ia, ib = self.pair_idx
+            T = self.params[ia].shape[0]
+            self._small_idx = [i for i, sh in enumerate(self.shard) if sh is None and (self.pair_idx is None or i not in self.pair_idx)]
+            n_small = sum(self.params[i].numel() for i in self._small_idx)
+            gp = symm.empty((T, 2, 2), dtype=torch.float32, device=dev)
+            hp = symm.empty((T, 2, 2), dtype=torch.float16, device=dev)
+            sm = symm.empty((n_small + 8,), dtype=torch.float32, device=dev)
+            gp.zero_(); sm.zero_()
+            hp.copy_(self.half_pair)
+            hg, hh, hs = symm.rendezvous(gp, group), symm.rendezvous(hp, group), symm.rendezvous(sm, group)
+            as_dev = lambda h: torch.tensor([int(p) for p in h.buffer_ptrs], dtype=torch.int64, device=dev)      # noqa: E731
+            self._p2p = {'hg': hg, 'hh': hh, 'hs': hs, 'grad_ptrs': as_dev(hg), 'half_ptrs': as_dev(hh), 'small_ptrs': as_dev(hs),
+                         'grad_mc': int(hg.multicast_ptr) if hg.has_multicast_support else 0,
+                         'half_mc': int(hh.multicast_ptr) if hh.has_multicast_support else 0,
+                         'small': sm, 'n_small': n_small, 'small_red': torch.zeros(n_small, dtype=torch.float32, device=dev)}
+            if os.environ.get('NRF_P2P_NO_MULTICAST', '0') == '1':
+                self._p2p['grad_mc'] = self._p2p['half_mc'] = 0
+        except Exception as e:        # symmetric memory not available on this build / fabric: NCCL path
+            self._p2p = None
+            self._p2p_error = '%s: %s' % (type(e).__name__, e)
+            return False
+        self.grad_pair, self.half_pair = gp, hp
+        self.grad_pair_valid = False
+        return True
+
+    def _step_p2p(self, grads, lib, dev, st, omd):
+        """The N > 1 step with the exchange fused into the kernels (see __init__ / csrc/optim_p2p.cu)."""
+        P = self._p2p
+        ia, ib = self.pair_idx
+        sh = self.shard[ia]
+        # 1. local inf / nan check BEFORE the exchange (a non-finite sum needs a non-finite addend), flag + small gradients
+        #    into this rank's symmetric buffer
+        L.check(lib.nrf_grads_check(self.grad_pair.data_ptr(), self.grad_pair.numel(), self.state.data_ptr(), st), 'grads_check')
+        o = 0
+        for i in self._small_idx:
+            g, n = grads[i], self.params[i].numel()
+            if g is None:
+                P['small'][o:o + n].zero_()
+            else:
+                L.check(lib.nrf_grads_check(g.data_ptr(), n, self.state.data_ptr(), st), 'grads_check')
+                P['small'][o:o + n].copy_(g.reshape(-1))
+            o += n
+        others = [i for i, s_ in enumerate(self.shard) if s_ is not None and i not in self.pair_idx]      # sharded, not paired
+        for i in others:
+            if grads[i] is None and self.params[i].requires_grad:
+                grads[i] = torch.zeros(self.params[i].shape, dtype=torch.float32, device=dev)
+            if grads[i] is not None:
+                L.check(lib.nrf_grads_check(grads[i].data_ptr(), grads[i].numel(), self.state.data_ptr(), st), 'grads_check')
+        P['small'][o:o + 1].copy_(self.state[4:8].view(torch.int32))
+        # 2. every rank's gradients are complete
+        with self._timed('barrier'):
+            P['hg'].barrier()
+        # 3. small tensors + the skip decision, identical on every rank (summed in rank order)
+        with self._timed('p2p_small'):
+            L.check(lib.nrf_small_allreduce_p2p(P['small_ptrs'].data_ptr(), self.world_size, P['n_small'], P['small_red'].data_ptr(),
+                                                self.state.data_ptr(), st), 'small_allreduce_p2p')
+        # 4. reduce-scatter + Adam / EMA + all-gather of the paired tables in one kernel over peer memory
+        lo, n = sh[0], sh[1] - sh[0]
+        with self._timed('p2p_adam_pair'):
+            L.check(lib.nrf_adam_step_pair_p2p(
+                self.params[ia].data_ptr() + 4 * lo, self.params[ib].data_ptr() + 4 * lo, P['grad_ptrs'].data_ptr(), P['grad_mc'] or None,
+                P['half_ptrs'].data_ptr(), P['half_mc'] or None, self.world_size, lo // 2,
+                self.exp_avg[ia].data_ptr(), self.exp_avg[ib].data_ptr(), self.exp_avg_sq[ia].data_ptr(), self.exp_avg_sq[ib].data_ptr(),
+                L.ptr(self.ema[ia]) if self.ema is not None else None, L.ptr(self.ema[ib]) if self.ema is not None else None, n // 2,
+                self.state.data_ptr(), self.lrs[ia], self.lr_decay_steps, self.betas[0], self.betas[1], self.eps, omd, st),
+                'adam_step_pair_p2p')
+        self.master_complete = False
+        # 5. the replicated small tensors from the reduced gradients
+        o = 0
+        for i in self._small_idx:
+            p, n = self.params[i], self.params[i].numel()
+            if p.requires_grad:
+                h_ptr = self.half[i].data_ptr() if self.half[i] is not None else None
+                L.check(lib.nrf_adam_step_ex(p.data_ptr(), P['small_red'].data_ptr() + 4 * o, self.exp_avg[i].data_ptr(),
+                                             self.exp_avg_sq[i].data_ptr(), L.ptr(self.ema[i]) if self.ema is not None else None, h_ptr, n,
+                                             self.state.data_ptr(), self.lrs[i], self.lr_decay_steps, self.betas[0], self.betas[1],
+                                             self.eps, omd, 1, 1, st), 'adam_step')
+            o += n
+        # 5b. sharded tensors outside the pair (none in the reference's model) keep the NCCL exchange
+        if others:
+            from . import parallel
+            for i in others:
+                if grads[i] is None:
+                    continue
+                so = self.shard[i]
+                parallel.reduce_scatter_sum(grads[i].view(-1), self.grad_shard[i], self.world_size, self.rank)
+                h_ptr = (self.half[i].data_ptr() + 2 * so[0]) if self.half[i] is not None else None
+                L.check(lib.nrf_adam_step_ex(self.params[i].data_ptr() + 4 * so[0], self.grad_shard[i].data_ptr(), self.exp_avg[i].data_ptr(),
+                                             self.exp_avg_sq[i].data_ptr(), L.ptr(self.ema[i]) if self.ema is not None else None, h_ptr,
+                                             so[1] - so[0], self.state.data_ptr(), self.lrs[i], self.lr_decay_steps, self.betas[0],
+                                             self.betas[1], self.eps, omd, 1, 1, st), 'adam_step')
+                if self.half[i] is not None:
+                    hflat = self.half[i].view(-1)
+                    parallel.all_gather_shards(hflat, hflat[so[0]:so[1]], self.world_size)
+        # 6. every rank's table rows have landed (and nobody still reads this rank's gradients): on the side stream, the next
+        #    step's first table read waits for it
+        side = None
+        if self.overlap_gather:
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream(device=dev)
+            side = self._comm_stream
+            side.wait_stream(torch.cuda.current_stream(dev))
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            with self._timed('barrier_tail'):
+                P['hh'].barrier()
+            if side is not None:
+                self._gather_done = torch.cuda.Event()
+                self._gather_done.record(side)
 
     # ------------------------------------------------------------------------------------------------ ownership
     def detach(self):
@@ -401,6 +539,11 @@ class FusedAdamEMA:
                 self.grad_pair_buffer()          # this rank produced no table gradient (empty batch): exchange zeros
             pair_grads = pair_grads and self.grad_pair_valid
             pair_src = self.grad_pair if pair_grads else None      # tensor holding this rank's interleaved gradient rows
+            if self._p2p is not None and pair_grads:
+                self._step_p2p(grads, lib, dev, st, omd)
+                L.check(lib.nrf_scaler_update(self.state.data_ptr(), self.growth_factor, self.backoff_factor,
+                                              int(self.growth_interval) if self.enable_amp else (1 << 30), st), 'scaler_update')
+                return
             if self.world_size > 1:
                 # every rank must issue the same collectives: a trainable tensor without a gradient contributes zeros
                 for i, p in enumerate(self.params):
