@@ -238,6 +238,16 @@ int nrf_mlp_backward_ex(const void* x, int x_dtype, const void* params_f16, cons
                         uint32_t width, int hidden_act, int out_act, float loss_scale, void* dx, int dx_dtype,
                         int dx_accumulate, float* dparams, void* stream);
 
+/* The four networks of the field (networks/style_nerf.py:120-142, use_dir=False: density 32->64->1 with trunc_exp,
+ * class 32->64->K, color1 32->64->16, color2 16->64->64->3 with sigmoid) in ONE launch -- same arithmetic and rounding
+ * points as four nrf_mlp_forward_ex calls, five MMA round trips per 128-point tile instead of nine (csrc/field_tc.cu).
+ * enc_d / enc_c f16 [M, 32]; w_*: f16, tcnn layout of the respective network; sigmas f32 [M]; rgbs f32 [M, ld_rgbs]
+ * (columns 0-2 rgb, 3..3+K class logits); c1_out f16 [M, 16] or NULL (color1's output, needed by the backward);
+ * M_dev: device int32 row count (or NULL) for the device-driven inference loop. */
+int nrf_field_forward(const void* enc_d, const void* enc_c, const void* w_density, const void* w_class, const void* w_color1,
+                      const void* w_color2, uint32_t M, uint32_t n_classes, float* sigmas, float* rgbs, uint32_t ld_rgbs,
+                      void* c1_out, const int32_t* M_dev, void* stream);
+
 /* fp32 PARITY MODE of the same network (SURVEY.md 8c "fp32 (parity mode)"): fp32 weights (same tcnn layout), fp32
  * activations and fp32 FMA accumulation, nothing rounded to f16 and therefore no loss_scale.  x is f32 or f16 (dx follows
  * it), y / dy are f32; ld_y / ld_dy / dx_accumulate / NRF_ACT_TRUNC_EXP as in the _ex forms.  Not a performance path: it

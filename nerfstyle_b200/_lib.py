@@ -61,6 +61,7 @@ SIGNATURES = {
     'nrf_mlp_forward_ex': (_i32, [_vp, _i32, _vp, _u32, _u32, _u32, _u32, _u32, _i32, _i32, _vp, _i32, _u32, _vp]),
     'nrf_mlp_backward_ex': (_i32, [_vp, _i32, _vp, _vp, _i32, _u32, _u32, _u32, _u32, _u32, _u32, _i32, _i32, _f32, _vp, _i32,
                                    _i32, _vp, _vp]),
+    'nrf_field_forward': (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _u32, _vp, _vp, _vp]),
     'nrf_mlp_forward_f32': (_i32, [_vp, _i32, _vp, _u32, _u32, _u32, _u32, _u32, _i32, _i32, _vp, _u32, _vp]),
     'nrf_mlp_backward_f32': (_i32, [_vp, _i32, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _i32, _i32, _vp, _i32, _vp, _vp]),
     'nrf_march_rays_dev': (_i32, [_vp, _u32, _vp, _vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -100,6 +101,7 @@ EXTRA_SIGNATURES = {
     'nrf_grid_set_transpose_min': (None, [_i32]),
     'nrf_march_set_mode': (None, [_i32]),
     'nrf_mlp_set_mode': (None, [_i32]),
+    'nrf_mlp_get_mode': (_i32, []),
     'nrf_nnfm_set_mode': (None, [_i32]),
     'nrf_mlp_set_tuning': (None, [_i32, _i32]),
     'nrf_mlp_set_profile': (None, [_vp]),
@@ -118,7 +120,7 @@ KERNELS_PER_CALL = {
     'nrf_composite_rays': 1, 'nrf_compact_alive': 3, 'nrf_grid_encode_forward': 1, 'nrf_grid_encode_backward': 1, 'nrf_grid_encode_forward_dual': 1,
     'nrf_grid_encode_backward_dual': 1, 'nrf_grid_encode_forward_pair': 1, 'nrf_grid_encode_backward_pair': 1,
     'nrf_grid_initialize': 1, 'nrf_mlp_forward': 1, 'nrf_mlp_backward': 1, 'nrf_sh_encode_forward': 1, 'nrf_march_rays_dev': 1,
-    'nrf_composite_rays_dev': 1, 'nrf_compact_alive_dev': 4, 'nrf_grid_encode_forward_dual_dev': 1, 'nrf_mlp_forward_dev': 1, 'nrf_mlp_forward_ex': 1, 'nrf_mlp_backward_ex': 1, 'nrf_mlp_forward_f32': 1, 'nrf_mlp_backward_f32': 1, 'nrf_nnfm_forward': 5,
+    'nrf_composite_rays_dev': 1, 'nrf_compact_alive_dev': 4, 'nrf_grid_encode_forward_dual_dev': 1, 'nrf_mlp_forward_dev': 1, 'nrf_mlp_forward_ex': 1, 'nrf_mlp_backward_ex': 1, 'nrf_mlp_forward_f32': 1, 'nrf_field_forward': 1, 'nrf_mlp_backward_f32': 1, 'nrf_nnfm_forward': 5,
     'nrf_adam_step': 1, 'nrf_adam_step_ex': 1, 'nrf_adam_step_pair': 1, 'nrf_adam_step_pair_p2p': 1, 'nrf_small_allreduce_p2p': 1, 'nrf_grads_check': 1, 'nrf_scaler_update': 1, 'nrf_generate_rays': 1,
     'nrf_occ_points_full': 1, 'nrf_occ_points_sparse': 1, 'nrf_occ_flags': 1, 'nrf_occ_scatter_max': 1, 'nrf_occ_update': 2,
     'nrf_packbits_dev': 1, 'nrf_recon_loss': 1,

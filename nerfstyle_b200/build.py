@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libnerfstyle_b200.so')
 OBJ = os.path.join(HERE, 'build')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-SOURCES = ['raymarching.cu', 'gridencoder.cu', 'mlp.cu', 'mlp_tc.cu', 'mlp_f32.cu', 'nnfm.cu', 'nnfm_tc.cu', 'optim.cu', 'optim_p2p.cu', 'rays.cu', 'occupancy.cu', 'loss.cu']
+SOURCES = ['raymarching.cu', 'gridencoder.cu', 'mlp.cu', 'mlp_tc.cu', 'mlp_f32.cu', 'field_tc.cu', 'nnfm.cu', 'nnfm_tc.cu', 'optim.cu', 'optim_p2p.cu', 'rays.cu', 'occupancy.cu', 'loss.cu']
 FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
          '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr']
 

@@ -438,6 +438,7 @@ void nrf_mlp_tc_set_ctas(int fwd_per_sm, int bwd_per_sm);
 void nrf_mlp_tc_set_prof(unsigned long long* buf16);
 static int g_mlp_mode = 0;      // 0 = tcgen05 (mlp_tc.cu), 1 = mma.sync (this file)
 NRF_EXPORT void nrf_mlp_set_mode(int mode) { g_mlp_mode = mode; }
+NRF_EXPORT int nrf_mlp_get_mode(void) { return g_mlp_mode; }
 NRF_EXPORT void nrf_mlp_set_profile(void* device_buf_16_u64) { nrf_mlp_tc_set_prof((unsigned long long*)device_buf_16_u64); }
 NRF_EXPORT void nrf_mlp_set_tuning(int fwd_ctas_per_sm, int bwd_ctas_per_sm) { nrf_mlp_tc_set_ctas(fwd_ctas_per_sm, bwd_ctas_per_sm); }
 

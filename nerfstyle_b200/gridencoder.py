@@ -109,7 +109,7 @@ class _grid_encode_dual(Function):
     @staticmethod
     @custom_fwd(device_type='cuda')
     def forward(ctx, inputs, emb0, emb1, offsets, per_level_scale, base_resolution, gridtype, align_corners, style,
-                xform=None):
+                xform=None, pipeline=False):
         L.require_cuda(inputs, emb0, emb1, offsets, xform)
         inputs = inputs.contiguous()
         if inputs.dtype != torch.float32:
@@ -136,12 +136,28 @@ class _grid_encode_dual(Function):
         if pair is not None:
             out0 = torch.empty(B, Lv * C, device=inputs.device, dtype=pair.dtype)
             out1 = torch.empty_like(out0)
+            esz = out0.element_size() * Lv * C
+            chunks = _pipeline_chunks(B) if pipeline else [(0, B)]
+            ready = []
             with torch.cuda.device(inputs.device):
-                L.check(L.lib().nrf_grid_encode_forward_pair(L.ptr(inputs), L.ptr(pair), L.ptr(offsets), L.ptr(out0), L.ptr(out1),
-                                                             B, Lv, S, H, int(gridtype), int(bool(align_corners)), int(style),
-                                                             L.dtype_code(pair.dtype), L.ptr(xform), None, None,
-                                                             L.stream_of(inputs)),
-                        'grid_encode_forward_pair')
+                main = torch.cuda.current_stream(inputs.device)
+                side = _side_stream(inputs.device) if len(chunks) > 1 else main
+                if side is not main:
+                    side.wait_stream(main)                   # inputs / tables / freshly allocated outputs are ordered on `main`
+                with torch.cuda.stream(side):
+                    for (r0, r1) in chunks:
+                        L.check(L.lib().nrf_grid_encode_forward_pair(inputs.data_ptr() + 12 * r0, L.ptr(pair), L.ptr(offsets),
+                                                                     out0.data_ptr() + esz * r0, out1.data_ptr() + esz * r0, r1 - r0, Lv, S, H,
+                                                                     int(gridtype), int(bool(align_corners)), int(style),
+                                                                     L.dtype_code(pair.dtype), L.ptr(xform), None, None, side.cuda_stream),
+                                'grid_encode_forward_pair')
+                        if side is not main:
+                            ev = torch.cuda.Event()
+                            ev.record(side)
+                            ready.append((r0, r1, ev))
+            # the consumer (tcnn.field_heads) makes `main` wait chunk by chunk, so the networks of chunk i run while chunk
+            # i + 1 is still being gathered; grid_encode_dual() hands the events over (or waits for them itself)
+            _last_ready[0] = ready
             ctx.save_for_backward(inputs, offsets, xform)
             ctx.meta = (B, Lv, S, H, gridtype, align_corners, style, pair.dtype, emb0.shape)
             return out0, out1
@@ -176,7 +192,7 @@ class _grid_encode_dual(Function):
         dev = inputs.device
         need = [bool(ctx.needs_input_grad[1]), bool(ctx.needs_input_grad[2])]
         if not any(need):
-            return None, None, None, None, None, None, None, None, None, None
+            return None, None, None, None, None, None, None, None, None, None, None
         gs = []
         for g in (g0, g1):
             if g is None:
@@ -193,7 +209,7 @@ class _grid_encode_dual(Function):
                                                               B, Lv, S, H, int(gridtype), int(bool(align_corners)), int(style),
                                                               L.dtype_code(dtype), L.ptr(xform), L.stream_of(inputs)),
                         'grid_encode_backward_pair')
-            return None, None, None, None, None, None, None, None, None, None
+            return None, None, None, None, None, None, None, None, None, None, None
         # a frozen table (requires_grad False, e.g. the density table of the stylization stage when the caller freezes it)
         # passes NULL: no zero fill, no reductions for it
         ge0 = torch.zeros(shape, dtype=torch.float32, device=dev) if need[0] else None
@@ -204,7 +220,7 @@ class _grid_encode_dual(Function):
                                                           int(gridtype), int(bool(align_corners)), int(style), L.dtype_code(dtype),
                                                           L.DTYPE_F32, L.ptr(xform), L.stream_of(inputs)),
                     'grid_encode_backward_dual')
-        return None, ge0, ge1, None, None, None, None, None, None, None
+        return None, ge0, ge1, None, None, None, None, None, None, None, None
 
 
 def same_geometry(a, b):
@@ -215,7 +231,46 @@ def same_geometry(a, b):
             and a.embeddings.shape == b.embeddings.shape and torch.equal(a.offsets, b.offsets))
 
 
-def grid_encode_dual(inputs, enc_a, enc_b, bound=1, style=0, xform=None):
+_last_ready = [None]   # [(row0, row1, event)] of the pipelined gather just launched by _grid_encode_dual.forward
+_side = {}
+
+
+def _side_stream(device):
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _side:
+        _side[key] = torch.cuda.Stream(device=device)
+    return _side[key]
+
+
+def _pipeline_chunks(B, min_rows=1 << 19, n=4):
+    """Row ranges (multiples of 128 rows) for the gather -> networks pipeline; one range when the batch is small."""
+    if B < 2 * min_rows:
+        return [(0, B)]
+    n = min(n, B // min_rows)
+    per = (B // n + 127) // 128 * 128
+    out, r = [], 0
+    while r < B:
+        out.append((r, min(B, r + per)))
+        r += per
+    return out
+
+
+def take_ready(t):
+    """The per-chunk completion events of an encoding produced with pipeline=True (and forget them), or None."""
+    ev = getattr(t, '_nrf_ready', None)
+    if ev is not None:
+        del t._nrf_ready
+    return ev
+
+
+def wait_ready(*tensors):
+    """Make the current stream wait for every gather chunk of these encodings (consumers that do not pipeline)."""
+    for t in tensors:
+        for (_, _, e) in (take_ready(t) or []):
+            torch.cuda.current_stream(t.device).wait_event(e)
+
+
+def grid_encode_dual(inputs, enc_a, enc_b, bound=1, style=0, xform=None, pipeline=False):
     """(enc_a(inputs, bound, style), enc_b(inputs, bound, style)) in one pass; the encoders must satisfy same_geometry().
     xform (device f32[7] = bbox_min, bbox_size, bound): `inputs` are RAW points and the kernel applies
     ((x - min) / size + bound) / (2 bound) itself (same f32 operations as the two Python lines it replaces)."""
@@ -223,8 +278,16 @@ def grid_encode_dual(inputs, enc_a, enc_b, bound=1, style=0, xform=None):
         inputs = (inputs + bound) / (2 * bound)          # GridEncoder.forward, grid.py:174
     prefix_shape = list(inputs.shape[:-1])
     inputs = inputs.reshape(-1, enc_a.input_dim)
+    _last_ready[0] = None
     o0, o1 = _grid_encode_dual.apply(inputs, enc_a.embeddings, enc_b.embeddings, enc_a.offsets, enc_a.per_level_scale,
-                                     enc_a.base_resolution, enc_a.gridtype_id, enc_a.align_corners, style, xform)
+                                     enc_a.base_resolution, enc_a.gridtype_id, enc_a.align_corners, style, xform, pipeline)
+    ready, _last_ready[0] = _last_ready[0], None
+    if ready:
+        if pipeline and len(prefix_shape) == 1:
+            o0._nrf_ready = o1._nrf_ready = ready        # consumed (and waited for) by tcnn.field_heads
+            return o0, o1
+        for (_, _, e) in ready:
+            torch.cuda.current_stream(o0.device).wait_event(e)
     return o0.view(prefix_shape + [enc_a.output_dim]), o1.view(prefix_shape + [enc_b.output_dim])
 
 

@@ -109,11 +109,13 @@ class StyleTCNerf(nn.Module):
                 self._xform = torch.cat([self.bbox_min, self.bbox_size, self.bbox_min.new_ones(1)]).contiguous()
             if self._dual and pts.dtype == torch.float32:
                 # one index computation for both hash tables; BBox.normalize + the encoder's input map run in the kernel
+                # pipeline=True: the gather runs chunk by chunk on a side stream and field_heads starts the networks of a
+                # chunk as soon as its encodings exist (the two kernels co-reside on the SMs: the gather holds no shared
+                # memory / TMEM)
                 x_embedded, x_color_embedded = grid_encode_dual(pts, self.x_density_embedder, self.x_color_embedder,
-                                                                xform=self._xform)
-                sigmas = tcnn.density_head(x_embedded, self.density_net)
-                rgbs = tcnn.color_heads(x_color_embedded, self.class_net, self.color1_net, self.color2_net)
-                return rgbs, sigmas
+                                                                xform=self._xform, pipeline=pts.dim() == 2)
+                return tcnn.field_heads(x_embedded, x_color_embedded, self.density_net, self.class_net, self.color1_net,
+                                        self.color2_net)
         pts = (pts - self.bbox_min) / self.bbox_size            # BBox.normalize, common.py:288
         if self.fused_heads and pts.is_cuda:
             if dirs is None:
@@ -122,9 +124,8 @@ class StyleTCNerf(nn.Module):
                 x_embedded, x_color_embedded = grid_encode_dual(pts, self.x_density_embedder, self.x_color_embedder)
             else:
                 x_embedded, x_color_embedded = self.x_density_embedder(pts), self.x_color_embedder(pts)
-            sigmas = tcnn.density_head(x_embedded, self.density_net)
-            rgbs = tcnn.color_heads(x_color_embedded, self.class_net, self.color1_net, self.color2_net)
-            return rgbs, sigmas
+            return tcnn.field_heads(x_embedded, x_color_embedded, self.density_net, self.class_net, self.color1_net,
+                                    self.color2_net)
         x_embedded = self.x_density_embedder(pts)
         density_output = self.density_net(x_embedded)
         sigmas = trunc_exp(density_output)
@@ -494,10 +495,16 @@ class Renderer(nn.Module):
                                             getattr(m, net).n_input_dims, n_out, getattr(m, net).n_hidden_layers, 64,
                                             getattr(m, net).hidden_act, act, y.data_ptr() + col * y.element_size(),
                                             L.dtype_code(y.dtype), y.shape[1], rows, s), 'mlp_forward_dev')
-        mlp('density_net', st['enc_d'], st['sigmas'], 0, 1, L.ACT['trunc_exp'])
-        mlp('color1_net', st['enc_c'], st['c1'], 0, 16, m.color1_net.out_act)
-        mlp('color2_net', st['c1'], st['rgbs'], 0, 3, m.color2_net.out_act)
-        mlp('class_net', st['enc_c'], st['rgbs'], 3, m.class_dim, m.class_net.out_act)
+        if tcnn._field_fusable(st['enc_d'], st['enc_c'], m.density_net, m.class_net, m.color1_net, m.color2_net) and lib.nrf_mlp_get_mode() == 0:
+            L.check(lib.nrf_field_forward(st['enc_d'].data_ptr(), st['enc_c'].data_ptr(), st['w']['density_net'].data_ptr(),
+                                          st['w']['class_net'].data_ptr(), st['w']['color1_net'].data_ptr(), st['w']['color2_net'].data_ptr(),
+                                          cap, m.class_dim, st['sigmas'].data_ptr(), st['rgbs'].data_ptr(), st['rgbs'].shape[1], None, rows, s),
+                    'field_forward')
+        else:
+            mlp('density_net', st['enc_d'], st['sigmas'], 0, 1, L.ACT['trunc_exp'])
+            mlp('color1_net', st['enc_c'], st['c1'], 0, 16, m.color1_net.out_act)
+            mlp('color2_net', st['c1'], st['rgbs'], 0, 3, m.color2_net.out_act)
+            mlp('class_net', st['enc_c'], st['rgbs'], 3, m.class_dim, m.class_net.out_act)
         if self.density_scale != 1.0:
             st['sigmas'].mul_(self.density_scale)
         L.check(lib.nrf_composite_rays_dev(ctl.data_ptr(), N, float(self.t_thresh), a_in.data_ptr(), st['rays_t'].data_ptr(),

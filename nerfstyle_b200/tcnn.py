@@ -260,6 +260,103 @@ class _color_heads(Function):
         return dx, dp_class, dp_c1, dp_c2, None, None, None
 
 
+def _field_fusable(enc_d, enc_c, density_net, class_net, color1_net, color2_net):
+    """The one-launch forward (csrc/field_tc.cu) covers exactly the reference's default field: f16 32-wide encodings,
+    density 32->64->1 / class 32->64->K / color1 32->64->16 (one hidden layer, linear out), color2 16->64->64->3 sigmoid."""
+    def shape(n, ni, no, nh, act):
+        return (n.n_input_dims, n.n_output_dims, n.n_hidden_layers, n.n_neurons, n.hidden_act, n.out_act) == (ni, no, nh, 64, _ACT['relu'], act)
+    return (not _parity and _fuse_field and enc_d.is_cuda and enc_d.dtype == torch.float16 and enc_c.dtype == torch.float16
+            and enc_d.shape == enc_c.shape and enc_d.shape[-1] == 32 and class_net.n_output_dims <= 16
+            and shape(density_net, 32, 1, 1, _ACT['none']) and shape(class_net, 32, class_net.n_output_dims, 1, _ACT['none'])
+            and shape(color1_net, 32, 16, 1, _ACT['none']) and shape(color2_net, 16, 3, 2, _ACT['sigmoid']))
+
+
+_fuse_field = True
+
+
+def set_field_fusion(on):
+    """False: the field heads run as four launches (density_head + color_heads) -- for A/B measurements and tests."""
+    global _fuse_field
+    _fuse_field = bool(on)
+
+
+class _field_heads(Function):
+    """(rgbs, sigmas) of the whole field head in ONE forward launch (nrf_field_forward); the backward is the four
+    tensor-core backward launches of _density_head / _color_heads on the saved encodings and color1 output."""
+
+    @staticmethod
+    def forward(ctx, enc_d, enc_c, p_density, p_class, p_c1, p_c2, density_net, class_net, color1_net, color2_net, ready=None):
+        L.require_cuda(enc_d, enc_c, p_density, p_class, p_c1, p_c2)
+        enc_d, enc_c = enc_d.contiguous(), enc_c.contiguous()
+        B, K = enc_d.shape[0], class_net.n_output_dims
+        hp = [half_params(p, n) for p, n in ((p_density, density_net), (p_class, class_net), (p_c1, color1_net), (p_c2, color2_net))]
+        sigmas = torch.empty(B, 1, dtype=torch.float32, device=enc_d.device)
+        rgbs = torch.empty(B, 3 + K, dtype=torch.float32, device=enc_d.device)
+        need_bwd = any(ctx.needs_input_grad[:6])
+        c1 = torch.empty(B, 16, dtype=torch.float16, device=enc_d.device) if need_bwd else None
+        with torch.cuda.device(enc_d.device):
+            main = torch.cuda.current_stream(enc_d.device)
+            # `ready`: the encodings are still being gathered chunk by chunk on a side stream (gridencoder pipeline=True);
+            # the networks of a chunk start as soon as that chunk's gather has finished
+            for (r0, r1, ev) in (ready or [(0, B, None)]):
+                if ev is not None:
+                    main.wait_event(ev)
+                L.check(L.lib().nrf_field_forward(enc_d.data_ptr() + 64 * r0, enc_c.data_ptr() + 64 * r0, L.ptr(hp[0]), L.ptr(hp[1]),
+                                                  L.ptr(hp[2]), L.ptr(hp[3]), r1 - r0, K, sigmas.data_ptr() + 4 * r0,
+                                                  rgbs.data_ptr() + 4 * (3 + K) * r0, 3 + K, (c1.data_ptr() + 32 * r0) if c1 is not None else None,
+                                                  None, main.cuda_stream), 'field_forward')
+        if need_bwd:
+            ctx.save_for_backward(enc_d, enc_c, c1, *hp)
+        ctx.nets = (density_net, class_net, color1_net, color2_net)
+        ctx.need = ctx.needs_input_grad[:6]
+        return rgbs, sigmas
+
+    @staticmethod
+    def backward(ctx, g_rgbs, g_sigmas):
+        enc_d, enc_c, c1, h_d, h_class, h_c1, h_c2 = ctx.saved_tensors
+        density_net, class_net, color1_net, color2_net = ctx.nets
+        K = class_net.n_output_dims
+        dev = enc_d.device
+        z = lambda h, need: torch.zeros(h.shape, dtype=torch.float32, device=dev) if need else None      # noqa: E731
+        dp_d, dp_class, dp_c1, dp_c2 = z(h_d, ctx.need[2]), z(h_class, ctx.need[3]), z(h_c1, ctx.need[4]), z(h_c2, ctx.need[5])
+        dx_d = dx_c = None
+        with torch.cuda.device(dev):
+            if g_sigmas is not None and (ctx.need[0] or ctx.need[2]):
+                g = g_sigmas.contiguous()
+                g = g if g.dtype in (torch.float16, torch.float32) else g.float()
+                dx_d = torch.empty_like(enc_d) if ctx.need[0] else None
+                _bwd_ex(density_net, enc_d, h_d, g, 0, 1, L.ACT['trunc_exp'], dx_d, False, dp_d)
+            if g_rgbs is not None and any(ctx.need[i] for i in (1, 3, 4, 5)):
+                g = g_rgbs.contiguous()
+                g = g if g.dtype in (torch.float16, torch.float32) else g.float()
+                need_dx = ctx.need[1]
+                dc1 = torch.empty_like(c1) if (need_dx or ctx.need[4]) else None
+                dx_c = torch.empty_like(enc_c) if need_dx else None
+                if dc1 is not None or dp_c2 is not None:
+                    _bwd_ex(color2_net, c1, h_c2, g, 0, 3, color2_net.out_act, dc1, False, dp_c2)
+                if dc1 is not None:
+                    _bwd_ex(color1_net, enc_c, h_c1, dc1, 0, 16, color1_net.out_act, dx_c, False, dp_c1)
+                if dx_c is not None or dp_class is not None:
+                    _bwd_ex(class_net, enc_c, h_class, g, 3, K, class_net.out_act, dx_c, dx_c is not None, dp_class)
+        return dx_d, dx_c, dp_d, dp_class, dp_c1, dp_c2, None, None, None, None, None
+
+
+def field_heads(enc_d, enc_c, density_net, class_net, color1_net, color2_net):
+    """(rgbs f32 [B, 3 + K], sigmas f32 [B, 1]) = (cat(color2(color1(enc_c)), class(enc_c)), trunc_exp(density(enc_d))):
+    one launch when the networks have the reference's default shapes, else density_head + color_heads."""
+    from .gridencoder import take_ready, wait_ready
+    if _field_fusable(enc_d, enc_c, density_net, class_net, color1_net, color2_net) and enc_d.dim() == 2 \
+            and L.lib().nrf_mlp_get_mode() == 0:
+        ready = take_ready(enc_d)
+        take_ready(enc_c)
+        return _field_heads.apply(enc_d, enc_c, density_net.params, class_net.params, color1_net.params, color2_net.params,
+                                  density_net, class_net, color1_net, color2_net, ready)
+    wait_ready(enc_d, enc_c)
+    enc_d = enc_d.reshape(-1, density_net.n_input_dims)
+    enc_c = enc_c.reshape(-1, class_net.n_input_dims)
+    return color_heads(enc_c, class_net, color1_net, color2_net), density_head(enc_d, density_net)
+
+
 def density_head(enc, net):
     """trunc_exp(net(enc)) fused (f32 [B, 1])."""
     return _density_head.apply(enc.reshape(-1, net.n_input_dims), net.params, net)

@@ -177,3 +177,46 @@ def test_half_param_cache_is_scoped(cuda_lib, dev):
         assert a is b
     c = tcnn.half_params(net.params, net)
     assert c is not a
+
+
+@pytest.mark.parametrize('B', [5000, 128, 77])
+def test_field_forward_one_launch_equals_four(cuda_lib, dev, B, mlp_impl):
+    """nrf_field_forward (csrc/field_tc.cu: the four networks of the field in one tcgen05 launch, five MMA round trips
+    per tile) against the four nrf_mlp_forward_ex launches it replaces: colour / class outputs bit-identical (same MMA
+    sequences, the stacked / block-diagonal operands only add exact zeros), density within one f16 ulp of the
+    pre-activation (its single output is a 64-term f32 dot product on the CUDA cores: another summation order), and the
+    same gradients through the shared backward."""
+    from nerfstyle_b200 import tcnn
+    if mlp_impl != 'tcgen05':
+        pytest.skip('the one-launch field forward exists on the tcgen05 implementation only')
+    K = 8
+    mk = lambda ni, no, nh, act, seed: tcnn.Network(ni, no, {'otype': 'FullyFusedMLP', 'activation': 'ReLU', 'output_activation': act,      # noqa: E731
+                                                            'n_neurons': 64, 'n_hidden_layers': nh}, seed=seed).to(dev)
+    density, cls, c1n, c2n = mk(32, 1, 1, 'None', 1), mk(32, K, 1, 'None', 2), mk(32, 16, 1, 'None', 3), mk(16, 3, 2, 'Sigmoid', 4)
+    g = torch.Generator().manual_seed(B)
+    outs = []
+    for fused in (True, False):
+        tcnn.set_field_fusion(fused)
+        try:
+            ed = (torch.randn(B, 32, generator=torch.Generator().manual_seed(B)) * 0.5).to(dev).half().requires_grad_(True)
+            ec = (torch.randn(B, 32, generator=torch.Generator().manual_seed(B + 1)) * 0.5).to(dev).half().requires_grad_(True)
+            for n in (density, cls, c1n, c2n):
+                n.params.grad = None
+            rgbs, sigmas = tcnn.field_heads(ed, ec, density, cls, c1n, c2n)
+            assert rgbs.shape == (B, 3 + K) and sigmas.shape == (B, 1) and rgbs.dtype == sigmas.dtype == torch.float32
+            gr = (torch.randn(B, 3 + K, generator=torch.Generator().manual_seed(7)) * 0.1).to(dev)
+            gs = (torch.randn(B, 1, generator=torch.Generator().manual_seed(8)) * 0.1).to(dev)
+            torch.autograd.backward([rgbs, sigmas], [gr * 128.0, gs * 128.0])
+            outs.append((rgbs.detach(), sigmas.detach(), ed.grad.clone(), ec.grad.clone(),
+                         [n.params.grad.clone() for n in (density, cls, c1n, c2n)]))
+        finally:
+            tcnn.set_field_fusion(True)
+    (ra, sa, da, ca, pa), (rb, sb, db, cb, pb) = outs
+    assert torch.equal(ra, rb)
+    rel = ((sa - sb).abs() / sb.abs()).flatten()
+    # (identical f16 pre-activations can still differ in the last f32 bit of the exp: separately compiled __expf)
+    assert float(rel.max()) <= 2.0 ** -9 and float((rel > 1e-5).float().mean()) < 0.01, (float(rel.max()), float((rel > 1e-5).float().mean()))
+    assert torch.equal(ca, cb)                                     # colour-side input gradient: identical saved tensors
+    assert float((da - db).abs().max()) <= 1e-3 * float(db.abs().max())      # density backward sees sigma-independent inputs
+    for x, y in zip(pa, pb):
+        assert float((x - y).abs().max()) <= 1e-5 * float(y.abs().max()) + 1e-8   # float-atomic flush order only
