@@ -46,6 +46,7 @@ def parse():
     ap.add_argument('--skip-cpu-baseline', action='store_true')
     ap.add_argument('--skip-ref-ext', action='store_true')
     ap.add_argument('--skip-extras', action='store_true')
+    ap.add_argument('--skip-strong', action='store_true')
     return ap.parse_args()
 
 
@@ -302,6 +303,30 @@ def run_ours(args):
     e2e_s = float(t.item())
     clk = clocks.stop()
 
+    # -------- strong-scaling point: a FIXED global batch of 65 536 rays per step split over the ranks (the default line
+    # above is weak scaling: 8192 rays per GPU).  Same trainer state, 2 warm-up + 6 timed steps, device-resident inputs.
+    strong = None
+    if not args.skip_strong:
+        g_rays = 65536
+        per = g_rays // world
+        _, sb = make_batches(8, per, rank, world, device)
+        for s in range(2):
+            ts.step(*unpack(sb[s]))
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for s in range(2, 8):
+            ts.step(*unpack(sb[s]))
+        s1.record()
+        barrier()
+        t = torch.tensor([s0.elapsed_time(s1)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sms = float(t.item()) / 6
+        strong = {'global_rays_per_step': g_rays, 'rays_per_gpu_per_step': per, 'steps': 6, 'ms_per_step': round(sms, 4),
+                  'value': round(g_rays / (sms / 1e3), 1), 'unit': 'rays/s', 'scaling': 'strong'}
+        del sb
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -334,6 +359,9 @@ def run_ours(args):
                     'traffic_source': (traffic.get(top) or {}).get('source'), 'peak_source': peak_src,
                     'algorithmic_bytes_per_point': ALGO_BYTES[top][amp], 'points_per_launch': v['units'] / v['calls'],
                     'us_per_launch': round(sec_per_launch * 1e6, 1),
+                    'hbm_frac_actual': (round((traffic.get(top) or {}).get('dram_bytes_per_launch') / sec_per_launch / 1e9 / hbm_peak, 4)
+                                        if (traffic.get(top) or {}).get('dram_bytes_per_launch') else None),
+                    'binding_counter': (traffic.get(top) or {}).get('binding_counter'),
                     'note': 'algorithmic bytes count every table row touched; both tables (and most of their f32 gradients) stay '
                             'L2-resident, so real DRAM traffic (`traffic`) is far lower and frac can exceed 1 -- ncu shows the '
                             'scatter bound by the LSU data pipe (warp shuffles + reductions), profiles/r01f_ncu_kernels.md'}
@@ -361,6 +389,8 @@ def run_ours(args):
         'final_loss': lv,
         'cuda_mallocs_in_timed_region': int(seg1 - seg0),
     }
+    if strong is not None:
+        line['strong_scaling'] = strong
     if world > 1:
         # exchange time per step (CUDA events around every collective / peer-memory kernel on the stream it is issued on,
         # instrumented pass).  Peer-memory path (default): `barrier` (all ranks' gradients complete), `p2p_small` (MLP
@@ -384,7 +414,9 @@ def run_ours(args):
     if world == 1 and not args.skip_ref_ext:
         try:
             from bench_ref_ext import time_reference_ext
-            line['reference_cuda_ext'] = time_reference_ext(args.rays, min(K, 10), device)
+            line['reference_cuda_ext'] = time_reference_ext(args.rays, 16, device)
+            from bench_ref_ext import time_reference_ext_render
+            line['reference_cuda_ext']['render_full_frame'] = time_reference_ext_render(1008, 756, device)
         except Exception as e:      # the rebuilt reference extensions are optional evidence
             line['reference_cuda_ext'] = {'unavailable': '%s: %s' % (type(e).__name__, str(e)[:200])}
     print(json.dumps(line))
