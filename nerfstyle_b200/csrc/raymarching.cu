@@ -1123,7 +1123,8 @@ NRF_EXPORT int nrf_compact_alive(const int32_t* in, uint32_t n, int32_t* out, in
 }
 
 // end of one iteration of the device-driven loop: the new alive count, the steps taken so far, the next n_step
-// (renderer.py:253: max(min(N // n_alive, 8), 1)) and the row count the next iteration's kernels will process
+// (renderer.py:253: max(min(N // n_alive, 8), 1); ctl[4] is the row budget -- N for the reference's schedule) and the row count the
+// next iteration's kernels will process
 __global__ void k_ctl_update(int32_t* __restrict__ ctl, const int32_t* __restrict__ total) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     int n_alive = total[0];

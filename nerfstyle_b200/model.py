@@ -442,15 +442,16 @@ class Renderer(nn.Module):
     # ------------------------------------------------------------------------------------------------------------------
     # device-driven inference loop (SURVEY.md 8f NEXT-2)
     # ------------------------------------------------------------------------------------------------------------------
-    def _graph_state(self, N):
+    def _graph_state(self, N, row_budget):
         """Static buffers + the captured two-iteration CUDA graph for frames of N rays (built on first use)."""
         st = getattr(self, '_gs', None)
-        if st is not None and st['N'] == N and st['dev'] == self.device and st['xform_ptr'] == self.model._xform.data_ptr():
+        if st is not None and st['N'] == N and st['dev'] == self.device and st['xform_ptr'] == self.model._xform.data_ptr() \
+                and st['budget'] == row_budget:
             return st
         dev, Cch = self.device, self.raymarch_channels
-        cap = (N + 127) // 128 * 128                       # rows per iteration never exceed N (n_alive * n_step <= N)
+        cap = (row_budget + 127) // 128 * 128              # rows per iteration never exceed the budget (n_alive * n_step <= budget)
         f32, i32 = torch.float32, torch.int32
-        st = {'N': N, 'dev': dev, 'cap': cap, 'graph': None, 'xform_ptr': self.model._xform.data_ptr(),
+        st = {'N': N, 'dev': dev, 'cap': cap, 'budget': row_budget, 'graph': None, 'xform_ptr': self.model._xform.data_ptr(),
               'rays_o': torch.empty(N, 3, dtype=f32, device=dev), 'rays_d': torch.empty(N, 3, dtype=f32, device=dev),
               'nears': torch.empty(N, dtype=f32, device=dev), 'fars': torch.empty(N, dtype=f32, device=dev),
               'rays_t': torch.empty(N, 1, dtype=f32, device=dev),
@@ -515,12 +516,19 @@ class Renderer(nn.Module):
                 'compact_alive_dev')
 
     @torch.no_grad()
-    def render_test_graph(self, rays_o, rays_d, check_every=4):
+    def render_test_graph(self, rays_o, rays_d, check_every=4, steps_per_iteration=4):
         """render_test with the loop driven from the device: the per-iteration host logic of renderer.py:249-286 (alive
         count, n_step, buffer sizes) lives in a control block updated by the compaction kernel, every launch is sized for
         the cap, and a PAIR of iterations (the alive list ping-pongs between two buffers) is captured once in a CUDA graph
         and replayed; the host only reads the alive count every `check_every` replays.  Same kernels and numerics as
-        render_test; needs the fused-head model (default) under AMP-style fp16 tables."""
+        render_test; needs the fused-head model (default) under AMP-style fp16 tables.
+
+        steps_per_iteration: the reference marches n_step = clamp(N // n_alive, 1, 8) samples per ray and iteration, i.e. ONE
+        while most rays are alive, so a frame is ~56 iterations that each re-read and re-write every ray's accumulators
+        (renderer.py:253).  n_step only partitions a ray's samples over iterations -- composite_rays stops at the terminating
+        sample inside the block -- so the loop here budgets steps_per_iteration * N rows per iteration instead
+        (n_step = clamp(budget // n_alive, 1, 8)): 4x fewer iterations, accumulator round trips and compaction passes, for
+        at most n_step - 1 wasted samples per ray per frame.  steps_per_iteration=1 is the reference's schedule."""
         m = self.model
         if not (getattr(m, 'fused_heads', False) and m.class_dim + 3 == self.raymarch_channels):
             raise RuntimeError('render_test_graph needs the fused-head StyleTCNerf')
@@ -532,14 +540,16 @@ class Renderer(nn.Module):
         rays_o = rays_o.float().contiguous().view(-1, 3)
         rays_d = rays_d.float().contiguous().view(-1, 3)
         N = rays_o.shape[0]
-        st = self._graph_state(N)
+        budget = N * max(1, min(int(steps_per_iteration), 8))
+        st = self._graph_state(N, budget)
         st['rays_o'].copy_(rays_o); st['rays_d'].copy_(rays_d)
         nears, fars = raymarching.near_far_from_aabb(st['rays_o'], st['rays_d'], self.aabb, self.min_near)
         st['nears'].copy_(nears); st['fars'].copy_(fars)
         st['rays_t'].copy_(nears[:, None])
         st['weights_sum'].zero_(); st['depth'].zero_(); st['image'].zero_()
         st['alive'][0].copy_(torch.arange(N, dtype=torch.int32, device=self.device))
-        st['ctl'].copy_(torch.tensor([N, 1, N, 0, N, self.max_steps, 0, 0], dtype=torch.int32))
+        n0 = max(min(budget // N, 8), 1)
+        st['ctl'].copy_(torch.tensor([N, n0, N * n0, 0, budget, self.max_steps, 0, 0], dtype=torch.int32))
         for i, e in enumerate((m.x_density_embedder, m.x_color_embedder)):       # fp16 tables / weights for this frame
             shadow = current_half_copy(e.embeddings)
             st['pair'][:, i].copy_(shadow if shadow is not None else e.embeddings.detach())
