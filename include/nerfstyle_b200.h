@@ -270,6 +270,7 @@ int nrf_mlp_backward_f32(const void* x, int x_dtype, const float* params_f32, co
  * stop.  Kernels and numerics are those of nrf_march_rays / nrf_composite_rays / nrf_compact_alive /
  * nrf_grid_encode_forward_dual / nrf_mlp_forward_ex; rows >= ctl[2] are left untouched.  row_deltas (the [B,4] deltas of
  * march_rays, or NULL) lets the encoder skip padding slots (delta == 0: composite_rays never reads them). */
+/* (dirs may be NULL in nrf_march_rays_dev: a field without a direction input never reads them) */
 int nrf_march_rays_dev(const int32_t* ctl, uint32_t n_alive_cap, const int32_t* rays_alive, const float* rays_t,
                        const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C,
                        uint32_t H, const uint8_t* grid, const float* fars, float* xyzs, float* dirs, float* deltas,

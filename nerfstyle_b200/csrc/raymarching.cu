@@ -892,7 +892,7 @@ k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays
             const uint32_t total_threads = gridDim.x * blockDim.x;
             for (uint32_t i = n_alive * n_step + (n - n_alive); i < Mpad; i += total_threads - n_alive) {
                 xyzs[3 * (size_t)i] = 0; xyzs[3 * (size_t)i + 1] = 0; xyzs[3 * (size_t)i + 2] = 0;
-                dirs[3 * (size_t)i] = 0; dirs[3 * (size_t)i + 1] = 0; dirs[3 * (size_t)i + 2] = 0;
+                if (dirs) { dirs[3 * (size_t)i] = 0; dirs[3 * (size_t)i + 1] = 0; dirs[3 * (size_t)i + 2] = 0; }
                 reinterpret_cast<float4*>(deltas)[i] = make_float4(0, 0, 0, 0);
             }
         }
@@ -900,16 +900,16 @@ k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays
     }
     const int32_t index = rays_alive[n];
     float* px = xyzs + 3 * (size_t)n * n_step;
-    float* pd = dirs + 3 * (size_t)n * n_step;
+    float* pd = dirs ? dirs + 3 * (size_t)n * n_step : nullptr;      // NULL: the field has no direction input
     float4* pl = reinterpret_cast<float4*>(deltas) + (size_t)n * n_step;
     uint32_t step = 0;
     if (index < 0) {
         // extension: a dead slot (-1) left in the list by a caller that compacts without reading the count back every
         // iteration (Renderer.render_test of the host mirror); its rows are zero so that composite_rays skips them
         for (; step < n_step; step++) {
-            px[0] = 0; px[1] = 0; px[2] = 0; pd[0] = 0; pd[1] = 0; pd[2] = 0;
+            px[0] = 0; px[1] = 0; px[2] = 0; if (pd) { pd[0] = 0; pd[1] = 0; pd[2] = 0; }
             *pl = make_float4(0, 0, 0, 0);
-            px += 3; pd += 3; pl += 1;
+            px += 3; if (pd) pd += 3; pl += 1;
         }
         return;
     }
@@ -925,7 +925,7 @@ k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays
     while (t < far && step < n_step) {
         if (march_visit(c, grid, t, x, y, z, dt)) {
             px[0] = x; px[1] = y; px[2] = z;
-            pd[0] = c.dx; pd[1] = c.dy; pd[2] = c.dz;
+            if (pd) { pd[0] = c.dx; pd[1] = c.dy; pd[2] = c.dz; }
             t = __fadd_rn(t, dt);
             float4 dl = make_float4(dt, __fsub_rn(t, last_t), 0.0f, 0.0f);
             if (is_ndc) {   // raymarching.cu:1094-1099 (inference updates last_z = new_z)
@@ -936,14 +936,91 @@ k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays
             }
             last_t = t;
             *pl = dl;
-            px += 3; pd += 3; pl += 1; step++;
+            px += 3; if (pd) pd += 3; pl += 1; step++;
         }
     }
     if (zero_fill) {
         for (; step < n_step; step++) {
-            px[0] = 0; px[1] = 0; px[2] = 0; pd[0] = 0; pd[1] = 0; pd[2] = 0;
+            px[0] = 0; px[1] = 0; px[2] = 0; if (pd) { pd[0] = 0; pd[1] = 0; pd[2] = 0; }
+            *pl = make_float4(0, 0, 0, 0);
+            px += 3; if (pd) pd += 3; pl += 1;
+        }
+    }
+}
+
+// Block-staged form of k_march_rays for n_step > 1 (non-NDC): a block's 128 consecutive alive slots own ONE contiguous span
+// of the output (rows [128 b n_step, 128 (b + 1) n_step)), so every ray writes its samples into shared memory and the block
+// then stores the span with full 16-byte coalesced writes -- the per-thread version writes 12-byte pieces n_step * 12 bytes
+// apart.  Same marching state machine, same values.
+#define MRB_THREADS 128
+#define MRB_MAX_STEP 8
+__global__ void __launch_bounds__(MRB_THREADS)
+k_march_rays_blk(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays_alive, const float* __restrict__ rays_t,
+                 const float* __restrict__ rays_o, const float* __restrict__ rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                 uint32_t C, uint32_t H, const uint8_t* __restrict__ grid, const float* __restrict__ fars, float* __restrict__ xyzs,
+                 float* __restrict__ dirs, float* __restrict__ deltas, const float* __restrict__ noises, const int32_t* __restrict__ ctl) {
+    __shared__ __align__(16) float s_xyz[MRB_THREADS * MRB_MAX_STEP * 3];
+    __shared__ __align__(16) float s_dir[MRB_THREADS * MRB_MAX_STEP * 3];
+    __shared__ __align__(16) float4 s_del[MRB_THREADS * MRB_MAX_STEP];
+    if (ctl) { n_alive = (uint32_t)ctl[0]; n_step = (uint32_t)ctl[1]; }
+    const uint32_t n0 = blockIdx.x * MRB_THREADS;
+    if (n0 >= n_alive) return;
+    const uint32_t n = n0 + threadIdx.x;
+    const uint32_t rays_here = min((uint32_t)MRB_THREADS, n_alive - n0);
+    if (n < n_alive) {
+        const int32_t index = rays_alive[n];
+        float* px = s_xyz + 3 * threadIdx.x * n_step;
+        float* pd = s_dir + 3 * threadIdx.x * n_step;
+        float4* pl = s_del + threadIdx.x * n_step;
+        uint32_t step = 0;
+        if (index >= 0) {
+            MarchCtx c;
+            march_init(c, rays_o + 3 * (size_t)index, rays_d + 3 * (size_t)index, bound, dt_gamma, max_steps, C, H);
+            float t = rays_t[index];
+            const float far = fars[index];
+            t = march_t0(c, t, noises ? noises[n] : 0.0f);
+            float last_t = t;
+            float x, y, z, dt;
+            while (t < far && step < n_step) {
+                if (march_visit(c, grid, t, x, y, z, dt)) {
+                    px[0] = x; px[1] = y; px[2] = z;
+                    if (dirs) { pd[0] = c.dx; pd[1] = c.dy; pd[2] = c.dz; }
+                    t = __fadd_rn(t, dt);
+                    *pl = make_float4(dt, __fsub_rn(t, last_t), 0.0f, 0.0f);
+                    last_t = t;
+                    px += 3; pd += 3; pl += 1; step++;
+                }
+            }
+        }
+        for (; step < n_step; step++) {       // unused slots (ray left the volume / dead slot) are zero: composite_rays stops at them
+            px[0] = 0; px[1] = 0; px[2] = 0;
+            if (dirs) { pd[0] = 0; pd[1] = 0; pd[2] = 0; }
             *pl = make_float4(0, 0, 0, 0);
             px += 3; pd += 3; pl += 1;
+        }
+    }
+    __syncthreads();
+    // coalesced copy-out of the block's span: rows [n0 * n_step, (n0 + rays_here) * n_step)
+    const size_t row0 = (size_t)n0 * n_step;
+    const uint32_t rows = rays_here * n_step;
+    float4* gd = reinterpret_cast<float4*>(deltas) + row0;
+    for (uint32_t i = threadIdx.x; i < rows; i += MRB_THREADS) gd[i] = s_del[i];
+    // 3 floats per row: the span starts at float 3 * row0 (16-byte aligned because row0 is a multiple of 128 * n_step ... of 4)
+    const uint32_t nf = rows * 3;
+    float* gx = xyzs + 3 * row0;
+    if ((((uintptr_t)gx) & 15) == 0) {
+        for (uint32_t i = threadIdx.x; i < nf / 4; i += MRB_THREADS) reinterpret_cast<float4*>(gx)[i] = reinterpret_cast<const float4*>(s_xyz)[i];
+        for (uint32_t i = (nf / 4) * 4 + threadIdx.x; i < nf; i += MRB_THREADS) gx[i] = s_xyz[i];
+    } else {
+        for (uint32_t i = threadIdx.x; i < nf; i += MRB_THREADS) gx[i] = s_xyz[i];
+    }
+    if (dirs) {
+        float* gdr = dirs + 3 * row0;
+        if ((((uintptr_t)gdr) & 15) == 0) {
+            for (uint32_t i = threadIdx.x; i < nf / 4; i += MRB_THREADS) reinterpret_cast<float4*>(gdr)[i] = reinterpret_cast<const float4*>(s_dir)[i];
+            for (uint32_t i = (nf / 4) * 4 + threadIdx.x; i < nf; i += MRB_THREADS) gdr[i] = s_dir[i];
+        } else {
+            for (uint32_t i = threadIdx.x; i < nf; i += MRB_THREADS) gdr[i] = s_dir[i];
         }
     }
 }
@@ -960,6 +1037,13 @@ NRF_EXPORT int nrf_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* 
     if (is_ndc && !z_hats) return NRF_E_INVALID;
     if ((uint64_t)n_alive * n_step > Mpad) return NRF_E_INVALID;
     const uint32_t pad = Mpad - n_alive * n_step;
+    if (!is_ndc && n_step >= 2 && n_step <= MRB_MAX_STEP && n_alive > 0) {
+        k_march_rays_blk<<<ceil_div_u32(n_alive, MRB_THREADS), MRB_THREADS, 0, (cudaStream_t)stream>>>(n_alive, n_step, rays_alive, rays_t, rays_o,
+                                                                                                   rays_d, bound, dt_gamma, max_steps, C, H, grid,
+                                                                                                   fars, xyzs, dirs, deltas, noises, nullptr);
+        if (zero_fill && pad) k_zero_rows<<<ceil_div_u32(pad, 256), 256, 0, (cudaStream_t)stream>>>(xyzs, dirs, deltas, n_alive * n_step, Mpad);
+        return nrf_check_launch();
+    }
     const uint32_t threads = n_alive + (zero_fill ? min(pad, 4096u) : 0u);
     if (threads == 0) return NRF_OK;
     k_march_rays<<<ceil_div_u32(threads, 128), 128, 0, (cudaStream_t)stream>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d,
@@ -978,12 +1062,13 @@ NRF_EXPORT int nrf_march_rays_dev(const int32_t* ctl, uint32_t n_alive_cap, cons
                                   const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C,
                                   uint32_t H, const uint8_t* grid, const float* fars, float* xyzs, float* dirs, float* deltas,
                                   void* stream) {
-    if (!ctl || !rays_alive || !rays_t || !rays_o || !rays_d || !grid || !fars || !xyzs || !dirs || !deltas) return NRF_E_INVALID;
+    if (!ctl || !rays_alive || !rays_t || !rays_o || !rays_d || !grid || !fars || !xyzs || !deltas) return NRF_E_INVALID;      // dirs may be NULL
     if ((((uintptr_t)deltas) & 15) != 0) return NRF_E_INVALID;
     if (n_alive_cap == 0) return NRF_OK;
-    k_march_rays<<<ceil_div_u32(n_alive_cap, 128), 128, 0, (cudaStream_t)stream>>>(n_alive_cap, 1, rays_alive, rays_t, rays_o, rays_d, nullptr,
-                                                                                 bound, dt_gamma, max_steps, false, C, H, grid, fars, xyzs,
-                                                                                 dirs, deltas, nullptr, 0, true, ctl);
+    // n_step (device-side, <= 8) is not known to the host: the block-staged kernel handles every n_step
+    k_march_rays_blk<<<ceil_div_u32(n_alive_cap, MRB_THREADS), MRB_THREADS, 0, (cudaStream_t)stream>>>(n_alive_cap, 1, rays_alive, rays_t, rays_o, rays_d,
+                                                                                                  bound, dt_gamma, max_steps, C, H, grid, fars, xyzs,
+                                                                                                  dirs, deltas, nullptr, ctl);
     return nrf_check_launch();
 }
 

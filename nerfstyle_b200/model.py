@@ -484,7 +484,7 @@ class Renderer(nn.Module):
         L.check(lib.nrf_march_rays_dev(ctl.data_ptr(), N, a_in.data_ptr(), st['rays_t'].data_ptr(), st['rays_o'].data_ptr(),
                                        st['rays_d'].data_ptr(), float(self.bound), 0.0, int(self.max_steps), int(self.cascade),
                                        int(self.grid_size), self.density_bitfield.data_ptr(), st['fars'].data_ptr(),
-                                       st['xyzs'].data_ptr(), st['dirs'].data_ptr(), st['deltas'].data_ptr(), s), 'march_rays_dev')
+                                       st['xyzs'].data_ptr(), None, st['deltas'].data_ptr(), s), 'march_rays_dev')      # no direction input
         L.check(lib.nrf_grid_encode_forward_pair(st['xyzs'].data_ptr(), st['pair'].data_ptr(), enc.offsets.data_ptr(),
                                                  st['enc_d'].data_ptr(), st['enc_c'].data_ptr(), cap, enc.num_levels, S,
                                                  int(enc.base_resolution), enc.gridtype_id, int(enc.align_corners), 0,
