@@ -327,6 +327,11 @@ def run_ours(args):
                   'value': round(g_rays / (sms / 1e3), 1), 'unit': 'rays/s', 'scaling': 'strong'}
         del sb
 
+    # -------- full-frame inference at N > 1 (BASELINE config 3: row tiles sharded over the ranks, image gathered on rank 0)
+    render_n = None
+    if world > 1 and not args.skip_extras:
+        render_n = render_sharded(device, rank, world)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -391,6 +396,8 @@ def run_ours(args):
     }
     if strong is not None:
         line['strong_scaling'] = strong
+    if render_n is not None:
+        line['render_full_frame'] = render_n
     if world > 1:
         # exchange time per step (CUDA events around every collective / peer-memory kernel on the stream it is issued on,
         # instrumented pass).  Peer-memory path (default): `barrier` (all ranks' gradients complete), `p2p_small` (MLP
@@ -425,6 +432,42 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------------ secondary measurements
+def render_sharded(device, rank, world, w=1008, h=756, frames=3):
+    """Config 3 at N GPUs: each rank renders a contiguous block of rows of the 1008 x 756 frame with the device-driven
+    loop, the tiles are gathered on rank 0 (39.6 MB); ms/frame = max over ranks, wall clock around render + gather."""
+    import torch
+    import torch.distributed as dist
+    from nerfstyle_b200 import model as M, parallel, raymarching, scenes
+    torch.manual_seed(0)
+    m = M.StyleTCNerf([-2., -2., -2.], [2., 2., 2.], class_dim=N_CLASSES).to(device)
+    r = M.Renderer(m, 2.0, raymarch_channels=3 + N_CLASSES, density_scale=50.0).to(device)
+    r.density_bitfield = raymarching.packbits(scenes.analytic_density_grid(2, 128, 2.0).to(device), 0.5)
+    intr = scenes.scaled_intrinsics(w, h)
+    poses = scenes.synthetic_poses(frames + 1, 1)
+    lo, hi = parallel.shard_bounds(w * h, rank, world)
+    idx = torch.arange(lo, hi, device=device)
+    ts = []
+    for f in range(frames + 1):
+        o, d = scenes.generate_rays(poses[f], intr, device, idx)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.no_grad(), torch.autocast('cuda', dtype=torch.float16):
+            img, depth, cls = r.render_test_graph(o, d)
+        full = parallel.gather_rows(torch.cat([img, depth[:, None], cls], dim=1), w * h, rank, world)
+        if rank == 0:
+            float(full[:, :3].sum().item())
+        dist.barrier()
+        torch.cuda.synchronize()
+        if f > 0:
+            ts.append(time.perf_counter() - t0)
+    t = torch.tensor([sum(ts) / len(ts)], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec = float(t.item())
+    return {'w': w, 'h': h, 'n_gpus': world, 'ms_per_frame': round(sec * 1e3, 2), 'mrays_per_s': round(w * h / sec / 1e6, 2),
+            'case': 'analytic occupancy, density_scale 50; row tiles sharded, image gathered on rank 0'}
+
+
 def extras(device, peaks):
     """The other two numbers BASELINE.json's metric names, measured in the same run (N = 1 only, a few seconds):
     full-frame render Mrays/s (config 3, trained-like case) and the tensor-core kernels against the measured bf16 peak."""
@@ -471,7 +514,20 @@ def extras(device, peaks):
     torch.cuda.synchronize()
     t = e0.elapsed_time(e1) / 10
     tf = 2.0 * N1 * N2 * K / t / 1e9
-    out['nnfm_matching'] = {'N1': N1, 'N2': N2, 'K': K, 'ms': round(t, 3),
+    # the reference's own composition (loss.py:32-36,199-214: fp16 matmul -> per-class inf mask loop -> amin), same operands
+    def torch_composition():
+        dists = 1.0 - a @ b.T
+        for i in range(8):
+            dists[torch.logical_and(*torch.meshgrid(preds == i, clusters != i, indexing='ij'))] = float('inf')
+        return torch.amin(dists, dim=1)
+    torch_composition()
+    e0.record()
+    for _ in range(3):
+        torch_composition()
+    e1.record()
+    torch.cuda.synchronize()
+    t_ref = e0.elapsed_time(e1) / 3
+    out['nnfm_matching'] = {'N1': N1, 'N2': N2, 'K': K, 'ms': round(t, 3), 'reference_torch_composition_ms': round(t_ref, 3),
                             'roofline': {'bound': 'tensor', 'achieved': round(tf, 1), 'peak': tf_peak, 'unit': 'TFLOP/s',
                                          'frac': round(tf / tf_peak, 4), 'kernel': 'k_nnfm_gemm_tc (tcgen05, incl. operand packing)'}}
     # ---- the fused MLPs (tcgen05): forward + backward of the density net on 4 Mi rows

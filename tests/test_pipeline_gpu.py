@@ -507,3 +507,81 @@ def test_occupancy_kernels_against_cpu_oracle(cuda_lib, oracle, dev):
     assert np.array_equal(grid.cpu().numpy().view(np.uint32), e_grid.view(np.uint32))
     assert abs(float(state[0]) - e_mean) <= 1e-6 * e_mean and abs(float(state[1]) - min(e_mean, 10.0)) <= 1e-6 * e_mean
     assert int((bits.cpu().numpy() != np.asarray(e_bits).reshape(-1)).sum()) <= 1
+
+
+def test_peer_memory_optimizer_kernels_on_one_gpu(cuda_lib, dev):
+    """The kernels of the fused data-parallel exchange (csrc/optim_p2p.cu) with the ranks emulated by several local
+    buffers (their "peer pointers" all point into this GPU's memory; no multicast object, so the rank-order load / store
+    loops run): nrf_adam_step_pair_p2p over W gradient buffers must equal nrf_adam_step_pair on their sum -- parameters,
+    both Adam moments, EMA bit for bit -- and must write the updated fp16 rows into EVERY rank's table copy;
+    nrf_small_allreduce_p2p must sum the small buffers in rank order and raise found-inf when any rank flagged it.
+    (The multi-process run over NVLink -- multimem.ld_reduce / multimem.st through the NVLS mapping -- is checked by
+    tools/check_sharded_optimizer.py under torchrun at N = 2 and N = 8: bit-identical to all-reduce + replicated Adam at N = 2.)"""
+    import struct
+    from nerfstyle_b200 import _lib as L
+    lib = L.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(5)
+    T, W = 40000, 3
+    row_lo, rows = 10000, 20000                                   # this "rank" owns rows [10000, 30000) of the pair buffers
+    grads = [torch.randn(T, 2, 2, generator=g).to(dev) * 512.0 for _ in range(W)]
+    halves = [torch.zeros(T, 2, 2, dtype=torch.float16, device=dev) for _ in range(W)]
+    total = grads[0].clone()
+    for q in grads[1:]:
+        total += q                                                # rank order, like the kernel's loop
+
+    def state(found_inf=0):
+        raw = struct.pack('fiii', 512.0, found_inf, 0, 7) + b'\\0' * (int(lib.nrf_opt_state_bytes()) - 16)
+        return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+
+    def fresh():
+        gg = torch.Generator().manual_seed(6)
+        mk = lambda: torch.randn(2 * rows, generator=gg).to(dev)             # noqa: E731  (shard-local tensors)
+        return {'p0': mk() * 0.1, 'p1': mk() * 0.1, 'm0': mk() * 0.01, 'm1': mk() * 0.01, 'v0': mk().abs() * 1e-3, 'v1': mk().abs() * 1e-3,
+                'e0': mk() * 0.1, 'e1': mk() * 0.1}
+    a, b = fresh(), fresh()
+    gp = torch.tensor([q.data_ptr() for q in grads], dtype=torch.int64, device=dev)
+    hp = torch.tensor([h.data_ptr() for h in halves], dtype=torch.int64, device=dev)
+    sa, sb = state(), state()
+    args = (0.01, 50.0, 0.9, 0.999, 1e-15, 0.05)
+    L.check(lib.nrf_adam_step_pair_p2p(a['p0'].data_ptr(), a['p1'].data_ptr(), gp.data_ptr(), None, hp.data_ptr(), None, W, row_lo,
+                                       a['m0'].data_ptr(), a['m1'].data_ptr(), a['v0'].data_ptr(), a['v1'].data_ptr(), a['e0'].data_ptr(),
+                                       a['e1'].data_ptr(), rows, sa.data_ptr(), *args, st), 'adam_step_pair_p2p')
+    ref_half = torch.zeros(rows, 2, 2, dtype=torch.float16, device=dev)
+    L.check(lib.nrf_adam_step_pair(b['p0'].data_ptr(), b['p1'].data_ptr(), total[row_lo:row_lo + rows].contiguous().data_ptr(),
+                                   b['m0'].data_ptr(), b['m1'].data_ptr(), b['v0'].data_ptr(), b['v1'].data_ptr(), b['e0'].data_ptr(),
+                                   b['e1'].data_ptr(), ref_half.data_ptr(), rows, sb.data_ptr(), *args, st), 'adam_step_pair')
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    for h in halves:                                              # the all-gather: every rank's copy got this shard's rows, nothing else
+        assert torch.equal(h[row_lo:row_lo + rows], ref_half)
+        assert float(h[:row_lo].abs().max()) == 0.0 and float(h[row_lo + rows:].abs().max()) == 0.0
+    assert float(ref_half.abs().max()) > 0
+    # found-inf on the state block skips the update (and the table writes) like nrf_adam_step_pair
+    c, sc = fresh(), state(found_inf=1)
+    before = {k: v.clone() for k, v in c.items()}
+    halves2 = [torch.zeros(T, 2, 2, dtype=torch.float16, device=dev)]
+    hp2 = torch.tensor([halves2[0].data_ptr()], dtype=torch.int64, device=dev)
+    L.check(lib.nrf_adam_step_pair_p2p(c['p0'].data_ptr(), c['p1'].data_ptr(), gp.data_ptr(), None, hp2.data_ptr(), None, 1, row_lo,
+                                       c['m0'].data_ptr(), c['m1'].data_ptr(), c['v0'].data_ptr(), c['v1'].data_ptr(), c['e0'].data_ptr(),
+                                       c['e1'].data_ptr(), rows, sc.data_ptr(), *args, st), 'adam_step_pair_p2p')
+    for k in ('p0', 'p1', 'm0', 'm1', 'v0', 'v1'):
+        assert torch.equal(c[k], before[k]), k
+    assert float(halves2[0].abs().max()) == 0.0
+    # ---- small tensors + flag
+    n = 3077
+    bufs = [torch.randn(n + 8, generator=g).to(dev) for _ in range(W)]
+    for q in bufs:
+        q[n:] = 0.0
+    sp = torch.tensor([q.data_ptr() for q in bufs], dtype=torch.int64, device=dev)
+    out = torch.empty(n, device=dev)
+    s0 = state()
+    L.check(lib.nrf_small_allreduce_p2p(sp.data_ptr(), W, n, out.data_ptr(), s0.data_ptr(), st), 'small_allreduce_p2p')
+    want = bufs[0][:n].clone()
+    for q in bufs[1:]:
+        want += q[:n]
+    assert torch.equal(out, want)
+    assert int(s0[4:8].view(torch.int32)) == 0
+    bufs[1][n] = 1.0                                              # rank 1 saw an inf
+    L.check(lib.nrf_small_allreduce_p2p(sp.data_ptr(), W, n, out.data_ptr(), s0.data_ptr(), st), 'small_allreduce_p2p')
+    assert int(s0[4:8].view(torch.int32)) == 1
