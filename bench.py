@@ -218,7 +218,7 @@ def run_ours(args):
                'nrf_grid_encode_backward_dual', 'nrf_grid_encode_forward_pair', 'nrf_grid_encode_backward_pair', 'nrf_mlp_forward', 'nrf_mlp_backward',
                'nrf_mlp_forward_ex', 'nrf_mlp_backward_ex', 'nrf_field_forward',
                'nrf_composite_rays_train_forward', 'nrf_composite_rays_train_backward', 'nrf_composite_rays_train_backward_ex',
-               'nrf_march_rays_train_count',
+               'nrf_march_rays_train_count', 'nrf_march_rays_train_count_staged', 'nrf_march_rays_train_emit',
                'nrf_march_rays_train_write']
     timed_ops = ['nrf_grid_encode_forward', 'nrf_grid_encode_backward', 'nrf_grid_encode_forward_dual',
                  'nrf_grid_encode_backward_dual', 'nrf_grid_encode_forward_pair', 'nrf_grid_encode_backward_pair']

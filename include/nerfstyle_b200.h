@@ -108,6 +108,19 @@ int nrf_march_rays_train(const float* rays_o, const float* rays_d, const float* 
                          float* deltas, int32_t* rays, int32_t* counter, const float* noises, void* scratch,
                          void* stream);
 
+/* Staged marching (no second walk of the occupancy grid): the count pass records the marching time of every emitted sample
+ * in t_stage [N, max_steps] f32; after the host has read the total (the contract's D2H read) and allocated the outputs,
+ * nrf_march_rays_train_emit produces xyzs / dirs / deltas from those times -- bit-identical to nrf_march_rays_train_write.
+ * Warp-per-ray walker, non-NDC only (NRF_E_UNSUPPORTED otherwise: use _count + _write). */
+int nrf_march_rays_train_count_staged(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                                      float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                      const float* nears, const float* fars, const float* noises, int32_t* rays,
+                                      int32_t* counter, void* scratch, float* t_stage, void* stream);
+int nrf_march_rays_train_emit(const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t N,
+                              uint32_t C, uint32_t H, uint32_t M, uint32_t rows, uint32_t zero_from, const float* nears,
+                              const float* noises, const int32_t* rays, const float* t_stage, float* xyzs, float* dirs,
+                              float* deltas, void* stream);
+
 /* raymarching.cu:807-879.  sigmas [M], rgbs [M,C], deltas [M,4], rays [N,3] ->
  * weights_sum [N], depth [N], image [N,C] (all f32). */
 int nrf_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas,

@@ -32,6 +32,10 @@ SIGNATURES = {
                                           _vp, _vp]),
     'nrf_march_rays_train_write': (_i32, [_vp, _vp, _vp, _vp, _f32, _f32, _u32, _i32, _u32, _u32, _u32, _u32, _u32,
                                           _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'nrf_march_rays_train_count_staged': (_i32, [_vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp,
+                                                 _vp, _vp, _vp]),
+    'nrf_march_rays_train_emit': (_i32, [_vp, _vp, _f32, _f32, _u32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp,
+                                         _vp, _vp]),
     'nrf_march_rays_train': (_i32, [_vp, _vp, _vp, _vp, _f32, _f32, _u32, _i32, _u32, _u32, _u32, _u32, _vp, _vp, _vp,
                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'nrf_composite_rays_train_forward': (_i32, [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _f32, _i32, _vp, _vp, _vp, _vp]),
@@ -115,7 +119,7 @@ _lib = None
 # kernels launched per C call (lower bound; used for the `gpu_launches` claim of bench.py)
 KERNELS_PER_CALL = {
     'nrf_near_far_from_aabb': 1, 'nrf_sph_from_ray': 1, 'nrf_morton3D': 1, 'nrf_morton3D_invert': 1, 'nrf_packbits': 1,
-    'nrf_march_rays_train_count': 4, 'nrf_march_rays_train_write': 1, 'nrf_march_rays_train': 4,
+    'nrf_march_rays_train_count': 4, 'nrf_march_rays_train_write': 1, 'nrf_march_rays_train_count_staged': 4, 'nrf_march_rays_train_emit': 1, 'nrf_march_rays_train': 4,
     'nrf_composite_rays_train_forward': 1, 'nrf_composite_rays_train_backward': 1, 'nrf_composite_rays_train_backward_ex': 1, 'nrf_march_rays': 1,
     'nrf_composite_rays': 1, 'nrf_compact_alive': 3, 'nrf_grid_encode_forward': 1, 'nrf_grid_encode_backward': 1, 'nrf_grid_encode_forward_dual': 1,
     'nrf_grid_encode_backward_dual': 1, 'nrf_grid_encode_forward_pair': 1, 'nrf_grid_encode_backward_pair': 1,

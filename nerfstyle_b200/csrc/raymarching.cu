@@ -272,7 +272,11 @@ __global__ void __launch_bounds__(MW_WARPS * 32)
 k_march_warp(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const uint8_t* __restrict__ grid,
              float bound, float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, uint32_t rows,
              const float* __restrict__ nears, const float* __restrict__ fars, const float* __restrict__ noises,
-             int32_t* __restrict__ rays, float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas) {
+             int32_t* __restrict__ rays, float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
+             float* __restrict__ t_stage) {
+    // t_stage (count pass only, or NULL): [N, max_steps] -- the marching time of every sample the ray emits, in order.  A
+    // sample is a pure function of its time (x = clamp(fma(d, t, o)), dt = clamp(t dt_gamma), delta = t_after - previous
+    // t_after), so the second pass need not walk the occupancy grid again: k_march_emit streams these times back.
     __shared__ float s_t[MW_WARPS][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t n = blockIdx.x * MW_WARPS + wib;
@@ -347,6 +351,7 @@ k_march_warp(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
             }
             if (E) last_t = __shfl_sync(NRF_FULL_MASK, t_after, 31 - __clz(E));
         }
+        if (!WRITE && t_stage && ((E >> lane) & 1u)) t_stage[(size_t)n * max_steps + count + __popc(E & lt_mask)] = my_t;
         count += __popc(E);
         if (finished) break;
         const int Lv = 31 - __clz(V);                       // V != 0: lane 0 is valid inside the loop
@@ -475,10 +480,32 @@ NRF_EXPORT uint64_t nrf_march_scratch_bytes(uint32_t N) {
     return ((uint64_t)ceil_div_u32(N, MARCH_BLOCK) + 1024) * sizeof(uint32_t);
 }
 
+static int march_count_impl(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma, uint32_t max_steps,
+                            uint32_t N, uint32_t C, uint32_t H, const float* nears, const float* fars, const float* noises, int32_t* rays,
+                            int32_t* counter, void* scratch, float* t_stage, void* stream);
+
 NRF_EXPORT int nrf_march_rays_train_count(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
                                           float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
                                           const float* nears, const float* fars, const float* noises,
                                           int32_t* rays, int32_t* counter, void* scratch, void* stream) {
+    return march_count_impl(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, counter, scratch, nullptr,
+                            stream);
+}
+
+// Count pass that also records the marching time of every emitted sample in t_stage [N, max_steps] f32 (warp-per-ray
+// walker only); nrf_march_rays_train_emit then produces the samples without a second walk of the occupancy grid.
+NRF_EXPORT int nrf_march_rays_train_count_staged(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                                                 float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                                 const float* nears, const float* fars, const float* noises, int32_t* rays,
+                                                 int32_t* counter, void* scratch, float* t_stage, void* stream) {
+    if (!t_stage || !g_march_warp_per_ray) return NRF_E_UNSUPPORTED;
+    return march_count_impl(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars, noises, rays, counter, scratch, t_stage,
+                            stream);
+}
+
+static int march_count_impl(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma, uint32_t max_steps,
+                            uint32_t N, uint32_t C, uint32_t H, const float* nears, const float* fars, const float* noises, int32_t* rays,
+                            int32_t* counter, void* scratch, float* t_stage, void* stream) {
     if (N == 0) return NRF_OK;
     if (!rays_o || !rays_d || !grid || !nears || !fars || !rays || !scratch) return NRF_E_INVALID;
     if (C < 1 || C > 24 || H < 1 || H > 1024) return NRF_E_INVALID;
@@ -486,7 +513,7 @@ NRF_EXPORT int nrf_march_rays_train_count(const float* rays_o, const float* rays
     uint32_t* block_sums = (uint32_t*)scratch;
     if (g_march_warp_per_ray) {
         k_march_warp<false><<<ceil_div_u32(N, MW_WARPS), MW_WARPS * 32, 0, s>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H,
-                                                                              0, 0, nears, fars, noises, rays, nullptr, nullptr, nullptr);
+                                                                              0, 0, nears, fars, noises, rays, nullptr, nullptr, nullptr, t_stage);
         const uint32_t nb = ceil_div_u32(N, SCAN_BLOCK);
         k_scan_counts_local<<<nb, SCAN_BLOCK, 0, s>>>(rays, N, block_sums);
         k_scan_block_sums<<<1, 1024, 0, s>>>(block_sums, nb, counter, N);
@@ -577,12 +604,68 @@ NRF_EXPORT int nrf_march_rays_train_write(const float* rays_o, const float* rays
     if (g_march_warp_per_ray && !is_ndc) {
         k_march_warp<true><<<ceil_div_u32(N, MW_WARPS), MW_WARPS * 32, 0, s>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M,
                                                                              rows, nears, fars, noises, const_cast<int32_t*>(rays), xyzs, dirs,
-                                                                             deltas);
+                                                                             deltas, nullptr);
         return nrf_check_launch();
     }
     k_march_write<<<ceil_div_u32(N, MARCH_BLOCK), MARCH_BLOCK, 0, s>>>(rays_o, rays_d, z_hats, grid, bound, dt_gamma, max_steps,
                                                                   is_ndc != 0, N, C, H, M, rows, nears, fars, noises, rays,
                                                                   xyzs, dirs, deltas);
+    return nrf_check_launch();
+}
+
+// Second pass of the staged marching: warp per ray, lane j produces sample j, j + 32, ... from its recorded time.  The same
+// float operations as the walker's write pass (k_march_warp<true>): x = clamp(fma(d, t, o)), dt = clamp(t dt_gamma),
+// t_after = t + dt, delta = (dt, t_after - previous t_after | t0) -- bit-identical samples, no occupancy lookups.
+__global__ void __launch_bounds__(MW_WARPS * 32)
+k_march_emit(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t N,
+             uint32_t C, uint32_t H, uint32_t M, uint32_t rows, const float* __restrict__ nears, const float* __restrict__ noises,
+             const int32_t* __restrict__ rays, const float* __restrict__ t_stage, float* __restrict__ xyzs, float* __restrict__ dirs,
+             float* __restrict__ deltas) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t n = blockIdx.x * MW_WARPS + (threadIdx.x >> 5);
+    if (n >= N) return;
+    const uint32_t point_index = (uint32_t)rays[3 * (size_t)n + 1], count = (uint32_t)rays[3 * (size_t)n + 2];
+    if (count == 0) return;
+    if (point_index + count >= M) {      // dropped ray (raymarching.cu:517): its slots stay zero
+        for (uint32_t i = point_index + lane; i < min(point_index + count, rows); i += 32) {
+            xyzs[3 * (size_t)i] = 0; xyzs[3 * (size_t)i + 1] = 0; xyzs[3 * (size_t)i + 2] = 0;
+            if (dirs) { dirs[3 * (size_t)i] = 0; dirs[3 * (size_t)i + 1] = 0; dirs[3 * (size_t)i + 2] = 0; }
+            reinterpret_cast<float4*>(deltas)[i] = make_float4(0, 0, 0, 0);
+        }
+        return;
+    }
+    MarchCtx c;
+    march_init(c, rays_o + 3 * (size_t)n, rays_d + 3 * (size_t)n, bound, dt_gamma, max_steps, C, H);
+    const float t0 = march_t0(c, nears[n], noises ? noises[n] : 0.0f);
+    const float* ts = t_stage + (size_t)n * max_steps;
+    for (uint32_t j = lane; j < count; j += 32) {
+        const float t = __ldg(ts + j);
+        const float x = nrf_clamp(__fmaf_rn(c.dx, t, c.ox), c.nbound, c.bound);
+        const float y = nrf_clamp(__fmaf_rn(c.dy, t, c.oy), c.nbound, c.bound);
+        const float z = nrf_clamp(__fmaf_rn(c.dz, t, c.oz), c.nbound, c.bound);
+        const float dt = nrf_clamp(__fmul_rn(t, c.dt_gamma), c.dt_min, c.dt_max);
+        const float t_after = __fadd_rn(t, dt);
+        float prev = t0;
+        if (j > 0) { const float tp = __ldg(ts + j - 1); prev = __fadd_rn(tp, nrf_clamp(__fmul_rn(tp, c.dt_gamma), c.dt_min, c.dt_max)); }
+        const size_t o = (size_t)point_index + j;
+        xyzs[3 * o] = x; xyzs[3 * o + 1] = y; xyzs[3 * o + 2] = z;
+        if (dirs) { dirs[3 * o] = c.dx; dirs[3 * o + 1] = c.dy; dirs[3 * o + 2] = c.dz; }
+        reinterpret_cast<float4*>(deltas)[o] = make_float4(dt, __fsub_rn(t_after, prev), 0.0f, 0.0f);
+    }
+}
+
+// Same arguments as nrf_march_rays_train_write minus the occupancy grid / fars (not needed) plus the staged times.
+NRF_EXPORT int nrf_march_rays_train_emit(const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t N,
+                                         uint32_t C, uint32_t H, uint32_t M, uint32_t rows, uint32_t zero_from, const float* nears,
+                                         const float* noises, const int32_t* rays, const float* t_stage, float* xyzs, float* dirs,
+                                         float* deltas, void* stream) {
+    if (N == 0) return NRF_OK;
+    if (!rays_o || !rays_d || !nears || !rays || !t_stage || !xyzs || !dirs || !deltas) return NRF_E_INVALID;
+    if ((((uintptr_t)deltas) & 15) != 0) return NRF_E_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (zero_from < rows) k_zero_rows<<<ceil_div_u32(rows - zero_from, 256), 256, 0, s>>>(xyzs, dirs, deltas, zero_from, rows);
+    k_march_emit<<<ceil_div_u32(N, MW_WARPS), MW_WARPS * 32, 0, s>>>(rays_o, rays_d, bound, dt_gamma, max_steps, N, C, H, M, rows, nears, noises,
+                                                                   rays, t_stage, xyzs, dirs, deltas);
     return nrf_check_launch();
 }
 

@@ -126,6 +126,19 @@ class _packbits(Function):
 packbits = _packbits.apply
 
 
+STAGED_MARCH = True       # False: count pass + second DDA walk (nrf_march_rays_train_write), the round-1 form
+_stage = {}
+
+
+def _stage_buffer(dev, n):
+    """Per-device [N * max_steps] f32 staging buffer of the emitted samples' marching times (33 MB at 8192 rays)."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    buf = _stage.get(key)
+    if buf is None or buf.numel() < n:
+        buf = _stage[key] = torch.empty(n, dtype=torch.float32, device=dev)
+    return buf
+
+
 class _march_rays_train(Function):
     """raymarching.py:174-288 -> raymarching.cu:411-589.
 
@@ -163,13 +176,27 @@ class _march_rays_train(Function):
         noises = None  # perturb is hard-disabled in the reference (raymarching.py:247)
         lib = L.lib()
         scratch = L.scratch(dev, lib.nrf_march_scratch_bytes(N))
+        # staged marching: the count pass records every emitted sample's time, the second pass streams them back instead of
+        # walking the occupancy grid again (csrc/raymarching.cu: k_march_emit); NDC keeps the two-walk form
+        staged = (not is_ndc) and STAGED_MARCH and N * max_steps <= (1 << 29)
+        t_stage = _stage_buffer(dev, N * max_steps) if staged else None
         with torch.cuda.device(dev):
             st = L.stream_of(rays_o)
             counter_before = step_counter[:1].clone()
-            L.check(lib.nrf_march_rays_train_count(L.ptr(rays_o), L.ptr(rays_d), L.ptr(density_bitfield), float(bound),
-                                                   float(dt_gamma), int(max_steps), N, int(C), int(H), L.ptr(nears),
-                                                   L.ptr(fars), L.ptr(noises), L.ptr(rays), L.ptr(step_counter),
-                                                   L.ptr(scratch), st), 'march_rays_train(count)')
+            if staged:
+                rc = lib.nrf_march_rays_train_count_staged(L.ptr(rays_o), L.ptr(rays_d), L.ptr(density_bitfield), float(bound),
+                                                           float(dt_gamma), int(max_steps), N, int(C), int(H), L.ptr(nears),
+                                                           L.ptr(fars), L.ptr(noises), L.ptr(rays), L.ptr(step_counter),
+                                                           L.ptr(scratch), L.ptr(t_stage), st)
+                if rc == -2:          # NRF_E_UNSUPPORTED (thread-per-ray mode selected): two-walk form
+                    staged = False
+                else:
+                    L.check(rc, 'march_rays_train(count, staged)')
+            if not staged:
+                L.check(lib.nrf_march_rays_train_count(L.ptr(rays_o), L.ptr(rays_d), L.ptr(density_bitfield), float(bound),
+                                                       float(dt_gamma), int(max_steps), N, int(C), int(H), L.ptr(nears),
+                                                       L.ptr(fars), L.ptr(noises), L.ptr(rays), L.ptr(step_counter),
+                                                       L.ptr(scratch), st), 'march_rays_train(count)')
             if force_all_rays or mean_count <= 0:
                 # the contract's D2H read (one copy: [count before, count after])
                 base, m = torch.cat([counter_before, step_counter[:1]]).tolist()
@@ -187,7 +214,12 @@ class _march_rays_train(Function):
                 zero_from = rows
             elif rows > 0 and base > 0:   # caller did not zero the counter: rows below the base stay zero
                 xyzs[:base].zero_(), dirs[:base].zero_(), deltas[:base].zero_()
-            if N > 0 and rows > 0:
+            if N > 0 and rows > 0 and staged:
+                L.check(lib.nrf_march_rays_train_emit(L.ptr(rays_o), L.ptr(rays_d), float(bound), float(dt_gamma), int(max_steps), N,
+                                                      int(C), int(H), M, rows, min(zero_from, rows), L.ptr(nears), L.ptr(noises),
+                                                      L.ptr(rays), L.ptr(t_stage), L.ptr(xyzs), L.ptr(dirs), L.ptr(deltas), st),
+                        'march_rays_train(emit)')
+            elif N > 0 and rows > 0:
                 L.check(lib.nrf_march_rays_train_write(L.ptr(rays_o), L.ptr(rays_d), L.ptr(z_hats),
                                                        L.ptr(density_bitfield), float(bound), float(dt_gamma),
                                                        int(max_steps), int(bool(is_ndc)), N, int(C), int(H), M, rows,
