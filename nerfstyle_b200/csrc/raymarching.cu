@@ -710,22 +710,33 @@ k_composite_train_fwd(const float* __restrict__ sigmas, const float* __restrict_
     float ws = 0.0f, d = 0.0f;
     if (num_steps != 0 && offset + num_steps < M) {
         float T_run = 1.0f, t_run = 0.0f;
+        // software pipeline: the loads of block k + 1 are issued before the scans of block k (the blocks of a ray are a serial
+        // chain -- T_run / t_run -- so without the prefetch every block pays a full memory round trip)
+        float4 n_dl = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        float n_sigma = 0.0f;
+        float n_rgb[CMAX];
+        auto fetch = [&](uint32_t base) {
+            const uint32_t i = base + lane;
+            n_dl = make_float4(0.0f, 0.0f, 0.0f, 0.0f); n_sigma = 0.0f;
+#pragma unroll
+            for (int c = 0; c < CMAX; c++) n_rgb[c] = 0.0f;
+            if (i < num_steps) {
+                n_dl = __ldg(reinterpret_cast<const float4*>(deltas) + offset + i);
+                n_sigma = __ldg(sigmas + offset + i);
+                const float* r = rgbs + (size_t)(offset + i) * C;
+#pragma unroll
+                for (int c = 0; c < CMAX; c++) if (c < (int)C) n_rgb[c] = __ldg(r + c);
+            }
+        };
+        fetch(0);
         for (uint32_t base = 0; base < num_steps; base += 32) {
             const uint32_t i = base + lane;
             const bool valid = i < num_steps;
-            float sigma = 0.0f, d0 = 0.0f, d1 = 0.0f;
+            const float sigma = n_sigma, d0 = is_ndc ? n_dl.z : n_dl.x, d1 = is_ndc ? n_dl.w : n_dl.y;
             float rgb[CMAX];
-            if (valid) {
-                // every load of the block is issued before the scans below (one memory round trip per 32 samples; the
-                // rgb row used to be fetched only after the weights were known -- a second, dependent round trip)
-                const float4 dl = __ldg(reinterpret_cast<const float4*>(deltas) + offset + i);
-                sigma = __ldg(sigmas + offset + i);
-                const float* r = rgbs + (size_t)(offset + i) * C;
 #pragma unroll
-                for (int c = 0; c < CMAX; c++) rgb[c] = (c < (int)C) ? __ldg(r + c) : 0.0f;
-                d0 = is_ndc ? dl.z : dl.x;
-                d1 = is_ndc ? dl.w : dl.y;
-            }
+            for (int c = 0; c < CMAX; c++) rgb[c] = n_rgb[c];
+            if (base + 32 < num_steps) fetch(base + 32);
             const float alpha = valid ? alpha_from(sigma, d0) : 0.0f;
             const float P = warp_scan_mul(1.0f - alpha, lane);            // inclusive product
             float Pex = __shfl_up_sync(NRF_FULL_MASK, P, 1);
@@ -833,23 +844,32 @@ k_composite_train_bwd(const float* __restrict__ grad_ws, const float* __restrict
     }
     const float ws_term = __ldg(grad_ws + index) * (1.0f - __ldg(weights_sum + index));
     float T_run = 1.0f, pre_run = 0.0f;
+    // software pipeline, as in the forward: block k + 1 is in flight while block k is scanned
+    float4 n_dl = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float n_sigma = 0.0f;
+    float n_rgb[CMAX];
+    auto fetch = [&](uint32_t base) {
+        const uint32_t i = base + lane;
+        n_dl = make_float4(0.0f, 0.0f, 0.0f, 0.0f); n_sigma = 0.0f;
+#pragma unroll
+        for (int c = 0; c < CMAX; c++) n_rgb[c] = 0.0f;
+        if (i < num_steps) {
+            n_dl = __ldg(reinterpret_cast<const float4*>(deltas) + offset + i);
+            n_sigma = __ldg(sigmas + offset + i);
+            const float* r = rgbs + (size_t)(offset + i) * C;
+#pragma unroll
+            for (int c = 0; c < CMAX; c++) if (c < (int)C) n_rgb[c] = __ldg(r + c);
+        }
+    };
+    fetch(0);
     for (uint32_t base = 0; base < num_steps; base += 32) {
         const uint32_t i = base + lane;
         const bool valid = i < num_steps;
-        float sigma = 0.0f, d0 = 0.0f;
-        float rgb[CMAX];
+        const float sigma = n_sigma, d0 = is_ndc ? n_dl.z : n_dl.x;
         float gdot = 0.0f;    // g . rgb_i
-        if (valid) {
-            const float4 dl = __ldg(reinterpret_cast<const float4*>(deltas) + offset + i);
-            sigma = __ldg(sigmas + offset + i);
-            d0 = is_ndc ? dl.z : dl.x;
-            const float* r = rgbs + (size_t)(offset + i) * C;
 #pragma unroll
-            for (int c = 0; c < CMAX; c++) {
-                rgb[c] = (c < (int)C) ? __ldg(r + c) : 0.0f;
-                gdot = __fmaf_rn(g[c], rgb[c], gdot);
-            }
-        }
+        for (int c = 0; c < CMAX; c++) gdot = __fmaf_rn(g[c], n_rgb[c], gdot);
+        if (base + 32 < num_steps) fetch(base + 32);
         const float alpha = valid ? alpha_from(sigma, d0) : 0.0f;
         const float P = warp_scan_mul(1.0f - alpha, lane);
         float Pex = __shfl_up_sync(NRF_FULL_MASK, P, 1);
