@@ -207,3 +207,15 @@ def test_fused_optimizer_ownership_and_freshness_on_cpu(cuda_lib):
     o3 = FusedAdamEMA([a, w, b], lr=[0.01, 0.005, 0.01])
     assert o3.lrs == [0.01, 0.005, 0.01] and o3.pair_idx == (0, 2)
     assert FusedAdamEMA([a, w, b], lr=[0.01, 0.005, 0.02]).pair_idx is None         # paired tables share one fused pass
+
+
+def test_pipeline_chunks_cover_all_rows():
+    """gridencoder._pipeline_chunks: the row ranges of the gather -> networks pipeline partition [0, B), start on multiples of
+    128 rows (the networks' tile size) and collapse to one range for small batches."""
+    from nerfstyle_b200.gridencoder import _pipeline_chunks
+    for B in (0, 1, 127, 1 << 19, (1 << 20) - 1, 1 << 20, 4_139_648, 4_430_363, 33_000_001):
+        ch = _pipeline_chunks(B)
+        assert ch[0][0] == 0 and ch[-1][1] == B
+        assert all(a[1] == b[0] for a, b in zip(ch[:-1], ch[1:]))
+        assert all(r0 % 128 == 0 for r0, _ in ch)
+        assert len(ch) == (1 if B < (1 << 20) else min(4, B >> 19))

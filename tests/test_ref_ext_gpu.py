@@ -259,3 +259,55 @@ def test_grid_initialize_matches_reference_ext(cuda_lib, oracle, dev, ref_ge):
             single = counts[slots - lo] == 1                                         # uncontested slots: one possible value
             assert bool((t[slots[single]] == ref_tab[srcs[single]]).all()), (name, lvl)
     assert n_contested > 1000                                                        # the race is really exercised
+
+
+@pytest.mark.parametrize('kind', ['analytic', 'bernoulli'])
+def test_inference_loop_matches_reference_ext(cuda_lib, dev, ref_rm, kind):
+    """R6 / R7 against the reference BINARY: the loop of renderer.py:237-293 driven twice in lock step -- once on the
+    reference's `march_rays` / `composite_rays` kernels (oracle/_ref), once on this library's (the block-staged march for
+    n_step >= 2, the register-resident image row in composite_rays) -- with the same analytic sigma / rgb field in between.
+    Sample positions, deltas and the alive sets must be identical at every iteration (n_step grows from 1 to 8 as rays die)
+    and the accumulators equal to f32 rounding."""
+    from nerfstyle_b200 import raymarching
+    o, d, grid, bits, aabb = _scene(dev, N=6000, kind=kind)
+    N, Cch = o.shape[0], 11
+    nears, fars = raymarching.near_far_from_aabb(o, d, aabb, 0.2)
+    zh = torch.tensor((), device=dev)
+
+    def field(xyz):
+        sig = 25.0 * (1.0 + torch.sin(5.0 * xyz[:, 0]) * torch.cos(3.0 * xyz[:, 1] + xyz[:, 2]))
+        rgb = 0.5 + 0.5 * torch.sin(xyz @ torch.linspace(0.3, 2.9, 3 * Cch, device=dev).view(3, Cch))
+        return sig.contiguous(), rgb.contiguous()
+    st = []
+    for _ in range(2):
+        st.append({'ws': torch.zeros(N, device=dev), 'depth': torch.zeros(N, device=dev), 'image': torch.zeros(N, Cch, device=dev),
+                   'alive': torch.arange(N, dtype=torch.int32, device=dev), 'rays_t': nears.clone()[:, None].contiguous()})
+    ours, ref = st
+    step, iters, seen_steps = 0, 0, set()
+    while step < 1024:
+        n_alive = len(ours['alive'])
+        assert n_alive == len(ref['alive'])
+        if n_alive <= 0:
+            break
+        n_step = max(min(N // n_alive, 8), 1)
+        seen_steps.add(n_step)
+        xyzs, dirs, deltas = raymarching.march_rays(n_alive, n_step, ours['alive'], ours['rays_t'], o, d, None, 2.0, bits, 2, 128, nears, fars,
+                                                    128, False, 0., 1024, False)
+        Mp = xyzs.shape[0]
+        rx, rd, rl = torch.zeros(Mp, 3, device=dev), torch.zeros(Mp, 3, device=dev), torch.zeros(Mp, 4, device=dev)
+        ref_rm.march_rays(n_alive, n_step, ref['alive'], ref['rays_t'], o, d, zh, 2.0, 0.0, 1024, False, 2, 128, bits, nears, fars, rx, rd, rl,
+                          torch.zeros(n_alive, device=dev))
+        assert torch.equal(xyzs, rx) and torch.equal(dirs, rd) and torch.equal(deltas, rl), (iters, n_step)
+        sig, rgb = field(xyzs)
+        raymarching.composite_rays(n_alive, n_step, ours['alive'], ours['rays_t'], sig, rgb, deltas, False, ours['ws'], ours['depth'],
+                                   ours['image'], 1e-4)
+        ref_rm.composite_rays(n_alive, n_step, 1e-4, ref['alive'], ref['rays_t'], sig, rgb, rl, Cch, False, ref['ws'], ref['depth'], ref['image'])
+        assert torch.equal(ours['alive'], ref['alive']), iters                     # who died this iteration
+        assert torch.equal(ours['rays_t'], ref['rays_t']), iters
+        for k in ('ws', 'depth', 'image'):
+            assert float((ours[k] - ref[k]).abs().max()) <= 2e-6 * max(1.0, float(ref[k].abs().max())), (k, iters)
+        for s in (ours, ref):
+            s['alive'] = s['alive'][s['alive'] >= 0]
+        step += n_step
+        iters += 1
+    assert iters > 10 and len(seen_steps) >= 3 and float(ours['ws'].max()) > 0.5
