@@ -405,6 +405,7 @@ class FusedAdamEMA:
     def grad_pair_buffer(self):
         """The interleaved gradient buffer the paired scatter accumulates into (called by the dual encoder's backward)."""
         self._require_alive()
+        self.wait_pending_gather()       # peer ranks may still be reading last step's gradients (peer-memory exchange)
         a = self.params[self.pair_idx[0]]
         if self.grad_pair is None:
             self.grad_pair = torch.zeros(a.shape[0], 2, 2, dtype=torch.float32, device=a.device)
