@@ -280,7 +280,9 @@ int nrf_mlp_backward_f32(const void* x, int x_dtype, const float* params_f32, co
  * n_step = max(min(N / n_alive, 8), 1) as renderer.py:253, n_alive = 0 once max_steps is reached).  Every launch is sized
  * for the caps (n_alive_cap = N rays, B_cap >= N rows since n_alive * n_step <= N), so an iteration is shape-static and
  * can be captured in a CUDA graph and replayed with no host involvement; the host reads ctl[0] every few iterations to
- * stop.  Kernels and numerics are those of nrf_march_rays / nrf_composite_rays / nrf_compact_alive /
+ * stop.  ctl[4] is the row budget of an iteration (n_step = clamp(ctl[4] / n_alive, 1, 8); N = the reference's schedule);
+ * ctl[7] = 1 selects STEP-MAJOR sample rows (sample s of alive slot n in row s * n_alive + n instead of n * n_step + s):
+ * nrf_march_rays_dev then writes and nrf_composite_rays_dev reads consecutive rows from consecutive lanes.  Kernels and numerics are those of nrf_march_rays / nrf_composite_rays / nrf_compact_alive /
  * nrf_grid_encode_forward_dual / nrf_mlp_forward_ex; rows >= ctl[2] are left untouched.  row_deltas (the [B,4] deltas of
  * march_rays, or NULL) lets the encoder skip padding slots (delta == 0: composite_rays never reads them). */
 /* (dirs may be NULL in nrf_march_rays_dev: a field without a direction input never reads them) */

@@ -20,7 +20,7 @@ NRF_EXPORT const char* nrf_error_string(int code) {
     }
 }
 NRF_EXPORT int nrf_last_cuda_error(void) { return g_nrf_last_cuda_error; }
-NRF_EXPORT int nrf_version(void) { return 4; }   // 4: fp32 parity-mode MLP (nrf_mlp_*_f32); 3: paired tables, ray generation, occupancy update, loss head, _ex forms
+NRF_EXPORT int nrf_version(void) { return 5; }   // 5: field forward, staged march, peer-memory optimizer, step-major device loop; 4: fp32 parity-mode MLP (nrf_mlp_*_f32); 3: paired tables, ray generation, occupancy update, loss head, _ex forms
 NRF_EXPORT int nrf_device_info(int* sm_count, int* cc_major, int* cc_minor, int* l2_bytes) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -1070,6 +1070,40 @@ k_march_rays_blk(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ 
     if (n0 >= n_alive) return;
     const uint32_t n = n0 + threadIdx.x;
     const uint32_t rays_here = min((uint32_t)MRB_THREADS, n_alive - n0);
+    if (ctl && ctl[7] != 0) {
+        // STEP-MAJOR rows (device-driven loop only, ctl[7] = 1): sample s of alive slot n lives in row s * n_alive + n, so
+        // consecutive lanes write -- and composite_rays later reads -- consecutive rows: coalesced without staging
+        if (n >= n_alive) return;
+        const int32_t index = rays_alive[n];
+        uint32_t step = 0;
+        if (index >= 0) {
+            MarchCtx c;
+            march_init(c, rays_o + 3 * (size_t)index, rays_d + 3 * (size_t)index, bound, dt_gamma, max_steps, C, H);
+            float t = rays_t[index];
+            const float far = fars[index];
+            t = march_t0(c, t, noises ? noises[n] : 0.0f);
+            float last_t = t;
+            float x, y, z, dt;
+            while (t < far && step < n_step) {
+                if (march_visit(c, grid, t, x, y, z, dt)) {
+                    const size_t row = (size_t)step * n_alive + n;
+                    xyzs[3 * row] = x; xyzs[3 * row + 1] = y; xyzs[3 * row + 2] = z;
+                    if (dirs) { dirs[3 * row] = c.dx; dirs[3 * row + 1] = c.dy; dirs[3 * row + 2] = c.dz; }
+                    t = __fadd_rn(t, dt);
+                    reinterpret_cast<float4*>(deltas)[row] = make_float4(dt, __fsub_rn(t, last_t), 0.0f, 0.0f);
+                    last_t = t;
+                    step++;
+                }
+            }
+        }
+        for (; step < n_step; step++) {
+            const size_t row = (size_t)step * n_alive + n;
+            xyzs[3 * row] = 0; xyzs[3 * row + 1] = 0; xyzs[3 * row + 2] = 0;
+            if (dirs) { dirs[3 * row] = 0; dirs[3 * row + 1] = 0; dirs[3 * row + 2] = 0; }
+            reinterpret_cast<float4*>(deltas)[row] = make_float4(0, 0, 0, 0);
+        }
+        return;
+    }
     if (n < n_alive) {
         const int32_t index = rays_alive[n];
         float* px = s_xyz + 3 * threadIdx.x * n_step;
@@ -1185,9 +1219,14 @@ k_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* __r
     if (n >= n_alive) return;
     const int32_t index = rays_alive[n];
     if (index < 0) return;          // dead slot (see k_march_rays)
-    const float* s = sigmas + (size_t)n * n_step;
-    const float* r = rgbs + (size_t)n * n_step * C;
-    const float4* dl4 = reinterpret_cast<const float4*>(deltas) + (size_t)n * n_step;
+    // row of sample `step` of this slot: n * n_step + step (the reference's ray-major layout) or, in the device-driven loop
+    // with ctl[7] = 1, step * n_alive + n (step-major: lanes read consecutive rows)
+    const bool step_major = ctl && ctl[7] != 0;
+    const size_t row0 = step_major ? (size_t)n : (size_t)n * n_step;
+    const size_t row_inc = step_major ? (size_t)n_alive : 1;
+    const float* s = sigmas + row0;
+    const float* r = rgbs + row0 * C;
+    const float4* dl4 = reinterpret_cast<const float4*>(deltas) + row0;
     float* rt = rays_t + (size_t)index * (is_ndc ? 2 : 1);
     float* img = image + (size_t)index * C;
     float t_rm = 0.0f, t_phy;
@@ -1201,15 +1240,15 @@ k_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* __r
 #pragma unroll
         for (int c = 0; c < 16; c++) acc[c] = ((uint32_t)c < C) ? img[c] : 0.0f;
         while (step < n_step) {
-            const float4 dl = __ldg(dl4 + step);
+            const float4 dl = __ldg(dl4 + step * row_inc);
             if (dl.x == 0.0f) break;
-            const float alpha = alpha_from(__ldg(s + step), is_ndc ? dl.z : dl.x);
+            const float alpha = alpha_from(__ldg(s + step * row_inc), is_ndc ? dl.z : dl.x);
             const float T = 1.0f - weight_sum;
             const float w = alpha * T;
             weight_sum += w;
             if (is_ndc) { t_rm += dl.y; t_phy += dl.w; } else { t_phy += dl.y; }
             d = __fmaf_rn(w, t_phy, d);
-            const float* rr = r + (size_t)step * C;
+            const float* rr = r + (size_t)step * row_inc * C;
 #pragma unroll
             for (int c = 0; c < 16; c++) if ((uint32_t)c < C) acc[c] = __fmaf_rn(w, __ldg(rr + c), acc[c]);
             if (T < T_thresh) break;
@@ -1219,15 +1258,15 @@ k_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* __r
         for (int c = 0; c < 16; c++) if ((uint32_t)c < C) img[c] = acc[c];
     } else {
         while (step < n_step) {
-            const float4 dl = __ldg(dl4 + step);
+            const float4 dl = __ldg(dl4 + step * row_inc);
             if (dl.x == 0.0f) break;
-            const float alpha = alpha_from(__ldg(s + step), is_ndc ? dl.z : dl.x);
+            const float alpha = alpha_from(__ldg(s + step * row_inc), is_ndc ? dl.z : dl.x);
             const float T = 1.0f - weight_sum;
             const float w = alpha * T;
             weight_sum += w;
             if (is_ndc) { t_rm += dl.y; t_phy += dl.w; } else { t_phy += dl.y; }
             d = __fmaf_rn(w, t_phy, d);
-            const float* rr = r + (size_t)step * C;
+            const float* rr = r + (size_t)step * row_inc * C;
             for (uint32_t c = 0; c < C; c++) img[c] = __fmaf_rn(w, __ldg(rr + c), img[c]);
             if (T < T_thresh) break;
             step++;

@@ -549,7 +549,7 @@ class Renderer(nn.Module):
         st['weights_sum'].zero_(); st['depth'].zero_(); st['image'].zero_()
         st['alive'][0].copy_(torch.arange(N, dtype=torch.int32, device=self.device))
         n0 = max(min(budget // N, 8), 1)
-        st['ctl'].copy_(torch.tensor([N, n0, N * n0, 0, budget, self.max_steps, 0, 0], dtype=torch.int32))
+        st['ctl'].copy_(torch.tensor([N, n0, N * n0, 0, budget, self.max_steps, 0, 1], dtype=torch.int32))      # ctl[7] = 1: step-major sample rows
         for i, e in enumerate((m.x_density_embedder, m.x_color_embedder)):       # fp16 tables / weights for this frame
             shadow = current_half_copy(e.embeddings)
             st['pair'][:, i].copy_(shadow if shadow is not None else e.embeddings.detach())
