@@ -242,8 +242,16 @@ def _side_stream(device):
     return _side[key]
 
 
-def _pipeline_chunks(B, min_rows=1 << 19, n=4):
+# Chunks of the optional gather -> networks stream pipeline.  1 = off (default): measured on the B200, running the gather of
+# chunk k + 1 next to the networks of chunk k does not pay -- both kernels are bound by the same SM resources (issue slots /
+# L1TEX: 73 % + 26 % and 64 % + 35 % in ncu), so each slows the other down by what the overlap gains (train step 4.43 ms
+# with 1 chunk, 4.48 with 4, 4.52 with 8, 4.67 with 16).  Kept for experiments (tools/_pipe_sweep.py).
+PIPELINE_CHUNKS = [1]
+
+
+def _pipeline_chunks(B, min_rows=1 << 19, n=None):
     """Row ranges (multiples of 128 rows) for the gather -> networks pipeline; one range when the batch is small."""
+    n = PIPELINE_CHUNKS[0] if n is None else n
     if B < 2 * min_rows:
         return [(0, B)]
     n = min(n, B // min_rows)

@@ -213,8 +213,9 @@ def test_pipeline_chunks_cover_all_rows():
     """gridencoder._pipeline_chunks: the row ranges of the gather -> networks pipeline partition [0, B), start on multiples of
     128 rows (the networks' tile size) and collapse to one range for small batches."""
     from nerfstyle_b200.gridencoder import _pipeline_chunks
+    assert _pipeline_chunks(4_139_648) == [(0, 4_139_648)]                  # the pipeline is off by default (measured: no gain)
     for B in (0, 1, 127, 1 << 19, (1 << 20) - 1, 1 << 20, 4_139_648, 4_430_363, 33_000_001):
-        ch = _pipeline_chunks(B)
+        ch = _pipeline_chunks(B, n=4)
         assert ch[0][0] == 0 and ch[-1][1] == B
         assert all(a[1] == b[0] for a, b in zip(ch[:-1], ch[1:]))
         assert all(r0 % 128 == 0 for r0, _ in ch)
