@@ -309,6 +309,9 @@ def run_ours(args):
     if not args.skip_strong:
         g_rays = 65536
         per = g_rays // world
+        # ~520 samples per ray x ~700 B of activations per sample: give the caching allocator one arena of that size first
+        # (set-up, like reserve_workspace above), so the timed steps do not cudaMalloc at each new high-water mark
+        TrainStep.reserve_workspace(device, min(int(per * 520 * 900), 64 << 30))
         _, sb = make_batches(8, per, rank, world, device)
         for s in range(2):
             ts.step(*unpack(sb[s]))
