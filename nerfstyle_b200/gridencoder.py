@@ -245,7 +245,7 @@ def _side_stream(device):
 # Chunks of the optional gather -> networks stream pipeline.  1 = off (default): measured on the B200, running the gather of
 # chunk k + 1 next to the networks of chunk k does not pay -- both kernels are bound by the same SM resources (issue slots /
 # L1TEX: 73 % + 26 % and 64 % + 35 % in ncu), so each slows the other down by what the overlap gains (train step 4.43 ms
-# with 1 chunk, 4.48 with 4, 4.52 with 8, 4.67 with 16).  Kept for experiments (tools/_pipe_sweep.py).
+# with 1 chunk, 4.48 with 4, 4.52 with 8, 4.67 with 16).  Kept for experiments (tools/pipe_sweep.py).
 PIPELINE_CHUNKS = [1]
 
 

@@ -1,3 +1,5 @@
+"""Train-step time against the number of chunks of the optional gather -> networks stream pipeline (gridencoder.PIPELINE_CHUNKS;
+1 = off, the default).  Usage (GPU box): python tools/pipe_sweep.py"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
