@@ -103,6 +103,8 @@ SIGNATURES = {
 EXTRA_SIGNATURES = {
     'nrf_grid_set_tuning': (None, [_i32, _i32, _i32]),
     'nrf_grid_set_transpose_min': (None, [_i32]),
+    'nrf_grid_set_bwd_walk': (None, [_i32]),
+    'nrf_grid_set_bwd_walk_queue': (None, [_i32]),
     'nrf_march_set_mode': (None, [_i32]),
     'nrf_mlp_set_mode': (None, [_i32]),
     'nrf_mlp_get_mode': (_i32, []),

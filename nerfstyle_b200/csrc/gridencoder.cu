@@ -831,6 +831,368 @@ NRF_EXPORT int nrf_grid_encode_forward_pair(const float* inputs, const void* tab
     return nrf_check_launch();
 }
 
+// ------------------------------------------------------------------------------------------------
+// paired backward, "walk" form: the samples of a train step arrive ray by ray, and consecutive samples of a ray stay in
+// the same cell for many steps on the coarse and middle levels (a cell of level 0 holds ~150 march steps, of level 8 ~8).
+// Instead of one thread per sample and a shuffle / shared-memory reduction over the lanes of a warp, ONE LANE WALKS a chunk
+// of CH consecutive samples at ONE level (a half-warp = 16 levels of one chunk) and keeps the 8 corners x 4 components of
+// its current cell in registers; the cell is flushed with 8 16-byte reductions when the walk leaves it.  The aggregation
+// costs nothing (32 fma per sample-level, no shuffles except the 3 that broadcast the position) and it spans the whole
+// chunk instead of one warp's 32 samples.  Gradient rows are read as 64 contiguous bytes per half-warp (point-major
+// [B, L] pairs), four steps ahead of their use.
+// ------------------------------------------------------------------------------------------------
+static int g_bwd_walk = 128;  // chunk length of the walk kernels (0: the thread-per-sample kernel above)
+NRF_EXPORT void nrf_grid_set_bwd_walk(int chunk) { g_bwd_walk = chunk; }
+
+__device__ __forceinline__ void walk_grads(const float2& a, const float2& b, float (&g)[4]) { g[0] = a.x; g[1] = a.y; g[2] = b.x; g[3] = b.y; }
+__device__ __forceinline__ void walk_grads(const __half2& a, const __half2& b, float (&g)[4]) {
+    const float2 fa = __half22float2(a), fb = __half22float2(b);
+    g[0] = fa.x; g[1] = fa.y; g[2] = fb.x; g[3] = fb.y;
+}
+
+#define WALK_WARPS 8       // warps per block
+
+// CH consecutive samples per half-warp.  L must be 16 and the gradient rows 16-byte aligned (checked by the launcher).
+template <typename T, int CH>
+__global__ void __launch_bounds__(WALK_WARPS * 32, sizeof(T) == 2 ? 2 : 1)
+k_grid_bwd_walk(const T* __restrict__ grad0, const T* __restrict__ grad1, const float* __restrict__ inputs,
+                const int32_t* __restrict__ offsets, float4* __restrict__ grad_pair, uint32_t B, float S, uint32_t H,
+                uint32_t gridtype, bool align_corners, uint32_t style, const float* __restrict__ xform) {
+    typedef typename Vec2<T>::type V2;
+    static_assert(CH % 16 == 0, "chunks are walked in groups of 16 samples");
+    constexpr int WPL = (int)sizeof(V2) / 4;      // 32-bit words per level of one sample's gradient row
+    constexpr int WR = 16 * WPL;                  // words per gradient row (16 levels)
+    constexpr int CPR = WR / 4;                   // 16-byte pieces per row
+    constexpr int STAGE = 2 * 16 * 2 * WR;        // words per stage of one warp: [encoder][step][half][level]
+    extern __shared__ __align__(16) uint32_t wbuf_all[];
+    __shared__ LevelP lps[16];
+    if (threadIdx.x < 16) level_setup(lps[threadIdx.x], offsets, threadIdx.x, 3, S, H, gridtype, align_corners, style);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, lvl = lane & 15, hf = lane >> 4, hb = lane & 16;
+    const LevelP p = lps[lvl];
+    uint32_t* wbuf = wbuf_all + (threadIdx.x >> 5) * (2 * STAGE);
+    const size_t chunk = ((size_t)blockIdx.x * WALK_WARPS + (threadIdx.x >> 5)) * 2 + hf;
+    const size_t b0 = chunk * CH;
+    const uint32_t nvalid = b0 < B ? (uint32_t)min((size_t)CH, (size_t)B - b0) : 0u;     // samples of this half-warp's chunk
+
+    // group g of the chunk = 16 samples = 16 contiguous gradient rows per encoder: copied global -> shared asynchronously
+    // (16-byte pieces, zero-filled past the end of the chunk), one group ahead of the walk
+    auto stage_grads = [&](int g, int buf) {
+        uint32_t* dst = wbuf + buf * STAGE;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(e == 0 ? grad0 : grad1) + (b0 + (size_t)g * 16) * WR;
+#pragma unroll
+            for (int i = 0; i < CPR; i++) {
+                const int c = i * 16 + lvl, s = c / CPR, part = c - s * CPR;
+                const bool ok = (uint32_t)(g * 16 + s) < nvalid;
+                const uint32_t sa = (uint32_t)__cvta_generic_to_shared(dst + ((e * 16 + s) * 2 + hf) * WR + part * 4);
+                const uint32_t* ga = ok ? src + (size_t)s * WR + part * 4 : reinterpret_cast<const uint32_t*>(grad0);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(ga), "r"(ok ? 16 : 0) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // the position of sample (16 g + lvl) of the chunk, transformed once per 16 steps and broadcast with shuffles;
+    // x = -1 marks a sample that contributes nothing (outside [0,1]^3, gridencoder.cu:268-273, or past the end)
+    auto fetch_pos = [&](int g, float& x, float& y, float& z) {
+        x = -1.0f; y = 0.0f; z = 0.0f;
+        const uint32_t s = (uint32_t)g * 16u + (uint32_t)lvl;
+        if (s < nvalid) {
+            const float* ip = inputs + 3 * (b0 + s);
+            float a = __ldg(ip), b = __ldg(ip + 1), c = __ldg(ip + 2);
+            if (xform) { a = xform1(a, xform, 0); b = xform1(b, xform, 1); c = xform1(c, xform, 2); }
+            if (!((a < 0 || a > 1) || (b < 0 || b > 1) || (c < 0 || c > 1))) { x = a; y = b; z = c; }
+        }
+    };
+
+    float acc[8][4];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.0f; }
+    uint32_t pcx = 0, pcy = 0, pcz = 0;
+    bool have = false;
+    // exact x % size without the power-of-two / size-1 branches of mod_size (the round-up magic is exact for every size >= 2)
+    const uint32_t msh = p.shift > 0 ? p.shift - 1 : 0u;
+    auto flush = [&]() {
+        uint32_t idx[8];
+        if (p.use_hash) {
+            const uint32_t hy0 = pcy * 2654435761u, hy1 = hy0 + 2654435761u;
+            const uint32_t hz0 = (pcz * 805459861u) ^ p.hash_style, hz1 = ((pcz + 1) * 805459861u) ^ p.hash_style;
+#pragma unroll
+            for (int k = 0; k < 8; k++) idx[k] = (pcx + (k & 1)) ^ ((k & 2) ? hy1 : hy0) ^ ((k & 4) ? hz1 : hz0);
+        } else {
+            const uint32_t base = pcx * p.stride[0] + pcy * p.stride[1] + pcz * p.stride[2] + p.style_term;
+#pragma unroll
+            for (int k = 0; k < 8; k++) idx[k] = base + ((k & 1) ? p.stride[0] : 0u) + ((k & 2) ? p.stride[1] : 0u) + ((k & 4) ? p.stride[2] : 0u);
+        }
+        float4* gl = grad_pair + p.offset;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t v = idx[k], t = __umulhi(v, p.mul);
+            uint32_t row = v - (((t + ((v - t) >> 1)) >> msh) * p.size);
+            if (p.size == 1u) row = 0u;
+            atomicAdd(gl + row, make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]));   // RED.ADD.F32x4
+        }
+    };
+
+    float nx, ny, nz;
+    fetch_pos(0, nx, ny, nz);
+    stage_grads(0, 0);
+#pragma unroll 1
+    for (int g = 0; g < CH / 16; g++) {
+        const float px = nx, py = ny, pz = nz;
+        if (g + 1 < CH / 16) {
+            fetch_pos(g + 1, nx, ny, nz);
+            stage_grads(g + 1, (g + 1) & 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
+        const uint32_t* rb = wbuf + (g & 1) * STAGE + hf * WR + lvl * WPL;
+#pragma unroll 2
+        for (int s = 0; s < 16; s++) {
+            const V2 c0 = *reinterpret_cast<const V2*>(rb + (s * 2) * WR);
+            const V2 c1 = *reinterpret_cast<const V2*>(rb + ((16 + s) * 2) * WR);
+            const float x = __shfl_sync(NRF_FULL_MASK, px, hb + s);
+            const float y = __shfl_sync(NRF_FULL_MASK, py, hb + s);
+            const float z = __shfl_sync(NRF_FULL_MASK, pz, hb + s);
+            float gq[4];
+            walk_grads(c0, c1, gq);
+            // exact zeros add nothing (samples behind an early-terminated ray): they neither open nor extend a cell
+            const bool contrib = x >= 0.0f && (gq[0] != 0.0f || gq[1] != 0.0f || gq[2] != 0.0f || gq[3] != 0.0f);
+            uint32_t cx, cy, cz; float fx, fy, fz;
+            locate1(x, p, align_corners, cx, fx);
+            locate1(y, p, align_corners, cy, fy);
+            locate1(z, p, align_corners, cz, fz);
+            if (contrib && (!have || cx != pcx || cy != pcy || cz != pcz)) {
+                if (have) flush();
+#pragma unroll
+                for (int k = 0; k < 8; k++) { acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.0f; }
+                pcx = cx; pcy = cy; pcz = cz; have = true;
+            }
+            if (contrib) {
+                float w[8];
+                corner_weights_d3(fx, fy, fz, w);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[k][c] = __fmaf_rn(w[k], gq[c], acc[k][c]);
+                }
+            }
+        }
+        __syncwarp();      // every lane is done with this stage before the copies of group g + 2 overwrite it
+    }
+    if (have) flush();
+}
+
+// Queue form of the walk: in the kernel above the flush block (8 hashes + 8 reductions) runs whenever ANY lane leaves
+// its cell -- nearly every step, because the fine levels change cell at every sample -- with on average 4.6 of 16 lanes
+// active.  Here a lane that leaves a cell only PARKS it (32 sums + cell + level = 144 bytes) in a per-warp ring in shared
+// memory; whenever the ring holds four cells the warp drains them with all 32 lanes busy: lane t takes corner t % 8 of
+// parked cell t / 8 -- one 16-byte shared load, one hash, one 16-byte reduction.
+#define WALKQ_SLOTS 40     // >= 3 left over + 32 parked in one step
+#define WALKQ_WORDS 36     // 32 sums + (cx, cy, cz, level)
+static int g_bwd_walk_queue = 1;
+NRF_EXPORT void nrf_grid_set_bwd_walk_queue(int on) { g_bwd_walk_queue = on; }
+
+template <typename T, int CH>
+__global__ void __launch_bounds__(WALK_WARPS * 32, sizeof(T) == 2 ? 2 : 1)
+k_grid_bwd_walkq(const T* __restrict__ grad0, const T* __restrict__ grad1, const float* __restrict__ inputs,
+                 const int32_t* __restrict__ offsets, float4* __restrict__ grad_pair, uint32_t B, float S, uint32_t H,
+                 uint32_t gridtype, bool align_corners, uint32_t style, const float* __restrict__ xform) {
+    typedef typename Vec2<T>::type V2;
+    static_assert(CH % 16 == 0, "chunks are walked in groups of 16 samples");
+    constexpr int WPL = (int)sizeof(V2) / 4;      // 32-bit words per level of one sample's gradient row
+    constexpr int WR = 16 * WPL;                  // words per gradient row (16 levels)
+    constexpr int CPR = WR / 4;                   // 16-byte pieces per row
+    constexpr int STAGE = 2 * 16 * 2 * WR;        // words per stage of one warp: [encoder][step][half][level]
+    constexpr int PERWARP = 2 * STAGE + WALKQ_SLOTS * WALKQ_WORDS;
+    extern __shared__ __align__(16) uint32_t wbuf_all[];
+    __shared__ LevelP lps[16];
+    __shared__ uint4 lrec[16];                    // what the drain needs of a level: {row offset, size - 1, style hash, hashed power-of-two level?}
+    if (threadIdx.x < 16) {
+        level_setup(lps[threadIdx.x], offsets, threadIdx.x, 3, S, H, gridtype, align_corners, style);
+        const LevelP& q = lps[threadIdx.x];
+        lrec[threadIdx.x] = make_uint4(q.offset, q.pow2mask, q.hash_style, (q.use_hash && q.pow2mask) ? 1u : 0u);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, lvl = lane & 15, hf = lane >> 4, hb = lane & 16;
+    const float scale = lps[lvl].scale;
+    const float rmax = (float)(lps[lvl].resolution - 1);
+    uint32_t* wbuf = wbuf_all + (threadIdx.x >> 5) * PERWARP;
+    float4* ring = reinterpret_cast<float4*>(wbuf + 2 * STAGE);
+    const size_t chunk = ((size_t)blockIdx.x * WALK_WARPS + (threadIdx.x >> 5)) * 2 + hf;
+    const size_t b0 = chunk * CH;
+    const uint32_t nvalid = b0 < B ? (uint32_t)min((size_t)CH, (size_t)B - b0) : 0u;     // samples of this half-warp's chunk
+
+    auto stage_grads = [&](int g, int buf) {
+        uint32_t* dst = wbuf + buf * STAGE;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(e == 0 ? grad0 : grad1) + (b0 + (size_t)g * 16) * WR;
+#pragma unroll
+            for (int i = 0; i < CPR; i++) {
+                const int c = i * 16 + lvl, s = c / CPR, part = c - s * CPR;
+                const bool ok = (uint32_t)(g * 16 + s) < nvalid;
+                const uint32_t sa = (uint32_t)__cvta_generic_to_shared(dst + ((e * 16 + s) * 2 + hf) * WR + part * 4);
+                const uint32_t* ga = ok ? src + (size_t)s * WR + part * 4 : reinterpret_cast<const uint32_t*>(grad0);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(ga), "r"(ok ? 16 : 0) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto fetch_pos = [&](int g, float& x, float& y, float& z) {
+        x = -1.0f; y = 0.0f; z = 0.0f;
+        const uint32_t s = (uint32_t)g * 16u + (uint32_t)lvl;
+        if (s < nvalid) {
+            const float* ip = inputs + 3 * (b0 + s);
+            float a = __ldg(ip), b = __ldg(ip + 1), c = __ldg(ip + 2);
+            if (xform) { a = xform1(a, xform, 0); b = xform1(b, xform, 1); c = xform1(c, xform, 2); }
+            if (!((a < 0 || a > 1) || (b < 0 || b > 1) || (c < 0 || c > 1))) { x = a; y = b; z = c; }
+        }
+    };
+
+    float acc[8][4];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.0f; }
+    uint32_t pcx = 0, pcy = 0, pcz = 0;
+    bool have = false;
+    int qhead = 0, qcount = 0;                     // warp-uniform ring state
+    // drain parked cells, four per round (all of them when `all`)
+    // (Measured and rejected: eight cells per round, two corners x / x + 1 per lane -- fewer shared-memory wavefronts per
+    //  cell, but 1.06 ms instead of 0.945.)
+    auto drain = [&](bool all) {
+        while (qcount >= 4 || (all && qcount > 0)) {
+            const int e = lane >> 3, k = lane & 7;
+            if (e < qcount) {
+                int slot = qhead + e; if (slot >= WALKQ_SLOTS) slot -= WALKQ_SLOTS;
+                const float4* qs = ring + slot * (WALKQ_WORDS / 4);
+                const uint4 cc = *reinterpret_cast<const uint4*>(qs + 8);
+                const float4 v = qs[k];
+                const uint4 rec = lrec[cc.w];
+                uint32_t row;
+                if (rec.w) {                        // every level of the model's grids but the coarsest five
+                    row = ((cc.x + (k & 1)) ^ ((cc.y + ((k >> 1) & 1)) * 2654435761u) ^ ((cc.z + (k >> 2)) * 805459861u) ^ rec.z) & rec.y;
+                } else {
+                    const LevelP& q = lps[cc.w];
+                    uint32_t idx;
+                    if (q.use_hash) idx = (cc.x + (k & 1)) ^ ((cc.y + ((k >> 1) & 1)) * 2654435761u) ^ ((cc.z + (k >> 2)) * 805459861u) ^ q.hash_style;
+                    else idx = (cc.x + (k & 1)) * q.stride[0] + (cc.y + ((k >> 1) & 1)) * q.stride[1] + (cc.z + (k >> 2)) * q.stride[2] + q.style_term;
+                    row = mod_size(q, idx);
+                }
+                atomicAdd(grad_pair + rec.x + row, v);        // RED.ADD.F32x4
+            }
+            const int n = min(qcount, 4);
+            qhead += n; if (qhead >= WALKQ_SLOTS) qhead -= WALKQ_SLOTS;
+            qcount -= n;
+            __syncwarp();
+        }
+    };
+    auto park = [&](bool mine) {
+        const uint32_t fm = __ballot_sync(NRF_FULL_MASK, mine);
+        if (fm == 0u) return;
+        if (mine) {
+            int slot = qhead + qcount + __popc(fm & ((1u << lane) - 1u));
+            if (slot >= WALKQ_SLOTS) slot -= WALKQ_SLOTS;
+            float4* qs = ring + slot * (WALKQ_WORDS / 4);
+#pragma unroll
+            for (int k = 0; k < 8; k++) qs[k] = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+            *reinterpret_cast<uint4*>(qs + 8) = make_uint4(pcx, pcy, pcz, (uint32_t)lvl);
+#pragma unroll
+            for (int k = 0; k < 8; k++) { acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.0f; }
+        }
+        qcount += __popc(fm);
+        __syncwarp();
+    };
+
+    float nx, ny, nz;
+    fetch_pos(0, nx, ny, nz);
+    stage_grads(0, 0);
+#pragma unroll 1
+    for (int g = 0; g < CH / 16; g++) {
+        const float px = nx, py = ny, pz = nz;
+        if (g + 1 < CH / 16) {
+            fetch_pos(g + 1, nx, ny, nz);
+            stage_grads(g + 1, (g + 1) & 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
+        const uint32_t* rb = wbuf + (g & 1) * STAGE + hf * WR + lvl * WPL;
+#pragma unroll 2
+        for (int s = 0; s < 16; s++) {
+            const V2 c0 = *reinterpret_cast<const V2*>(rb + (s * 2) * WR);
+            const V2 c1 = *reinterpret_cast<const V2*>(rb + ((16 + s) * 2) * WR);
+            const float x = __shfl_sync(NRF_FULL_MASK, px, hb + s);
+            const float y = __shfl_sync(NRF_FULL_MASK, py, hb + s);
+            const float z = __shfl_sync(NRF_FULL_MASK, pz, hb + s);
+            float gq[4];
+            walk_grads(c0, c1, gq);
+            // exact zeros add nothing (samples behind an early-terminated ray): they neither open nor extend a cell
+            const bool contrib = x >= 0.0f && (gq[0] != 0.0f || gq[1] != 0.0f || gq[2] != 0.0f || gq[3] != 0.0f);
+            // locate1, with the level's constants in registers
+            const float posx = __fmaf_rn(x, scale, align_corners ? 0.0f : 0.5f), posy = __fmaf_rn(y, scale, align_corners ? 0.0f : 0.5f),
+                        posz = __fmaf_rn(z, scale, align_corners ? 0.0f : 0.5f);
+            const uint32_t cx = (uint32_t)fminf(floorf(posx), rmax), cy = (uint32_t)fminf(floorf(posy), rmax), cz = (uint32_t)fminf(floorf(posz), rmax);
+            const bool change = contrib && (!have || cx != pcx || cy != pcy || cz != pcz);
+            // (Measured and rejected: letting the finest levels, which change cell at nearly every sample, reduce straight from
+            //  their registers instead of parking -- 8 reductions issued with 2-8 active lanes cost more than the trip through
+            //  shared memory: 1.05 ms instead of 0.945 for levels >= 13.)
+            park(change && have);
+            drain(false);
+            if (change) { pcx = cx; pcy = cy; pcz = cz; have = true; }
+            if (contrib) {
+                float w[8];
+                corner_weights_d3(__fsub_rn(posx, (float)cx), __fsub_rn(posy, (float)cy), __fsub_rn(posz, (float)cz), w);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[k][c] = __fmaf_rn(w[k], gq[c], acc[k][c]);
+                }
+            }
+        }
+        __syncwarp();      // every lane is done with this stage before the copies of group g + 2 overwrite it
+    }
+    park(have);
+    drain(true);
+}
+
+template <typename T>
+static void launch_bwd_walk(int ch, const void* grad0, const void* grad1, const float* inputs, const int32_t* offsets, float* grad_pair,
+                            uint32_t B, float S, uint32_t H, uint32_t gridtype, bool ac, uint32_t style, const float* xform,
+                            cudaStream_t s) {
+    const uint32_t CH = ch >= 256 ? 256u : (ch >= 128 ? 128u : (ch >= 64 ? 64u : (ch >= 32 ? 32u : 16u)));
+    const uint32_t chunks = ceil_div_u32(B, CH);
+    const uint32_t blocks = ceil_div_u32(ceil_div_u32(chunks, 2), WALK_WARPS);
+    constexpr int STAGES = WALK_WARPS * 2 * (2 * 16 * 2 * 16 * (int)sizeof(typename Vec2<T>::type));   // two stages per warp
+    constexpr int SMEMQ = STAGES + WALK_WARPS * WALKQ_SLOTS * WALKQ_WORDS * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_grid_bwd_walk<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGES);
+        cudaFuncSetAttribute(k_grid_bwd_walk<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGES);
+        cudaFuncSetAttribute(k_grid_bwd_walk<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGES);
+        cudaFuncSetAttribute(k_grid_bwd_walkq<T, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEMQ);
+        cudaFuncSetAttribute(k_grid_bwd_walkq<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEMQ);
+        cudaFuncSetAttribute(k_grid_bwd_walkq<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEMQ);
+        cudaFuncSetAttribute(k_grid_bwd_walkq<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEMQ);
+        attr_set = true;
+    }
+#define WALK_ARGS (const T*)grad0, (const T*)grad1, inputs, offsets, reinterpret_cast<float4*>(grad_pair), B, S, H, gridtype, ac, style, xform
+    if (g_bwd_walk_queue && CH >= 32 && sizeof(T) == 2) {      // f32 gradient rows (parity mode): the ring would leave one block per SM
+        if (CH == 256) k_grid_bwd_walkq<T, 256><<<blocks, WALK_WARPS * 32, SMEMQ, s>>>(WALK_ARGS);
+        else if (CH == 128) k_grid_bwd_walkq<T, 128><<<blocks, WALK_WARPS * 32, SMEMQ, s>>>(WALK_ARGS);
+        else if (CH == 64) k_grid_bwd_walkq<T, 64><<<blocks, WALK_WARPS * 32, SMEMQ, s>>>(WALK_ARGS);
+        else k_grid_bwd_walkq<T, 32><<<blocks, WALK_WARPS * 32, SMEMQ, s>>>(WALK_ARGS);
+    } else {
+        if (CH >= 64) k_grid_bwd_walk<T, 64><<<ceil_div_u32(ceil_div_u32(ceil_div_u32(B, 64), 2), WALK_WARPS), WALK_WARPS * 32, STAGES, s>>>(WALK_ARGS);
+        else if (CH == 32) k_grid_bwd_walk<T, 32><<<blocks, WALK_WARPS * 32, STAGES, s>>>(WALK_ARGS);
+        else k_grid_bwd_walk<T, 16><<<blocks, WALK_WARPS * 32, STAGES, s>>>(WALK_ARGS);
+    }
+#undef WALK_ARGS
+}
+
 NRF_EXPORT int nrf_grid_encode_backward_pair(const void* grad0, const void* grad1, const float* inputs, const int32_t* offsets,
                                              float* grad_pair, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype,
                                              int align_corners, uint32_t style, int dtype, const float* xform, void* stream) {
@@ -848,6 +1210,12 @@ NRF_EXPORT int nrf_grid_encode_backward_pair(const void* grad0, const void* grad
         attr_set = true;
     }
     const int tr_min = g_bwd_agg > 0 ? g_bwd_tr_min : (1 << 30);
+    if (g_bwd_walk > 0 && L == 16 && (dtype == NRF_DTYPE_F16 || dtype == NRF_DTYPE_F32) &&
+        ((((uintptr_t)grad0) | ((uintptr_t)grad1)) & 15) == 0) {
+        if (dtype == NRF_DTYPE_F16) launch_bwd_walk<__half>(g_bwd_walk, grad0, grad1, inputs, offsets, grad_pair, B, S, H, gridtype, ac, style, xform, s);
+        else launch_bwd_walk<float>(g_bwd_walk, grad0, grad1, inputs, offsets, grad_pair, B, S, H, gridtype, ac, style, xform, s);
+        return nrf_check_launch();
+    }
     if (dtype == NRF_DTYPE_F16)
         k_grid_bwd_d3c2<__half, float, 16, 2, true><<<dim3(nbx, ceil_div_u32(L, 16)), GRID_BLOCK, TR_BYTES, s>>>(
             (const __half*)grad0, (const __half*)grad1, inputs, offsets, grad_pair, nullptr, B, L, S, H, gridtype, ac, style, true, g_bwd_agg, xform, tr_min);

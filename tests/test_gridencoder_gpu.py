@@ -269,3 +269,52 @@ def test_backward_skips_exact_zero_gradients(cuda_lib, oracle, dev):
                                       enc.embeddings.shape[0], 2, enc.per_level_scale, 16, 0, True, 0)
     ge = enc.embeddings.grad.cpu().numpy()
     assert np.abs(ge - ege).max() <= 1e-5 * np.abs(ege).max()
+
+
+@pytest.mark.parametrize('B', [1, 15, 17, 63, 65, 1031, 40007])
+@pytest.mark.parametrize('half', [True, False])
+def test_pair_backward_walk(cuda_lib, oracle, dev, B, half):
+    """nrf_grid_encode_backward_pair's walk form (one lane walks a chunk of consecutive samples at one level and keeps the
+    current cell in registers; cells are flushed directly or parked in a shared-memory ring and drained four at a time)
+    against the CPU oracle's scatter and the thread-per-sample form, for every chunk length and both flush forms:
+    ragged chunk tails, ray-like runs, cell changes at ray boundaries, out-of-range rows, exact-zero gradient rows and
+    the in-kernel input transform."""
+    enc = _default_encoder(dev)
+    g = torch.Generator().manual_seed(B)
+    nray = B // 40 + 1
+    o = (torch.rand(nray, 3, generator=g) * 3.6 - 1.8).repeat_interleave(40, dim=0)[:B]
+    d = torch.nn.functional.normalize(torch.randn(nray, 3, generator=g), dim=-1).repeat_interleave(40, dim=0)[:B]
+    x = (o + d * (torch.arange(B)[:, None] % 40) * 3.4e-3).to(dev)             # world coordinates, box [-2, 2]^3
+    if B > 20:
+        x[7] = 5.0                                                               # outside the box: contributes nothing
+    xf = torch.tensor([-2., -2., -2., 4., 4., 4., 1.], device=dev)
+    dt = torch.float16 if half else torch.float32
+    g0 = torch.randn(B, 32, generator=g).to(dev).to(dt)
+    g1 = torch.randn(B, 32, generator=g).to(dev).to(dt)
+    if B > 1000:
+        g0[100:400] = 0; g1[100:400] = 0                                         # dead samples behind a terminated ray
+        g0[500:600:3] = 0
+        g1[700:800, 4:6] = 0
+    S = float(np.float32(np.log2(enc.per_level_scale)))
+    st = torch.cuda.current_stream().cuda_stream
+    T = enc.embeddings.shape[0]
+    pts = ((x - xf[:3]) / xf[3:6] + 1) * (1 / (2 * xf[6]))                      # what xform computes, operation for operation
+    exp = [oracle.grid_encode_backward(gg.float().cpu().numpy(), pts.cpu().numpy(), enc.offsets.cpu().numpy(), T, 2,
+                                       enc.per_level_scale, 16, 0, True, 0) for gg in (g0, g1)]
+    res = {}
+    try:
+        for walk, queue in ((0, 1), (16, 0), (32, 0), (64, 0), (32, 1), (64, 1), (128, 1), (256, 1)):
+            cuda_lib.nrf_grid_set_bwd_walk(walk)
+            cuda_lib.nrf_grid_set_bwd_walk_queue(queue)
+            gp = torch.zeros(T, 2, 2, device=dev)
+            assert cuda_lib.nrf_grid_encode_backward_pair(g0.data_ptr(), g1.data_ptr(), x.data_ptr(), enc.offsets.data_ptr(), gp.data_ptr(),
+                                                          B, 16, S, 16, 0, 1, 0, 1 if half else 0, xf.data_ptr(), st) == 0
+            torch.cuda.synchronize()
+            res[(walk, queue)] = gp
+            for e in (0, 1):
+                got = gp[:, e].cpu().numpy()
+                assert np.abs(got - exp[e]).max() <= 1e-5 * max(np.abs(exp[e]).max(), 1e-30), (walk, queue, e)
+    finally:
+        cuda_lib.nrf_grid_set_bwd_walk(128)
+        cuda_lib.nrf_grid_set_bwd_walk_queue(1)
+    assert float((res[(64, 1)] - res[(0, 1)]).abs().max()) <= 1e-5 * float(res[(0, 1)].abs().max())

@@ -45,6 +45,7 @@ for half in (True, False):
                                                        ge1.data_ptr(), B, 16, S, 16, 0, 1, 0, dtc, 0, None, st)
     b_pair = lambda: lib.nrf_grid_encode_backward_pair(g0.data_ptr(), g1.data_ptr(), pts.data_ptr(), off.data_ptr(), gp.data_ptr(),
                                                        B, 16, S, 16, 0, 1, 0, dtc, None, st)
+    lib.nrf_grid_set_bwd_walk(0)                                # the thread-per-sample form first
     assert b_dual() == 0 and b_pair() == 0
     torch.cuda.synchronize()
     e0 = float((gp[:, 0] - ge0).abs().max() / ge0.abs().max())
@@ -70,3 +71,17 @@ for half in (True, False):
         lib.nrf_grid_set_tuning(0, 0, amin)
         print('bwd half=%d  pair, aggregate only when the longest run >= %d: %.3f ms' % (half, amin, mb.timeit(b_pair)))
     lib.nrf_grid_set_tuning(0, 0, 1)
+    # the walk form (one lane per chunk of consecutive samples and level, current cell in registers)
+    for queue in (0, 1):
+        lib.nrf_grid_set_bwd_walk_queue(queue)
+        for ch in ((16, 32, 64) if not queue else (32, 64, 128, 256)):
+            lib.nrf_grid_set_bwd_walk(ch)
+            gp.zero_()
+            assert b_pair() == 0
+            torch.cuda.synchronize()
+            e0 = float((gp[:, 0] - ge0).abs().max() / ge0.abs().max())
+            e1 = float((gp[:, 1] - ge1).abs().max() / ge1.abs().max())
+            assert e0 < 1e-5 and e1 < 1e-5, (ch, e0, e1)
+            print('bwd half=%d  pair, walk chunks of %d, queue %d: %.3f ms   (rel err vs dual %.1e / %.1e)' % (half, ch, queue, mb.timeit(b_pair), e0, e1))
+    lib.nrf_grid_set_bwd_walk(128)
+    lib.nrf_grid_set_bwd_walk_queue(1)
