@@ -992,7 +992,7 @@ k_grid_bwd_walk(const T* __restrict__ grad0, const T* __restrict__ grad1, const 
 // memory; whenever the ring holds four cells the warp drains them with all 32 lanes busy: lane t takes corner t % 8 of
 // parked cell t / 8 -- one 16-byte shared load, one hash, one 16-byte reduction.
 #define WALKQ_SLOTS 40     // >= 3 left over + 32 parked in one step
-#define WALKQ_WORDS 36     // 32 sums + (cx, cy, cz, level)
+#define WALKQ_WORDS 36     // 32 sums + (cx, cy, cz | level << 16, the level's offset and size)
 static int g_bwd_walk_queue = 1;
 NRF_EXPORT void nrf_grid_set_bwd_walk_queue(int on) { g_bwd_walk_queue = on; }
 
@@ -1010,16 +1010,20 @@ k_grid_bwd_walkq(const T* __restrict__ grad0, const T* __restrict__ grad1, const
     constexpr int PERWARP = 2 * STAGE + WALKQ_SLOTS * WALKQ_WORDS;
     extern __shared__ __align__(16) uint32_t wbuf_all[];
     __shared__ LevelP lps[16];
-    __shared__ uint4 lrec[16];                    // what the drain needs of a level: {row offset, size - 1, style hash, hashed power-of-two level?}
-    if (threadIdx.x < 16) {
-        level_setup(lps[threadIdx.x], offsets, threadIdx.x, 3, S, H, gridtype, align_corners, style);
-        const LevelP& q = lps[threadIdx.x];
-        lrec[threadIdx.x] = make_uint4(q.offset, q.pow2mask, q.hash_style, (q.use_hash && q.pow2mask) ? 1u : 0u);
-    }
+    if (threadIdx.x < 16) level_setup(lps[threadIdx.x], offsets, threadIdx.x, 3, S, H, gridtype, align_corners, style);
     __syncthreads();
     const int lane = threadIdx.x & 31, lvl = lane & 15, hf = lane >> 4, hb = lane & 16;
+    // what the drain needs of this lane's level travels with every parked cell, so the drain has no dependent second load:
+    // row offset (bits 0-23), log2(size) of a hashed power-of-two level (bits 24-28; 0: slow path), level (bits 29-31 + cz word)
+    uint32_t lvl_word;
+    {
+        const LevelP& q = lps[lvl];
+        const uint32_t lg = (q.use_hash && q.pow2mask && q.offset < (1u << 24)) ? (uint32_t)__popc(q.pow2mask) : 0u;
+        lvl_word = (lg ? q.offset : 0u) | (lg << 24);
+    }
     const float scale = lps[lvl].scale;
     const float rmax = (float)(lps[lvl].resolution - 1);
+    const uint32_t hash_style = style * prime_of(3);
     uint32_t* wbuf = wbuf_all + (threadIdx.x >> 5) * PERWARP;
     float4* ring = reinterpret_cast<float4*>(wbuf + 2 * STAGE);
     const size_t chunk = ((size_t)blockIdx.x * WALK_WARPS + (threadIdx.x >> 5)) * 2 + hf;
@@ -1068,20 +1072,21 @@ k_grid_bwd_walkq(const T* __restrict__ grad0, const T* __restrict__ grad1, const
             if (e < qcount) {
                 int slot = qhead + e; if (slot >= WALKQ_SLOTS) slot -= WALKQ_SLOTS;
                 const float4* qs = ring + slot * (WALKQ_WORDS / 4);
-                const uint4 cc = *reinterpret_cast<const uint4*>(qs + 8);
+                const uint4 cc = *reinterpret_cast<const uint4*>(qs + 8);        // {cx, cy, cz | level << 16, offset | log2(size) << 24}
                 const float4 v = qs[k];
-                const uint4 rec = lrec[cc.w];
-                uint32_t row;
-                if (rec.w) {                        // every level of the model's grids but the coarsest five
-                    row = ((cc.x + (k & 1)) ^ ((cc.y + ((k >> 1) & 1)) * 2654435761u) ^ ((cc.z + (k >> 2)) * 805459861u) ^ rec.z) & rec.y;
+                const uint32_t ccx = cc.x + (k & 1), ccy = cc.y + ((k >> 1) & 1), ccz = (cc.z & 0xffffu) + (k >> 2);
+                const uint32_t lg = cc.w >> 24;
+                uint32_t row, off = cc.w & 0xffffffu;
+                if (lg) {                           // every level of the model's grids but the coarsest five
+                    row = (ccx ^ (ccy * 2654435761u) ^ (ccz * 805459861u) ^ hash_style) & ((1u << lg) - 1u);
                 } else {
-                    const LevelP& q = lps[cc.w];
+                    const LevelP& q = lps[cc.z >> 16];
                     uint32_t idx;
-                    if (q.use_hash) idx = (cc.x + (k & 1)) ^ ((cc.y + ((k >> 1) & 1)) * 2654435761u) ^ ((cc.z + (k >> 2)) * 805459861u) ^ q.hash_style;
-                    else idx = (cc.x + (k & 1)) * q.stride[0] + (cc.y + ((k >> 1) & 1)) * q.stride[1] + (cc.z + (k >> 2)) * q.stride[2] + q.style_term;
-                    row = mod_size(q, idx);
+                    if (q.use_hash) idx = ccx ^ (ccy * 2654435761u) ^ (ccz * 805459861u) ^ q.hash_style;
+                    else idx = ccx * q.stride[0] + ccy * q.stride[1] + ccz * q.stride[2] + q.style_term;
+                    row = mod_size(q, idx); off = q.offset;
                 }
-                atomicAdd(grad_pair + rec.x + row, v);        // RED.ADD.F32x4
+                atomicAdd(grad_pair + off + row, v);          // RED.ADD.F32x4
             }
             const int n = min(qcount, 4);
             qhead += n; if (qhead >= WALKQ_SLOTS) qhead -= WALKQ_SLOTS;
@@ -1098,7 +1103,7 @@ k_grid_bwd_walkq(const T* __restrict__ grad0, const T* __restrict__ grad1, const
             float4* qs = ring + slot * (WALKQ_WORDS / 4);
 #pragma unroll
             for (int k = 0; k < 8; k++) qs[k] = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
-            *reinterpret_cast<uint4*>(qs + 8) = make_uint4(pcx, pcy, pcz, (uint32_t)lvl);
+            *reinterpret_cast<uint4*>(qs + 8) = make_uint4(pcx, pcy, pcz | ((uint32_t)lvl << 16), lvl_word);
 #pragma unroll
             for (int k = 0; k < 8; k++) { acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.0f; }
         }
@@ -1140,6 +1145,7 @@ k_grid_bwd_walkq(const T* __restrict__ grad0, const T* __restrict__ grad1, const
             // (Measured and rejected: letting the finest levels, which change cell at nearly every sample, reduce straight from
             //  their registers instead of parking -- 8 reductions issued with 2-8 active lanes cost more than the trip through
             //  shared memory: 1.05 ms instead of 0.945 for levels >= 13.)
+            // (also measured: draining before parking, so a step never waits for its own shared-memory stores -- 0.934 ms, no gain)
             park(change && have);
             drain(false);
             if (change) { pcx = cx; pcy = cy; pcz = cz; have = true; }
@@ -1210,8 +1216,10 @@ NRF_EXPORT int nrf_grid_encode_backward_pair(const void* grad0, const void* grad
         attr_set = true;
     }
     const int tr_min = g_bwd_agg > 0 ? g_bwd_tr_min : (1 << 30);
-    if (g_bwd_walk > 0 && L == 16 && (dtype == NRF_DTYPE_F16 || dtype == NRF_DTYPE_F32) &&
-        ((((uintptr_t)grad0) | ((uintptr_t)grad1)) & 15) == 0) {
+    // the walk kernels: 16 levels (a half-warp per chunk), 16-byte aligned gradient rows, cell coordinates below 2^16
+    const bool walk_ok = L == 16 && ((((uintptr_t)grad0) | ((uintptr_t)grad1)) & 15) == 0 &&
+                         floorf(exp2f(15.0f * S) * (float)H) < 65535.0f;
+    if (g_bwd_walk > 0 && walk_ok && (dtype == NRF_DTYPE_F16 || dtype == NRF_DTYPE_F32)) {
         if (dtype == NRF_DTYPE_F16) launch_bwd_walk<__half>(g_bwd_walk, grad0, grad1, inputs, offsets, grad_pair, B, S, H, gridtype, ac, style, xform, s);
         else launch_bwd_walk<float>(g_bwd_walk, grad0, grad1, inputs, offsets, grad_pair, B, S, H, gridtype, ac, style, xform, s);
         return nrf_check_launch();
