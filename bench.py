@@ -370,9 +370,11 @@ def run_ours(args):
                     'hbm_frac_actual': (round((traffic.get(top) or {}).get('dram_bytes_per_launch') / sec_per_launch / 1e9 / hbm_peak, 4)
                                         if (traffic.get(top) or {}).get('dram_bytes_per_launch') else None),
                     'binding_counter': (traffic.get(top) or {}).get('binding_counter'),
-                    'note': 'algorithmic bytes count every table row touched; both tables (and most of their f32 gradients) stay '
-                            'L2-resident, so real DRAM traffic (`traffic`) is far lower and frac can exceed 1 -- ncu shows the '
-                            'scatter bound by the LSU data pipe (warp shuffles + reductions), profiles/r01f_ncu_kernels.md'}
+                    'note': 'algorithmic bytes (SURVEY 8d) charge a read-modify-write of every table row a point touches; the walk-form '
+                            'scatter sums consecutive samples of a ray in registers and touches a row once per cell visit, and both '
+                            'gradient tables stay L2-resident, so real DRAM traffic (`traffic`) is far lower and frac exceeds 1 -- ncu '
+                            'shows the kernel bound by the LSU data pipe and the L1->crossbar request rate of its reductions, '
+                            'profiles/r02c_ncu_kernels.md'}
     line = {
         'metric': 'train_rays_per_s', 'value': round(value, 1), 'unit': 'rays/s', 'n_gpus': world, 'steps': K, 'warmup': W,
         'ms_per_step': round(ms_total / K, 4), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,

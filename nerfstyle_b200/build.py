@@ -17,6 +17,7 @@ NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 SOURCES = ['raymarching.cu', 'gridencoder.cu', 'mlp.cu', 'mlp_tc.cu', 'mlp_f32.cu', 'field_tc.cu', 'nnfm.cu', 'nnfm_tc.cu', 'optim.cu', 'optim_p2p.cu', 'rays.cu', 'occupancy.cu', 'loss.cu']
 FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
          '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr']
+FLAGS += os.environ.get('NRF_EXTRA_NVCC_FLAGS', '').split()      # experiments (e.g. -DNRF_MBAR_HINT_NS=256)
 
 
 def _stale(target, deps):
