@@ -691,12 +691,19 @@ __global__ void k_grid_input_bwd(const T* __restrict__ grad, const T* __restrict
 }
 
 template <typename T, typename TO>
+static bool launch_bwd_walk_single(const void* grad, const float* inputs, const int32_t* offsets, void* grad_table, uint32_t B, uint32_t L, float S,
+                                   uint32_t H, uint32_t gridtype, bool ac, uint32_t style, cudaStream_t s);
+
+template <typename T, typename TO>
 static int launch_bwd(const void* grad, const float* inputs, const int32_t* offsets, void* grad_embeddings, uint32_t B,
                       uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, bool calc, const void* dy_dx, void* grad_inputs,
                       uint32_t gridtype, bool ac, uint32_t style, bool pm, cudaStream_t s) {
     const T* g = (const T*)grad; TO* ge = (TO*)grad_embeddings;
     const uint32_t nbx = ceil_div_u32(B, GRID_BLOCK);
-    if (D == 3 && C == 2 && (((uintptr_t)grad_embeddings) & 7) == 0) {
+    if (D == 3 && C == 2 && pm && g_bwd_lpt >= 16 && g_bwd_agg > 0 && (((uintptr_t)grad_embeddings) & 7) == 0 &&
+        launch_bwd_walk_single<T, TO>(grad, inputs, offsets, grad_embeddings, B, L, S, H, gridtype, ac, style, s)) {
+        // the walk form (below) took it
+    } else if (D == 3 && C == 2 && (((uintptr_t)grad_embeddings) & 7) == 0) {
         const int lpt = g_bwd_lpt;
 #define BWD_FAST(LPT) k_grid_bwd_d3c2<T, TO, LPT, 1><<<dim3(nbx, ceil_div_u32(L, LPT)), GRID_BLOCK, 0, s>>>(g, nullptr, inputs, offsets, ge, nullptr, B, L, S, H, gridtype, ac, style, pm, g_bwd_agg, nullptr, 1 << 30)
         if (lpt >= 16) BWD_FAST(16); else if (lpt >= 8) BWD_FAST(8); else if (lpt >= 4) BWD_FAST(4); else if (lpt >= 2) BWD_FAST(2); else BWD_FAST(1);
@@ -777,6 +784,10 @@ NRF_EXPORT int nrf_grid_encode_forward_dual_dev(const float* inputs, const void*
     return NRF_E_UNSUPPORTED;
 }
 
+// two separate f32 gradient tables through the walk form: one single-table walk per live table (defined with the walk kernels below)
+static bool launch_bwd_walk_dual(int dtype, const void* grad0, const void* grad1, const float* inputs, const int32_t* offsets, void* ge0, void* ge1,
+                                 uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool ac, uint32_t style, const float* xform, cudaStream_t s);
+
 NRF_EXPORT int nrf_grid_encode_backward_dual(const void* grad0, const void* grad1, const float* inputs, const int32_t* offsets,
                                              void* grad_embeddings0, void* grad_embeddings1, uint32_t B, uint32_t L, float S, uint32_t H,
                                              uint32_t gridtype, int align_corners, uint32_t style, int dtype, int grad_table_dtype,
@@ -790,6 +801,9 @@ NRF_EXPORT int nrf_grid_encode_backward_dual(const void* grad0, const void* grad
     cudaStream_t s = (cudaStream_t)stream;
     const bool ac = align_corners != 0;
     const uint32_t nbx = ceil_div_u32(B, GRID_BLOCK);
+    if (grad_table_dtype == NRF_DTYPE_F32 && g_bwd_agg > 0 &&
+        launch_bwd_walk_dual(dtype, grad0, grad1, inputs, offsets, grad_embeddings0, grad_embeddings1, B, L, S, H, gridtype, ac, style, xform, s))
+        return nrf_check_launch();
     if (dtype == NRF_DTYPE_F16 && grad_table_dtype == NRF_DTYPE_F32)
         k_grid_bwd_d3c2<__half, float, 16, 2><<<dim3(nbx, ceil_div_u32(L, 16)), GRID_BLOCK, 0, s>>>(
             (const __half*)grad0, (const __half*)grad1, inputs, offsets, (float*)grad_embeddings0, (float*)grad_embeddings1, B, L, S, H,
@@ -992,22 +1006,29 @@ k_grid_bwd_walk(const T* __restrict__ grad0, const T* __restrict__ grad1, const 
 // memory; whenever the ring holds four cells the warp drains them with all 32 lanes busy: lane t takes corner t % 8 of
 // parked cell t / 8 -- one 16-byte shared load, one hash, one 16-byte reduction.
 #define WALKQ_SLOTS 40     // >= 3 left over + 32 parked in one step
-#define WALKQ_WORDS 36     // 32 sums + (cx, cy, cz | level << 16, the level's offset and size)
 static int g_bwd_walk_queue = 1;
 NRF_EXPORT void nrf_grid_set_bwd_walk_queue(int on) { g_bwd_walk_queue = on; }
 
-template <typename T, int CH>
-__global__ void __launch_bounds__(WALK_WARPS * 32, sizeof(T) == 2 ? 2 : 1)
+// NE = 2: both tables, interleaved f32 gradient rows [row][table][2] (TO = float).  NE = 1: one table (grad0), gradient rows
+// of two TO (float: one 8-byte reduction per corner; __half: the reference's __half2 atomics, gridencoder.cu:313-319).
+__device__ __forceinline__ void walk_red(float* base, uint32_t row, float a, float b) { atomicAdd(reinterpret_cast<float2*>(base) + row, make_float2(a, b)); }
+__device__ __forceinline__ void walk_red(__half* base, uint32_t row, float a, float b) { atomicAdd(reinterpret_cast<__half2*>(base) + row, __floats2half2_rn(a, b)); }
+
+template <typename T, typename TO, int NE, int CH>
+__global__ void __launch_bounds__(WALK_WARPS * 32, 2)
 k_grid_bwd_walkq(const T* __restrict__ grad0, const T* __restrict__ grad1, const float* __restrict__ inputs,
-                 const int32_t* __restrict__ offsets, float4* __restrict__ grad_pair, uint32_t B, float S, uint32_t H,
+                 const int32_t* __restrict__ offsets, TO* __restrict__ grad_table, uint32_t B, float S, uint32_t H,
                  uint32_t gridtype, bool align_corners, uint32_t style, const float* __restrict__ xform) {
     typedef typename Vec2<T>::type V2;
+    static_assert(NE == 1 || sizeof(TO) == 4, "the interleaved pair buffer is f32");
+    constexpr int NA = 2 * NE;                    // sums per corner
+    constexpr int QW = 8 * NA + 4;                // words of a parked cell: the sums + (cx, cy, cz | level << 16, the level's offset and size)
     static_assert(CH % 16 == 0, "chunks are walked in groups of 16 samples");
     constexpr int WPL = (int)sizeof(V2) / 4;      // 32-bit words per level of one sample's gradient row
     constexpr int WR = 16 * WPL;                  // words per gradient row (16 levels)
     constexpr int CPR = WR / 4;                   // 16-byte pieces per row
-    constexpr int STAGE = 2 * 16 * 2 * WR;        // words per stage of one warp: [encoder][step][half][level]
-    constexpr int PERWARP = 2 * STAGE + WALKQ_SLOTS * WALKQ_WORDS;
+    constexpr int STAGE = NE * 16 * 2 * WR;       // words per stage of one warp: [encoder][step][half][level]
+    constexpr int PERWARP = 2 * STAGE + WALKQ_SLOTS * QW;
     extern __shared__ __align__(16) uint32_t wbuf_all[];
     __shared__ LevelP lps[16];
     if (threadIdx.x < 16) level_setup(lps[threadIdx.x], offsets, threadIdx.x, 3, S, H, gridtype, align_corners, style);
@@ -1033,7 +1054,7 @@ k_grid_bwd_walkq(const T* __restrict__ grad0, const T* __restrict__ grad1, const
     auto stage_grads = [&](int g, int buf) {
         uint32_t* dst = wbuf + buf * STAGE;
 #pragma unroll
-        for (int e = 0; e < 2; e++) {
+        for (int e = 0; e < NE; e++) {
             const uint32_t* src = reinterpret_cast<const uint32_t*>(e == 0 ? grad0 : grad1) + (b0 + (size_t)g * 16) * WR;
 #pragma unroll
             for (int i = 0; i < CPR; i++) {
@@ -1057,9 +1078,12 @@ k_grid_bwd_walkq(const T* __restrict__ grad0, const T* __restrict__ grad1, const
         }
     };
 
-    float acc[8][4];
+    float acc[8][NA];
 #pragma unroll
-    for (int k = 0; k < 8; k++) { acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.0f; }
+    for (int k = 0; k < 8; k++) {
+#pragma unroll
+        for (int c = 0; c < NA; c++) acc[k][c] = 0.0f;
+    }
     uint32_t pcx = 0, pcy = 0, pcz = 0;
     bool have = false;
     int qhead = 0, qcount = 0;                     // warp-uniform ring state
@@ -1071,9 +1095,11 @@ k_grid_bwd_walkq(const T* __restrict__ grad0, const T* __restrict__ grad1, const
             const int e = lane >> 3, k = lane & 7;
             if (e < qcount) {
                 int slot = qhead + e; if (slot >= WALKQ_SLOTS) slot -= WALKQ_SLOTS;
-                const float4* qs = ring + slot * (WALKQ_WORDS / 4);
-                const uint4 cc = *reinterpret_cast<const uint4*>(qs + 8);        // {cx, cy, cz | level << 16, offset | log2(size) << 24}
-                const float4 v = qs[k];
+                const float4* qs = ring + slot * (QW / 4);
+                const uint4 cc = *reinterpret_cast<const uint4*>(qs + 2 * NA);   // {cx, cy, cz | level << 16, offset | log2(size) << 24}
+                float v[NA];
+                if constexpr (NE == 2) { const float4 t = qs[k]; v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+                else { const float2 t = reinterpret_cast<const float2*>(qs)[k]; v[0] = t.x; v[1] = t.y; }
                 const uint32_t ccx = cc.x + (k & 1), ccy = cc.y + ((k >> 1) & 1), ccz = (cc.z & 0xffffu) + (k >> 2);
                 const uint32_t lg = cc.w >> 24;
                 uint32_t row, off = cc.w & 0xffffffu;
@@ -1086,7 +1112,8 @@ k_grid_bwd_walkq(const T* __restrict__ grad0, const T* __restrict__ grad1, const
                     else idx = ccx * q.stride[0] + ccy * q.stride[1] + ccz * q.stride[2] + q.style_term;
                     row = mod_size(q, idx); off = q.offset;
                 }
-                atomicAdd(grad_pair + off + row, v);          // RED.ADD.F32x4
+                if constexpr (NE == 2) atomicAdd(reinterpret_cast<float4*>(grad_table) + off + row, make_float4(v[0], v[1], v[2], v[3]));   // RED.ADD.F32x4
+                else walk_red(grad_table + (size_t)off * 2, row, v[0], v[1]);
             }
             const int n = min(qcount, 4);
             qhead += n; if (qhead >= WALKQ_SLOTS) qhead -= WALKQ_SLOTS;
@@ -1100,12 +1127,20 @@ k_grid_bwd_walkq(const T* __restrict__ grad0, const T* __restrict__ grad1, const
         if (mine) {
             int slot = qhead + qcount + __popc(fm & ((1u << lane) - 1u));
             if (slot >= WALKQ_SLOTS) slot -= WALKQ_SLOTS;
-            float4* qs = ring + slot * (WALKQ_WORDS / 4);
+            float4* qs = ring + slot * (QW / 4);
+            if constexpr (NE == 2) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) qs[k] = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
-            *reinterpret_cast<uint4*>(qs + 8) = make_uint4(pcx, pcy, pcz | ((uint32_t)lvl << 16), lvl_word);
+                for (int k = 0; k < 8; k++) qs[k] = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+            } else {
 #pragma unroll
-            for (int k = 0; k < 8; k++) { acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.0f; }
+                for (int k = 0; k < 8; k += 2) qs[k / 2] = make_float4(acc[k][0], acc[k][1], acc[k + 1][0], acc[k + 1][1]);
+            }
+            *reinterpret_cast<uint4*>(qs + 2 * NA) = make_uint4(pcx, pcy, pcz | ((uint32_t)lvl << 16), lvl_word);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+#pragma unroll
+                for (int c = 0; c < NA; c++) acc[k][c] = 0.0f;
+            }
         }
         qcount += __popc(fm);
         __syncwarp();
@@ -1129,14 +1164,14 @@ k_grid_bwd_walkq(const T* __restrict__ grad0, const T* __restrict__ grad1, const
 #pragma unroll 2
         for (int s = 0; s < 16; s++) {
             const V2 c0 = *reinterpret_cast<const V2*>(rb + (s * 2) * WR);
-            const V2 c1 = *reinterpret_cast<const V2*>(rb + ((16 + s) * 2) * WR);
+            const V2 c1 = NE == 2 ? *reinterpret_cast<const V2*>(rb + ((16 * (NE - 1) + s) * 2) * WR) : c0;
             const float x = __shfl_sync(NRF_FULL_MASK, px, hb + s);
             const float y = __shfl_sync(NRF_FULL_MASK, py, hb + s);
             const float z = __shfl_sync(NRF_FULL_MASK, pz, hb + s);
             float gq[4];
             walk_grads(c0, c1, gq);
             // exact zeros add nothing (samples behind an early-terminated ray): they neither open nor extend a cell
-            const bool contrib = x >= 0.0f && (gq[0] != 0.0f || gq[1] != 0.0f || gq[2] != 0.0f || gq[3] != 0.0f);
+            const bool contrib = x >= 0.0f && (gq[0] != 0.0f || gq[1] != 0.0f || (NE == 2 && (gq[2] != 0.0f || gq[3] != 0.0f)));
             // locate1, with the level's constants in registers
             const float posx = __fmaf_rn(x, scale, align_corners ? 0.0f : 0.5f), posy = __fmaf_rn(y, scale, align_corners ? 0.0f : 0.5f),
                         posz = __fmaf_rn(z, scale, align_corners ? 0.0f : 0.5f);
@@ -1155,7 +1190,7 @@ k_grid_bwd_walkq(const T* __restrict__ grad0, const T* __restrict__ grad1, const
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
 #pragma unroll
-                    for (int c = 0; c < 4; c++) acc[k][c] = __fmaf_rn(w[k], gq[c], acc[k][c]);
+                    for (int c = 0; c < NA; c++) acc[k][c] = __fmaf_rn(w[k], gq[c], acc[k][c]);
                 }
             }
         }
@@ -1165,38 +1200,86 @@ k_grid_bwd_walkq(const T* __restrict__ grad0, const T* __restrict__ grad1, const
     drain(true);
 }
 
+template <typename T, typename TO, int NE>
+static void launch_walkq(uint32_t CH, const void* grad0, const void* grad1, const float* inputs, const int32_t* offsets, void* grad_table,
+                         uint32_t B, float S, uint32_t H, uint32_t gridtype, bool ac, uint32_t style, const float* xform, cudaStream_t s) {
+    const uint32_t blocks = ceil_div_u32(ceil_div_u32(ceil_div_u32(B, CH), 2), WALK_WARPS);
+    constexpr int SMEMQ = WALK_WARPS * 4 * (2 * (NE * 16 * 2 * 16 * ((int)sizeof(typename Vec2<T>::type) / 4)) + WALKQ_SLOTS * (8 * 2 * NE + 4));
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_grid_bwd_walkq<T, TO, NE, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEMQ);
+        cudaFuncSetAttribute(k_grid_bwd_walkq<T, TO, NE, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEMQ);
+        cudaFuncSetAttribute(k_grid_bwd_walkq<T, TO, NE, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEMQ);
+        cudaFuncSetAttribute(k_grid_bwd_walkq<T, TO, NE, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEMQ);
+        attr_set = true;
+    }
+#define WALKQ(N) k_grid_bwd_walkq<T, TO, NE, N><<<blocks, WALK_WARPS * 32, SMEMQ, s>>>((const T*)grad0, (const T*)grad1, inputs, offsets, (TO*)grad_table, B, S, H, gridtype, ac, style, xform)
+    if (CH == 256) WALKQ(256); else if (CH == 128) WALKQ(128); else if (CH == 64) WALKQ(64); else WALKQ(32);
+#undef WALKQ
+}
+
+static uint32_t walk_chunk(int ch) { return ch >= 256 ? 256u : (ch >= 128 ? 128u : (ch >= 64 ? 64u : (ch >= 32 ? 32u : 16u))); }
+
+// the walk kernels need: 16 levels (a half-warp per chunk), 16-byte aligned point-major gradient rows, cell coordinates < 2^16
+static bool walk_applicable(uint32_t L, float S, uint32_t H, const void* g0, const void* g1) {
+    return g_bwd_walk > 0 && L == 16 && ((((uintptr_t)g0) | ((uintptr_t)g1)) & 15) == 0 && floorf(exp2f(15.0f * S) * (float)H) < 65535.0f;
+}
+
 template <typename T>
 static void launch_bwd_walk(int ch, const void* grad0, const void* grad1, const float* inputs, const int32_t* offsets, float* grad_pair,
                             uint32_t B, float S, uint32_t H, uint32_t gridtype, bool ac, uint32_t style, const float* xform,
                             cudaStream_t s) {
-    const uint32_t CH = ch >= 256 ? 256u : (ch >= 128 ? 128u : (ch >= 64 ? 64u : (ch >= 32 ? 32u : 16u)));
-    const uint32_t chunks = ceil_div_u32(B, CH);
-    const uint32_t blocks = ceil_div_u32(ceil_div_u32(chunks, 2), WALK_WARPS);
+    const uint32_t CH = walk_chunk(ch);
+    if constexpr (sizeof(T) == 2) {      // (f32 gradient rows -- parity mode: the ring would leave one block per SM)
+        if (g_bwd_walk_queue && CH >= 32) {
+            launch_walkq<T, float, 2>(CH, grad0, grad1, inputs, offsets, grad_pair, B, S, H, gridtype, ac, style, xform, s);
+            return;
+        }
+    }
+    const uint32_t blocks = ceil_div_u32(ceil_div_u32(ceil_div_u32(B, CH), 2), WALK_WARPS);
     constexpr int STAGES = WALK_WARPS * 2 * (2 * 16 * 2 * 16 * (int)sizeof(typename Vec2<T>::type));   // two stages per warp
-    constexpr int SMEMQ = STAGES + WALK_WARPS * WALKQ_SLOTS * WALKQ_WORDS * 4;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_grid_bwd_walk<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGES);
         cudaFuncSetAttribute(k_grid_bwd_walk<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGES);
         cudaFuncSetAttribute(k_grid_bwd_walk<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGES);
-        cudaFuncSetAttribute(k_grid_bwd_walkq<T, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEMQ);
-        cudaFuncSetAttribute(k_grid_bwd_walkq<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEMQ);
-        cudaFuncSetAttribute(k_grid_bwd_walkq<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEMQ);
-        cudaFuncSetAttribute(k_grid_bwd_walkq<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEMQ);
         attr_set = true;
     }
 #define WALK_ARGS (const T*)grad0, (const T*)grad1, inputs, offsets, reinterpret_cast<float4*>(grad_pair), B, S, H, gridtype, ac, style, xform
-    if (g_bwd_walk_queue && CH >= 32 && sizeof(T) == 2) {      // f32 gradient rows (parity mode): the ring would leave one block per SM
-        if (CH == 256) k_grid_bwd_walkq<T, 256><<<blocks, WALK_WARPS * 32, SMEMQ, s>>>(WALK_ARGS);
-        else if (CH == 128) k_grid_bwd_walkq<T, 128><<<blocks, WALK_WARPS * 32, SMEMQ, s>>>(WALK_ARGS);
-        else if (CH == 64) k_grid_bwd_walkq<T, 64><<<blocks, WALK_WARPS * 32, SMEMQ, s>>>(WALK_ARGS);
-        else k_grid_bwd_walkq<T, 32><<<blocks, WALK_WARPS * 32, SMEMQ, s>>>(WALK_ARGS);
-    } else {
-        if (CH >= 64) k_grid_bwd_walk<T, 64><<<ceil_div_u32(ceil_div_u32(ceil_div_u32(B, 64), 2), WALK_WARPS), WALK_WARPS * 32, STAGES, s>>>(WALK_ARGS);
-        else if (CH == 32) k_grid_bwd_walk<T, 32><<<blocks, WALK_WARPS * 32, STAGES, s>>>(WALK_ARGS);
-        else k_grid_bwd_walk<T, 16><<<blocks, WALK_WARPS * 32, STAGES, s>>>(WALK_ARGS);
-    }
+    if (CH >= 64) k_grid_bwd_walk<T, 64><<<ceil_div_u32(ceil_div_u32(ceil_div_u32(B, 64), 2), WALK_WARPS), WALK_WARPS * 32, STAGES, s>>>(WALK_ARGS);
+    else if (CH == 32) k_grid_bwd_walk<T, 32><<<blocks, WALK_WARPS * 32, STAGES, s>>>(WALK_ARGS);
+    else k_grid_bwd_walk<T, 16><<<blocks, WALK_WARPS * 32, STAGES, s>>>(WALK_ARGS);
 #undef WALK_ARGS
+}
+
+// single table (the reference-facing GridEncoder, gridencoder/grid.py:71-97): same walk, one 8-byte (f32) / 4-byte (f16) reduction per corner
+template <typename T, typename TO>
+static bool launch_bwd_walk_single(const void* grad, const float* inputs, const int32_t* offsets, void* grad_table, uint32_t B, uint32_t L, float S,
+                                   uint32_t H, uint32_t gridtype, bool ac, uint32_t style, cudaStream_t s) {
+    // f16 gradient tables keep the thread-per-sample kernel: that mode exists to reproduce the reference's per-sample __half2 atomics
+    if constexpr (sizeof(TO) == 4) {
+        if (!g_bwd_walk_queue || !walk_applicable(L, S, H, grad, grad) || walk_chunk(g_bwd_walk) < 32) return false;
+        launch_walkq<T, TO, 1>(walk_chunk(g_bwd_walk), grad, nullptr, inputs, offsets, grad_table, B, S, H, gridtype, ac, style, nullptr, s);
+        return true;
+    } else {
+        return false;
+    }
+}
+
+static bool launch_bwd_walk_dual(int dtype, const void* grad0, const void* grad1, const float* inputs, const int32_t* offsets, void* ge0, void* ge1,
+                                 uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool ac, uint32_t style, const float* xform, cudaStream_t s) {
+    const void* any = grad0 ? grad0 : grad1;
+    if (!g_bwd_walk_queue || walk_chunk(g_bwd_walk) < 32 || !walk_applicable(L, S, H, grad0 ? grad0 : any, grad1 ? grad1 : any)) return false;
+    if (dtype != NRF_DTYPE_F16 && dtype != NRF_DTYPE_F32) return false;
+    const uint32_t CH = walk_chunk(g_bwd_walk);
+    for (int e = 0; e < 2; e++) {
+        const void* g = e == 0 ? grad0 : grad1;
+        void* ge = e == 0 ? ge0 : ge1;
+        if (!g) continue;                  // frozen table
+        if (dtype == NRF_DTYPE_F16) launch_walkq<__half, float, 1>(CH, g, nullptr, inputs, offsets, ge, B, S, H, gridtype, ac, style, xform, s);
+        else launch_walkq<float, float, 1>(CH, g, nullptr, inputs, offsets, ge, B, S, H, gridtype, ac, style, xform, s);
+    }
+    return true;
 }
 
 NRF_EXPORT int nrf_grid_encode_backward_pair(const void* grad0, const void* grad1, const float* inputs, const int32_t* offsets,
@@ -1216,10 +1299,8 @@ NRF_EXPORT int nrf_grid_encode_backward_pair(const void* grad0, const void* grad
         attr_set = true;
     }
     const int tr_min = g_bwd_agg > 0 ? g_bwd_tr_min : (1 << 30);
-    // the walk kernels: 16 levels (a half-warp per chunk), 16-byte aligned gradient rows, cell coordinates below 2^16
-    const bool walk_ok = L == 16 && ((((uintptr_t)grad0) | ((uintptr_t)grad1)) & 15) == 0 &&
-                         floorf(exp2f(15.0f * S) * (float)H) < 65535.0f;
-    if (g_bwd_walk > 0 && walk_ok && (dtype == NRF_DTYPE_F16 || dtype == NRF_DTYPE_F32)) {
+    const bool walk_ok = walk_applicable(L, S, H, grad0, grad1);
+    if (walk_ok && (dtype == NRF_DTYPE_F16 || dtype == NRF_DTYPE_F32)) {
         if (dtype == NRF_DTYPE_F16) launch_bwd_walk<__half>(g_bwd_walk, grad0, grad1, inputs, offsets, grad_pair, B, S, H, gridtype, ac, style, xform, s);
         else launch_bwd_walk<float>(g_bwd_walk, grad0, grad1, inputs, offsets, grad_pair, B, S, H, gridtype, ac, style, xform, s);
         return nrf_check_launch();

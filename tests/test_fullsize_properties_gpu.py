@@ -138,6 +138,48 @@ def test_grid_encoder_linearity_and_adjointness_at_full_size(cuda_lib, dev):
     assert 0 < int(touched.sum()) < T.shape[0]
 
 
+@pytest.mark.parametrize('half_grads', [True, False])
+def test_paired_walk_scatter_is_the_adjoint_of_the_paired_gather_at_full_size(cuda_lib, dev, half_grads):
+    """4.2 M ray-ordered samples (8192 rays x 512 march steps: the cell runs the walk kernels aggregate): the paired
+    scatter -- ring form for f16 gradient rows, register-flush form for f32 rows -- is the adjoint of the paired f32 gather,
+    <enc(x; T0, T1), (G0, G1)> = <(T0, T1), grad_pair>, and agrees with the thread-per-sample kernel."""
+    from nerfstyle_b200.model import get_grid_encoder
+    enc = get_grid_encoder(max_bound=4.0).to(dev)
+    g = torch.Generator().manual_seed(11)
+    n_rays, n_steps = 8192, 512
+    o = (torch.rand(n_rays, 1, 3, generator=g) * 0.3 + 0.5).to(dev)
+    d = torch.nn.functional.normalize(torch.rand(n_rays, 1, 3, generator=g) + 0.05, dim=-1).to(dev)
+    t = (torch.arange(n_steps, device=dev, dtype=torch.float32) * 4.2e-4)[None, :, None]
+    x = (o + d * t).reshape(-1, 3).contiguous()                                  # a few rays leave [0, 1]^3: those rows contribute nothing
+    B_ = x.shape[0]
+    T_ = enc.embeddings.shape[0]
+    pair = torch.randn(T_, 2, 2, generator=g).to(dev)                             # [row][table][2] f32
+    S = float(np.float32(np.log2(enc.per_level_scale)))
+    st = torch.cuda.current_stream().cuda_stream
+    o0, o1 = torch.empty(B_, 32, device=dev), torch.empty(B_, 32, device=dev)
+    assert cuda_lib.nrf_grid_encode_forward_pair(x.data_ptr(), pair.data_ptr(), enc.offsets.data_ptr(), o0.data_ptr(), o1.data_ptr(),
+                                                 B_, 16, S, 16, 0, 1, 0, 0, None, None, None, st) == 0
+    dt = torch.float16 if half_grads else torch.float32
+    G0 = torch.randn(B_, 32, device=dev).to(dt)
+    G1 = torch.randn(B_, 32, device=dev).to(dt)
+    lhs = float((o0.double() * G0.double()).sum() + (o1.double() * G1.double()).sum())
+    out = {}
+    try:
+        for walk in (128, 0):
+            cuda_lib.nrf_grid_set_bwd_walk(walk)
+            gp = torch.zeros(T_, 2, 2, device=dev)
+            assert cuda_lib.nrf_grid_encode_backward_pair(G0.data_ptr(), G1.data_ptr(), x.data_ptr(), enc.offsets.data_ptr(), gp.data_ptr(),
+                                                          B_, 16, S, 16, 0, 1, 0, 1 if half_grads else 0, None, st) == 0
+            torch.cuda.synchronize()
+            out[walk] = gp
+    finally:
+        cuda_lib.nrf_grid_set_bwd_walk(128)
+    rhs = float((pair.double() * out[128].double()).sum())
+    assert abs(lhs - rhs) <= 1e-5 * abs(lhs), (lhs, rhs)
+    assert float((out[128] - out[0]).abs().max()) <= 2e-5 * float(out[0].abs().max())
+    assert torch.isfinite(out[128]).all() and 0 < int((out[128] != 0).any(dim=2).any(dim=1).sum()) < T_
+
+
 def test_morton_and_packbits_over_the_whole_grid(cuda_lib, dev):
     from nerfstyle_b200 import raymarching
     idx = torch.arange(H ** 3, dtype=torch.int32, device=dev)

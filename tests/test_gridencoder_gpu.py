@@ -318,3 +318,37 @@ def test_pair_backward_walk(cuda_lib, oracle, dev, B, half):
         cuda_lib.nrf_grid_set_bwd_walk(128)
         cuda_lib.nrf_grid_set_bwd_walk_queue(1)
     assert float((res[(64, 1)] - res[(0, 1)]).abs().max()) <= 1e-5 * float(res[(0, 1)].abs().max())
+
+
+@pytest.mark.parametrize('amp', [False, True])
+def test_single_table_backward_walk(cuda_lib, oracle, dev, amp):
+    """The reference-facing GridEncoder (one table, gridencoder/grid.py:71-97) takes the walk form of the scatter too when
+    its preconditions hold: against the CPU oracle and against the thread-per-sample kernel, ray-ordered samples with
+    exact-zero gradient rows, ragged length."""
+    enc = _default_encoder(dev)
+    B = 30011
+    g = torch.Generator().manual_seed(4)
+    nray = B // 50 + 1
+    o = (torch.rand(nray, 3, generator=g) * 1.6 - 0.8).repeat_interleave(50, dim=0)[:B]
+    d = torch.nn.functional.normalize(torch.randn(nray, 3, generator=g), dim=-1).repeat_interleave(50, dim=0)[:B]
+    x = (o + d * (torch.arange(B)[:, None] % 50) * 1.7e-3).to(dev)
+    x[9] = 2.5
+    grads = {}
+    for walk in (128, 0):
+        cuda_lib.nrf_grid_set_bwd_walk(walk)
+        try:
+            enc.embeddings.grad = None
+            with torch.autocast('cuda', dtype=torch.float16, enabled=amp):
+                out = enc(x)
+            grad = torch.randn(out.shape, generator=torch.Generator().manual_seed(5)).to(dev).to(out.dtype)
+            grad[2000:2600] = 0
+            grad[4000:4100:2] = 0
+            out.backward(grad)
+            grads[walk] = enc.embeddings.grad.clone()
+        finally:
+            cuda_lib.nrf_grid_set_bwd_walk(128)
+    assert grads[128].dtype == torch.float32
+    ege = oracle.grid_encode_backward(grad.float().cpu().numpy(), ((x + 1) / 2).cpu().numpy(), enc.offsets.cpu().numpy(),
+                                      enc.embeddings.shape[0], 2, enc.per_level_scale, 16, 0, True, 0)
+    for walk in (128, 0):
+        assert np.abs(grads[walk].cpu().numpy() - ege).max() <= 1e-5 * np.abs(ege).max(), walk

@@ -85,3 +85,8 @@ for half in (True, False):
             print('bwd half=%d  pair, walk chunks of %d, queue %d: %.3f ms   (rel err vs dual %.1e / %.1e)' % (half, ch, queue, mb.timeit(b_pair), e0, e1))
     lib.nrf_grid_set_bwd_walk(128)
     lib.nrf_grid_set_bwd_walk_queue(1)
+    ge0.zero_(); ge1.zero_(); gp.zero_()
+    assert b_dual() == 0 and b_pair() == 0
+    torch.cuda.synchronize()
+    e0 = float((gp[:, 0] - ge0).abs().max() / ge0.abs().max())
+    print('bwd half=%d  dual as two single-table walks: %.3f ms   (rel err vs pair %.1e)' % (half, mb.timeit(b_dual), e0))
