@@ -177,7 +177,10 @@ int nrf_grid_encode_forward(const float* inputs, const void* embeddings, const i
  * zero-filled by the caller (grid.py:82).  grad_table_dtype = dtype reproduces the reference (f16 grads are
  * accumulated with __half2 atomics, :313-319); f16 grads may also be accumulated into an f32 table
  * (grad_table_dtype = NRF_DTYPE_F32), which avoids the swamping of half-precision accumulation and the
- * half->float cast the autograd engine would add.  grad_inputs [B,D] (dtype) only when calc_grad_inputs. */
+ * half->float cast the autograd engine would add.  grad_inputs [B,D] (dtype) only when calc_grad_inputs.
+ * Row order never changes the result, only the speed: with f32 gradient tables, 16 levels and point-major rows the
+ * scatter (here and in the dual / paired forms below) walks chunks of consecutive rows and sums the rows that stay in one
+ * cell in registers, so samples should arrive ray by ray, as march_rays_train emits them. */
 int nrf_grid_encode_backward(const void* grad, const float* inputs, const void* embeddings, const int32_t* offsets,
                              void* grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
                              uint32_t H, int calc_grad_inputs, const void* dy_dx, void* grad_inputs,
