@@ -14,7 +14,7 @@ r.density_bitfield = raymarching.packbits(scenes.analytic_density_grid(2, 128, 2
 intr = scenes.scaled_intrinsics(1008, 756)
 pose = scenes.synthetic_poses(8, 1)[1]
 o, d = scenes.generate_rays(pose, intr, dev, torch.arange(0, 1008 * 756, device=dev))
-for spi, ce in ((4, 4), (4, 2), (4, 1), (6, 1), (8, 1), (8, 4)):
+for spi, ce in ((4, 4), (8, 4), (8, 2), (8, 1), (8, 8)):
     ts = []
     for f in range(4):
         torch.cuda.synchronize()
