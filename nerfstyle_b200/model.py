@@ -516,11 +516,12 @@ class Renderer(nn.Module):
                 'compact_alive_dev')
 
     @torch.no_grad()
-    def render_test_graph(self, rays_o, rays_d, check_every=4, steps_per_iteration=8):
+    def render_test_graph(self, rays_o, rays_d, check_every=2, steps_per_iteration=8):
         """render_test with the loop driven from the device: the per-iteration host logic of renderer.py:249-286 (alive
         count, n_step, buffer sizes) lives in a control block updated by the compaction kernel, every launch is sized for
         the cap, and a PAIR of iterations (the alive list ping-pongs between two buffers) is captured once in a CUDA graph
-        and replayed; the host only reads the alive count every `check_every` replays.  Same kernels and numerics as
+        and replayed; the host only reads the alive count every `check_every` replays (a replay = two iterations; with 8
+        steps per iteration a frame is ~4 replays, so 2 keeps the replays wasted after the last ray died to at most one).  Same kernels and numerics as
         render_test; needs the fused-head model (default) under AMP-style fp16 tables.
 
         steps_per_iteration: the reference marches n_step = clamp(N // n_alive, 1, 8) samples per ray and iteration, i.e. ONE
