@@ -164,7 +164,7 @@ k_field_fwd_tc(const __half* __restrict__ enc_d, const __half* __restrict__ enc_
 #pragma unroll
                     for (int q = 0; q < 16; q++) {
                         // the hidden activation exactly as the MMA path would see it: rounded to f16, then relu
-                        const __half2 h = __hmax2(__floats2half2_rn(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])), zero2);
+                        const __half2 h = bits2h(tpack_relu(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])));
                         const float2 hf = __half22float2(h);
                         zd = __fmaf_rn(hf.x, wod[32 * half + 2 * q], zd);
                         zd = __fmaf_rn(hf.y, wod[32 * half + 2 * q + 1], zd);
@@ -181,7 +181,7 @@ k_field_fwd_tc(const __half* __restrict__ enc_d, const __half* __restrict__ enc_
                         uint32_t p[4];
 #pragma unroll
                         for (int q = 0; q < 4; q++)
-                            p[q] = h2bits(__hmax2(__floats2half2_rn(__uint_as_float(v[8 * c + 2 * q]), __uint_as_float(v[8 * c + 2 * q + 1])), zero2));
+                            p[q] = tpack_relu(__uint_as_float(v[8 * c + 2 * q]), __uint_as_float(v[8 * c + 2 * q + 1]));
                         *reinterpret_cast<uint4*>(hrow + (4 * piece + c) * FCH) = make_uint4(p[0], p[1], p[2], p[3]);
                     }
                 }

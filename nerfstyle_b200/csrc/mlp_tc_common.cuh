@@ -38,6 +38,13 @@ __device__ __forceinline__ uint32_t tpack(float lo, float hi) {
     __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+// round two f32 to f16 and clamp negatives to zero in ONE instruction (F2FP.RELU.F16.F32.PACK_AB): relu(round(x)) ==
+// round(relu(x)), so this is the hidden activation exactly as cvt + HMNMX2 produced it
+__device__ __forceinline__ uint32_t tpack_relu(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 __device__ __forceinline__ uint32_t h2bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 __device__ __forceinline__ __half2 bits2h(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
 
@@ -239,22 +246,27 @@ __device__ __forceinline__ void stage_weight(uint8_t* dst, uint32_t ch, const __
 // relu is applied AFTER the rounding on packed halfs (rounding is monotonic and sign-preserving: same result, half the
 // instructions: one cvt.rn.f16x2.f32 + one HMNMX2 per pair of columns).
 __device__ __forceinline__ void hidden_fwd_epilogue(uint32_t tacc_lane, uint8_t* dst_row, bool relu, uint32_t CH) {
-    const __half2 zero = __float2half2_rn(0.0f);
 #pragma unroll
     for (int half = 0; half < 2; half++) {
         uint32_t v[32];
         tc05::tmem_ld32(tacc_lane + 32 * half, v);
         tc05::tmem_ld_wait();
+        if (relu) {            // warp-uniform
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            uint32_t p[4];
+            for (int c = 0; c < 4; c++) {
+                uint32_t p[4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                __half2 h = __floats2half2_rn(__uint_as_float(v[8 * c + 2 * q]), __uint_as_float(v[8 * c + 2 * q + 1]));
-                if (relu) h = __hmax2(h, zero);
-                p[q] = h2bits(h);
+                for (int q = 0; q < 4; q++) p[q] = tpack_relu(__uint_as_float(v[8 * c + 2 * q]), __uint_as_float(v[8 * c + 2 * q + 1]));
+                *reinterpret_cast<uint4*>(dst_row + (4 * half + c) * CH) = make_uint4(p[0], p[1], p[2], p[3]);
             }
-            *reinterpret_cast<uint4*>(dst_row + (4 * half + c) * CH) = make_uint4(p[0], p[1], p[2], p[3]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                uint32_t p[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) p[q] = tpack(__uint_as_float(v[8 * c + 2 * q]), __uint_as_float(v[8 * c + 2 * q + 1]));
+                *reinterpret_cast<uint4*>(dst_row + (4 * half + c) * CH) = make_uint4(p[0], p[1], p[2], p[3]);
+            }
         }
     }
 }
