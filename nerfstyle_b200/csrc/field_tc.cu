@@ -32,7 +32,7 @@ __host__ __device__ constexpr FieldSmem field_smem(int n_xbuf) {
     s.W2a = o;  o += 2 * CHW;          // color2 W1   [64 x 16]
     s.W2h = o;  o += 8 * CHW;          // color2 Wh   [64 x 64]
     s.W2o = o;  o += 8 * CHO;          // color2 Wo   [16 x 64]
-    s.wod = o;  o += 64 * 4;           // density Wo row 0 as f32
+    s.wod = o;  o += 64 * 4;           // density Wo row 0 (64 f16 in the first 128 bytes)
     s.X = o;    o += (uint32_t)n_xbuf * 8 * FCH;      // Xd (4 chunks) | Xc (4 chunks), per buffer
     s.H = o;    o += 16 * FCH;         // [Hk | Hc], later [G1 | G2]
     s.C1 = o;   o += 2 * FCH;          // color1 output, color2's input
@@ -76,7 +76,7 @@ k_field_fwd_tc(const __half* __restrict__ enc_d, const __half* __restrict__ enc_
     stage_block(smem + L.W2a, CHW, w_color2, 64, 16, 0, 0);
     stage_block(smem + L.W2h, CHW, w_color2 + 64 * 16, 64, 64, 0, 0);
     stage_block(smem + L.W2o, CHO, w_color2 + 64 * 16 + 64 * 64, 16, 64, 0, 0);
-    if (tid < 64) reinterpret_cast<float*>(smem + L.wod)[tid] = __half2float(__ldg(w_density + 64 * 32 + tid));
+    if (tid < 64) reinterpret_cast<__half*>(smem + L.wod)[tid] = __ldg(w_density + 64 * 32 + tid);
     if (warp == 0) { tc05::tmem_alloc(&tmem_slot, TCOLS); tc05::tmem_relinquish(); }
     if (tid == 0) { tc05::mbar_init(&bar_ready, TC_ROWS); tc05::mbar_init(&bar_done, 1); tc05::fence_mbar_init(); }
     publish_and_sync();
@@ -136,7 +136,7 @@ k_field_fwd_tc(const __half* __restrict__ enc_d, const __half* __restrict__ enc_
         uint32_t phase = 0;
         uint8_t* const hrow = smem + L.H + tid * 16;
         uint8_t* const c1row = smem + L.C1 + tid * 16;
-        const float* const wod = reinterpret_cast<const float*>(smem + L.wod);
+        const uint4* const wod = reinterpret_cast<const uint4*>(smem + L.wod);      // 8 x 8 f16 weights of the density output
         const __half2 zero2 = __float2half2_rn(0.0f);
         uint4 xd[4], xc[4];
         load_x_tile<4, false>(xd, enc_d, NRF_DTYPE_F16, (size_t)blockIdx.x * 128, true, B, 32, true, true, warp, lane, tid);
@@ -162,12 +162,15 @@ k_field_fwd_tc(const __half* __restrict__ enc_d, const __half* __restrict__ enc_
                     tc05::tmem_ld32(tl + T_HD + 32 * half, v);
                     tc05::tmem_ld_wait();
 #pragma unroll
-                    for (int q = 0; q < 16; q++) {
-                        // the hidden activation exactly as the MMA path would see it: rounded to f16, then relu
-                        const __half2 h = bits2h(tpack_relu(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1])));
-                        const float2 hf = __half22float2(h);
-                        zd = __fmaf_rn(hf.x, wod[32 * half + 2 * q], zd);
-                        zd = __fmaf_rn(hf.y, wod[32 * half + 2 * q + 1], zd);
+                    for (int c = 0; c < 4; c++) {
+                        const uint4 w8 = wod[4 * half + c];
+                        const uint32_t wp[4] = {w8.x, w8.y, w8.z, w8.w};
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            // the hidden activation exactly as the MMA path would see it (rounded to f16, then relu), times the
+                            // f16 weight, accumulated in f32: FHFMA, same value as cvt + FFMA
+                            zd = fhfma2(tpack_relu(__uint_as_float(v[8 * c + 2 * q]), __uint_as_float(v[8 * c + 2 * q + 1])), wp[q], zd);
+                        }
                     }
                 }
                 if (row_ok) sigmas[row] = tact_fwd(zd, NRF_ACT_TRUNC_EXP);

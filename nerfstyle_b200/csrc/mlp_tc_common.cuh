@@ -45,6 +45,14 @@ __device__ __forceinline__ uint32_t tpack_relu(float lo, float hi) {
     asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
+// c + a.lo * b.lo, then + a.hi * b.hi, for packed f16 pairs a, b: the mixed-precision FMA of sm_100 (FHFMA: f16 x f16 + f32 ->
+// f32, one rounding) -- the same value as converting both halves to f32 and using FFMA, without the conversions
+__device__ __forceinline__ float fhfma2(uint32_t a, uint32_t b, float c) {
+    float d;
+    asm("{\n\t.reg .b16 al, ah, bl, bh;\n\t.reg .f32 t;\n\tmov.b32 {al, ah}, %1;\n\tmov.b32 {bl, bh}, %2;\n\t"
+        "fma.rn.f32.f16 t, al, bl, %3;\n\tfma.rn.f32.f16 %0, ah, bh, t;\n\t}" : "=f"(d) : "r"(a), "r"(b), "f"(c));
+    return d;
+}
 __device__ __forceinline__ uint32_t h2bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 __device__ __forceinline__ __half2 bits2h(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
 
