@@ -2,8 +2,11 @@
 //
 // Behavioural contract: /root/reference/gridencoder/src/gridencoder.cu (cited per function).  Written from
 // scratch: the forward is a vectorised 8-corner gather that writes point-major [B, L*C] directly (the
-// reference writes [L,B,C] and pays a permute copy, grid.py:58), the backward is a warp-aggregated scatter
-// (lanes that fall into the same cell are reduced with shuffles before ONE vector atomic per corner).
+// reference writes [L,B,C] and pays a permute copy, grid.py:58).  The backward exists in two forms: a walk (one lane follows
+// a chunk of consecutive samples at one level and keeps the current cell's sums in registers; cells it leaves are parked in a
+// shared-memory ring and reduced by full warps -- k_grid_bwd_walkq, the default for f32 gradient tables) and the round-1
+// thread-per-sample kernel with warp aggregation (lanes that fall into the same cell are reduced with shuffles before ONE
+// vector atomic per corner -- k_grid_bwd_d3c2, the fallback and the f16-gradient-table reference mode).
 // Index arithmetic (hash, strides, modulo) is bit-exact with the reference; the float interpolation uses
 // explicit __fmaf_rn at the reference's contraction points so f32 outputs are bit-exact too.
 #include "common.cuh"
